@@ -1,0 +1,203 @@
+/*
+ * nf_b200.h -- C ABI of libnf_b200.so: B200 (sm_100a) kernels for NeuroFluid's two hot paths.
+ *
+ * The reference (syguan96/NeuroFluid) has no FFI layer of its own: its hot paths hide behind two
+ * Python module classes and three third-party operator call sites.  Each
+ * entry point below names the reference interface it replaces (paths relative to the reference
+ * repository).  INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, scalars; no torch / C++ types cross the boundary.
+ *   - every pointer is a DEVICE pointer into caller-owned memory unless its name ends in _host.
+ *   - every call is asynchronous on the CUDA stream passed as `stream` (a cudaStream_t cast to
+ *     void*; NULL = legacy default stream).  No call synchronises the device.
+ *   - no hidden device allocation: scratch comes from the caller, sized by the *_bytes() queries.
+ *   - return value: 0 = ok, < 0 = error (NF_E_*); nf_last_error() returns a thread-local message.
+ *   - fp32 everywhere at the boundary; neighbour indices int32; neighbour counts int64 where the
+ *     reference returns int64 tensors.
+ */
+#ifndef NF_B200_H
+#define NF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define NF_API __attribute__((visibility("default")))
+#else
+#define NF_API
+#endif
+
+#define NF_B200_VERSION 100
+
+#define NF_OK 0
+#define NF_E_INVALID (-1)   /* bad argument (null pointer, unsupported size)            */
+#define NF_E_WORKSPACE (-2) /* caller workspace too small                               */
+#define NF_E_CUDA (-3)      /* a CUDA runtime call failed; see nf_last_error()          */
+#define NF_E_UNSUPPORTED (-4)
+
+/* operand dtype of the tensor-core contractions (accumulation is always fp32) */
+#define NF_DTYPE_F16 0
+#define NF_DTYPE_BF16 1
+
+NF_API int nf_version(void);
+NF_API const char* nf_last_error(void);
+/* number of kernel launches issued by this library since process start (bench bookkeeping) */
+NF_API int64_t nf_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Spatial grid (shared by both neighbour searches)
+ * replaces: the O(R*S*P) scan + particles.repeat(R,1,1) of models/renderer.py:113-118 and
+ *           Open3D's FixedRadiusSearch hash-table build inside ContinuousConv (models/transmodel.py:116)
+ * cell: edge length of a grid cell (use >= 1.002 * search radius).
+ * ------------------------------------------------------------------------------------------- */
+NF_API size_t nf_grid_workspace_bytes(int n_points);
+NF_API int nf_grid_build(const float* pos /*(n,3)*/, int n_points, float cell, void* grid_ws, size_t grid_ws_bytes,
+                  void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * First-K-by-index ball query   (parity / debug entry point)
+ * replaces: pytorch3d.ops.ball_query(p1, p2, K=, radius=) at models/renderer.py:116-118
+ * idx_out (nq,K) int32: the K smallest particle indices with |q-p|^2 < radius^2, ascending,
+ *   -1 padded (pytorch3d returns the same set in the same order);  count_out (nq) int32 =
+ *   min(#in-radius, K).  Squared distances / gathered neighbours are recomputed by the consumer.
+ * ------------------------------------------------------------------------------------------- */
+NF_API int nf_ballquery_firstk(const void* grid_ws, const float* queries /*(nq,3)*/, int nq, float radius, int K,
+                        int32_t* idx_out, int32_t* count_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * NeRF MLP weights   replaces: models/nerf.py:57-81 parameter storage (nn.Linear fp32)
+ * params: 24 device pointers per net in this order (weight then bias for each):
+ *   xyz_encoding_1..8, xyz_encoding_final, dir_encoding, sigma, rgb       (row-major (out,in) fp32)
+ * packed_out: nf_render_packed_weights_bytes() bytes; layout is private (tcgen05 operand tiles).
+ * ------------------------------------------------------------------------------------------- */
+NF_API size_t nf_render_packed_weights_bytes(void);
+NF_API int nf_render_pack_weights(const float* const* params_host /*[24] device pointers*/, int dtype, void* packed_out,
+                           void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused positional-encoding + NeRF MLP over compact geometry records (parity / debug entry point)
+ * replaces: Embedding.forward x6 (models/nerf.py:21-38, called from models/renderer.py:125-179)
+ *           + NeRF.forward (models/nerf.py:83-124)
+ * records (n_rows,16) fp32: [x(3), density, smoothed(3), variance(3), ray_dir(3), smoothed_dir(3)]
+ * out (n_rows,4) fp32: [r,g,b,sigma]   (sigma_only != 0: [0,0,0,sigma], layers after sigma skipped)
+ * ------------------------------------------------------------------------------------------- */
+NF_API int nf_nerf_mlp_forward(const void* packed_weights, int dtype, const float* records, int n_rows, int sigma_only,
+                        float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Whole renderer forward over one chunk of rays
+ * replaces: RenderNet.forward (models/renderer.py:211-270), .coarse_rendering (:273-307),
+ *           .fine_rendering (:310-369) incl. utils/ray_utils.py coarse_sample_ray /
+ *           ImportanceSampling / sample_pdf and models/renderer.py render_image.
+ * ------------------------------------------------------------------------------------------- */
+#define NF_RENDER_FORWARD 0 /* coarse + fine                                   */
+#define NF_RENDER_COARSE 1  /* coarse only                                     */
+#define NF_RENDER_FINE 2    /* sigma-only coarse pass, then fine               */
+
+typedef struct nf_render_args {
+    /* scene */
+    const void* grid_ws;    /* nf_grid_build() of `particles` with cell >= 1.002*radius        */
+    const float* particles; /* (n_particles,3)                                                 */
+    int32_t n_particles;
+    /* rays */
+    const float* rays; /* (n_rays,6) [origin(3), direction(3)]                                  */
+    int32_t n_rays;
+    float ro[3]; /* camera position used for the smoothed-direction feature (set_ro)          */
+    /* sampling */
+    const float* z_coarse; /* (n_coarse) depths shared by all rays: near*(1-t)+far*t            */
+    const float* u_importance; /* (n_importance) inverse-CDF arguments: linspace(0,1,n)         */
+    int32_t n_coarse, n_importance;
+    /* search */
+    float radius;
+    int32_t K;
+    /* behaviour */
+    int32_t mode;       /* NF_RENDER_*                                                         */
+    int32_t use_mask;   /* cfg.use_mask                                                        */
+    int32_t white_background;
+    int32_t dtype;      /* NF_DTYPE_*                                                          */
+    const void* weights_coarse; /* packed                                                      */
+    const void* weights_fine;
+    /* outputs (any may be NULL): shapes as in the reference's result dict */
+    float* rgb0;      /* (n_rays,3) */
+    float* depth0;    /* (n_rays)   */
+    float* opacity0;  /* (n_rays)   */
+    int64_t* num_nn0; /* (n_rays,n_coarse)   */
+    float* mask0;     /* (n_rays)   */
+    float* rgb1;
+    float* depth1;
+    float* opacity1;
+    int64_t* num_nn1; /* (n_rays,n_coarse+n_importance) */
+    float* mask1;
+    /* scratch */
+    void* workspace;
+    size_t workspace_bytes;
+    /* optional statistics written by the device (may be NULL): int32[4] =
+       {rows evaluated coarse, rows evaluated fine, active samples coarse, active samples fine} */
+    int32_t* stats;
+} nf_render_args;
+
+NF_API size_t nf_render_workspace_bytes(int n_rays, int n_coarse, int n_importance);
+NF_API int nf_render_forward(const nf_render_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Transition model
+ * replaces: open3d.ml.torch.layers.ContinuousConv.forward (models/transmodel.py:116,118,125),
+ *           ml3d.ops.reduce_subarrays_sum (:135), nn.Linear x4 (:117,126) and
+ *           ParticleNet.forward (:151-163)
+ * params: device pointers, fp32, in this order:
+ *   conv0_fluid.{kernel,bias}, conv0_obstacle.{kernel,bias}, dense0_fluid.{weight,bias},
+ *   conv1.{kernel,bias}, dense1.{weight,bias}, conv2.{..}, dense2.{..}, conv3.{..}, dense3.{..}   (18)
+ *   kernels are (4,4,4,cin,cout), dense weights (out,in).
+ * ------------------------------------------------------------------------------------------- */
+NF_API size_t nf_transition_packed_weights_bytes(void);
+NF_API int nf_transition_pack_weights(const float* const* params_host /*[18] device pointers*/, int dtype,
+                               void* packed_out, void* stream);
+NF_API size_t nf_transition_workspace_bytes(int n_fluid, int n_box);
+
+typedef struct nf_transition_args {
+    const float* pos; /* (n_fluid,3) */
+    const float* vel; /* (n_fluid,3) */
+    int32_t n_fluid;
+    const float* box;         /* (n_box,3) */
+    const float* box_normals; /* (n_box,3) */
+    int32_t n_box;
+    float gravity[3];
+    float dt;
+    float filter_extent; /* diameter; search radius = extent/2 */
+    int32_t dtype;
+    const void* weights; /* packed */
+    /* outputs */
+    float* pos_out;  /* (n_fluid,3) */
+    float* vel_out;  /* (n_fluid,3) */
+    float* nnbr_out; /* (n_fluid) float: number of fluid neighbours */
+    /* optional debug outputs (may be NULL) */
+    float* feats0_out; /* (n_fluid,96) concatenated [obstacle, fluid, dense] */
+    float* delta_out;  /* (n_fluid,3) position correction */
+    void* workspace;
+    size_t workspace_bytes;
+    /* rank-sharded execution (n>1 GPUs): this rank computes particles [shard_begin, shard_end) of every
+       layer; rows outside the shard must be supplied by the caller between layers (see
+       neurofluid_b200/distributed.py).  Single GPU: 0, n_fluid. */
+    int32_t shard_begin, shard_end;
+    int32_t phase; /* -1: whole step;  >=0: run only phase `phase` (see nf_transition_num_phases) */
+} nf_transition_args;
+
+NF_API int nf_transition_num_phases(void);
+NF_API int nf_transition_step(const nf_transition_args* args, void* stream);
+
+/* One ContinuousConv layer on its own (parity / debug entry point): fp32 in/out.
+ * kernel (4,4,4,cin,cout), bias (cout) or NULL.  counts_out (n_out) int32 may be NULL. */
+NF_API size_t nf_cconv_workspace_bytes(int n_in, int n_out, int cin, int cout);
+NF_API int nf_cconv_forward(const float* in_pos, const float* in_feat, int n_in, int cin, const float* out_pos, int n_out,
+                     float extent, const float* kernel, const float* bias, int cout, int ignore_same_pos, int dtype,
+                     float* out, int32_t* counts_out, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NF_B200_H */

@@ -1,0 +1,111 @@
+"""ctypes binding of libnf_b200.so (C ABI declared in include/nf_b200.h).
+
+The product path has no fallback: if the library is missing or fails to load, every entry point
+raises.  Build it with `python -m neurofluid_b200.build` (or `__graft_entry__.build()`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnf_b200.so")
+
+NF_DTYPE_F16, NF_DTYPE_BF16 = 0, 1
+NF_RENDER_FORWARD, NF_RENDER_COARSE, NF_RENDER_FINE = 0, 1, 2
+
+_vp, _i32, _f32, _sz, _i64 = C.c_void_p, C.c_int32, C.c_float, C.c_size_t, C.c_int64
+
+
+class RenderArgs(C.Structure):
+    _fields_ = [
+        ("grid_ws", _vp), ("particles", _vp), ("n_particles", _i32),
+        ("rays", _vp), ("n_rays", _i32), ("ro", _f32 * 3),
+        ("z_coarse", _vp), ("u_importance", _vp), ("n_coarse", _i32), ("n_importance", _i32),
+        ("radius", _f32), ("K", _i32),
+        ("mode", _i32), ("use_mask", _i32), ("white_background", _i32), ("dtype", _i32),
+        ("weights_coarse", _vp), ("weights_fine", _vp),
+        ("rgb0", _vp), ("depth0", _vp), ("opacity0", _vp), ("num_nn0", _vp), ("mask0", _vp),
+        ("rgb1", _vp), ("depth1", _vp), ("opacity1", _vp), ("num_nn1", _vp), ("mask1", _vp),
+        ("workspace", _vp), ("workspace_bytes", _sz), ("stats", _vp),
+    ]
+
+
+class TransitionArgs(C.Structure):
+    _fields_ = [
+        ("pos", _vp), ("vel", _vp), ("n_fluid", _i32),
+        ("box", _vp), ("box_normals", _vp), ("n_box", _i32),
+        ("gravity", _f32 * 3), ("dt", _f32), ("filter_extent", _f32), ("dtype", _i32),
+        ("weights", _vp),
+        ("pos_out", _vp), ("vel_out", _vp), ("nnbr_out", _vp),
+        ("feats0_out", _vp), ("delta_out", _vp),
+        ("workspace", _vp), ("workspace_bytes", _sz),
+        ("shard_begin", _i32), ("shard_end", _i32), ("phase", _i32),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/nf_b200.h declares
+SIGNATURES = {
+    "nf_version": (C.c_int, []),
+    "nf_last_error": (C.c_char_p, []),
+    "nf_launch_count": (_i64, []),
+    "nf_grid_workspace_bytes": (_sz, [C.c_int]),
+    "nf_grid_build": (C.c_int, [_vp, C.c_int, _f32, _vp, _sz, _vp]),
+    "nf_ballquery_firstk": (C.c_int, [_vp, _vp, C.c_int, _f32, C.c_int, _vp, _vp, _vp]),
+    "nf_render_packed_weights_bytes": (_sz, []),
+    "nf_render_pack_weights": (C.c_int, [C.POINTER(_vp), C.c_int, _vp, _vp]),
+    "nf_nerf_mlp_forward": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, _vp, _vp]),
+    "nf_render_workspace_bytes": (_sz, [C.c_int, C.c_int, C.c_int]),
+    "nf_render_forward": (C.c_int, [C.POINTER(RenderArgs), _vp]),
+    "nf_transition_packed_weights_bytes": (_sz, []),
+    "nf_transition_pack_weights": (C.c_int, [C.POINTER(_vp), C.c_int, _vp, _vp]),
+    "nf_transition_workspace_bytes": (_sz, [C.c_int, C.c_int]),
+    "nf_transition_num_phases": (C.c_int, []),
+    "nf_transition_step": (C.c_int, [C.POINTER(TransitionArgs), _vp]),
+    "nf_cconv_workspace_bytes": (_sz, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "nf_cconv_forward": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int, _f32, _vp, _vp, C.c_int, C.c_int,
+                                    C.c_int, _vp, _vp, _vp, _sz, _vp]),
+}
+
+_lib = None
+
+
+class NFError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NFError(f"{LIB_PATH} is missing: the CUDA extension is not built "
+                          "(run `python -m neurofluid_b200.build`); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)          # AttributeError here = header/library mismatch
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().nf_last_error()
+        raise NFError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+def ptr(t):
+    """device (or host) pointer of a torch tensor as c_void_p; None -> NULL."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise NFError("neurofluid_b200 runs on CUDA tensors only (sm_100a kernels); got a CPU tensor and there "
+                          "is no CPU fallback")

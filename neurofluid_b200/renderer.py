@@ -1,0 +1,174 @@
+"""RenderNet -- drop-in for the reference's `models/renderer.py:RenderNet` on B200.
+
+Same constructor, same `forward / coarse_rendering / fine_rendering / set_ro` signatures, same
+result-dict keys, shapes and dtypes, same state-dict layout; the arithmetic runs in
+libnf_b200.so (csrc/nf_grid.cu, nf_render.cu, nf_mlp.cu) through the C ABI of include/nf_b200.h.
+There is no CPU or eager-torch fallback: CPU tensors or a missing extension raise.
+
+Differences a caller can observe (all documented in DESIGN.md):
+  * any number of rays per call (the reference needs `ray_chunk=1024` to bound its O(R*P) repeat);
+  * tensor-core operands are fp16 (or bf16) with fp32 accumulation -> outputs agree with the fp32
+    reference to ~1e-4 relative L2, not bit for bit;  integer outputs (num_nn_*, mask_*) are exact;
+  * forward only: outputs carry no autograd graph (backward kernels are SURVEY.md section 8f-1);
+  * `fine_rendering` works (the reference's raises on every shipped config, models/renderer.py:175,322).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+from torch import nn
+
+from . import _lib
+from ._lib import NFError, check, lib, ptr, require_cuda, stream_ptr
+from .nerf import Embedding, NeRF
+from .ops import CELL_SCALE, Grid, pack_nerf_weights
+
+
+class RenderNet(nn.Module):
+    def __init__(self, cfg, near, far, operand_dtype: str = "fp16", max_rays_per_launch: int = 131072):
+        super().__init__()
+        self.cfg = cfg
+        self.near, self.far = near, far
+        self.N_samples = cfg.ray.N_samples
+        self.N_importance = cfg.ray.N_importance
+        self.raduis = cfg.NN_search.search_raduis_scale * cfg.NN_search.particle_radius   # sic (reference spelling)
+        self.fix_radius = cfg.NN_search.fix_radius
+        self.num_neighbor = cfg.NN_search.N_neighbor
+        enc = cfg.encoding
+        if not (enc.density and enc.var and enc.smoothed_pos and enc.smoothed_dir and enc.exclude_ray):
+            raise NFError("the sm_100a kernels implement the shipped encoding set (density, var, smoothed_pos, "
+                          "smoothed_dir, exclude_ray all on; configs/end2end.yaml:43-49)")
+        if not self.fix_radius:
+            raise NFError("fix_radius=False has no live code path in the reference (models/renderer.py:119-121)")
+        self.embedding_xyz = Embedding(3, 10)
+        self.embedding_dir = Embedding(3, 4)
+        self.embedding_density = Embedding(1, 4)
+        in_xyz = 3 * self.embedding_xyz.out_channels + self.embedding_density.out_channels      # 198
+        in_dir = 2 * self.embedding_dir.out_channels                                            # 54
+        self.nerf_coarse = NeRF(in_channels_xyz=in_xyz, in_channels_dir=in_dir)
+        self.nerf_fine = NeRF(in_channels_xyz=in_xyz, in_channels_dir=in_dir)
+        self.operand_dtype = {"fp16": _lib.NF_DTYPE_F16, "bf16": _lib.NF_DTYPE_BF16}[operand_dtype]
+        self.max_rays_per_launch = int(max_rays_per_launch)
+        self._packed = {}      # net name -> (version key, packed tensor)
+        self._ws = None
+        self._tables = {}
+        self.last_stats = None
+
+    # ------------------------------------------------------------------ reference helpers
+    def set_ro(self, cw):
+        return cw[:, 3]
+
+    # ------------------------------------------------------------------ internals
+    def _packed_weights(self, name):
+        net = getattr(self, name)
+        params = net.ordered_params()
+        key = tuple((p.data_ptr(), p._version) for p in params) + (self.operand_dtype,)
+        hit = self._packed.get(name)
+        if hit is None or hit[0] != key:
+            self._packed[name] = (key, pack_nerf_weights(params, self.operand_dtype))
+        return self._packed[name][1]
+
+    def _sample_tables(self, device, use_disp):
+        key = (str(device), bool(use_disp), self.N_samples, self.N_importance, float(self.near), float(self.far))
+        if key not in self._tables:
+            t = torch.linspace(0, 1, self.N_samples)                       # utils/ray_utils.py:236-240
+            z = 1 / (1 / self.near * (1 - t) + 1 / self.far * t) if use_disp else self.near * (1 - t) + self.far * t
+            u = torch.linspace(0.0, 1.0, max(self.N_importance, 1))        # utils/ray_utils.py:186-188 (det=True)
+            self._tables[key] = (z.float().to(device), u.float().to(device))
+        return self._tables[key]
+
+    def _workspace(self, n_rays, n_imp, device):
+        need = lib().nf_render_workspace_bytes(n_rays, self.N_samples, n_imp)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=device)
+        return self._ws
+
+    def _run(self, mode, physical_particles, ro, rays, use_disp, perturb, noise_std, white_background):
+        if perturb != 0 or noise_std != 0:
+            raise NFError("perturb / noise_std are training-time jitter the reference's trainers never enable "
+                          "(trainer/basetrainer.py:284-289); only the deterministic path is implemented")
+        require_cuda(physical_particles, rays)
+        dev = rays.device
+        particles = physical_particles.detach().to(torch.float32).contiguous()
+        rays = rays.detach().to(torch.float32).contiguous()
+        ro_host = [float(v) for v in ro.detach().float().cpu().tolist()]
+        R, S0 = rays.shape[0], self.N_samples
+        fine = mode != _lib.NF_RENDER_COARSE
+        NI = self.N_importance if fine else 0
+        if mode != _lib.NF_RENDER_COARSE and self.N_importance <= 0:
+            if mode == _lib.NF_RENDER_FINE:
+                raise AssertionError("N_importance > 0 required")          # models/renderer.py:347
+            mode, fine, NI = _lib.NF_RENDER_COARSE, False, 0
+        S1 = S0 + NI
+        z_tab, u_tab = self._sample_tables(dev, use_disp)
+        grid = Grid(particles, CELL_SCALE * self.raduis)
+        wc = self._packed_weights("nerf_coarse")
+        wf = self._packed_weights("nerf_fine") if fine else None
+        want0 = mode != _lib.NF_RENDER_FINE
+        out = {}
+        f32 = dict(dtype=torch.float32, device=dev)
+        if want0:
+            out["rgb0"] = torch.empty((R, 3), **f32)
+            out["depth0"] = torch.empty((R,), **f32)
+            out["opacity0"] = torch.empty((R,), **f32)
+            out["num_nn_0"] = torch.empty((R, S0, 1), dtype=torch.int64, device=dev)
+            out["mask_0"] = torch.empty((R, 1), **f32)
+        if fine:
+            out["rgb1"] = torch.empty((R, 3), **f32)
+            out["depth1"] = torch.empty((R,), **f32)
+            out["opacity1"] = torch.empty((R,), **f32)
+            out["num_nn_1"] = torch.empty((R, S1, 1), dtype=torch.int64, device=dev)
+            out["mask_1"] = torch.empty((R, 1), **f32)
+        chunk = max(1, min(self.max_rays_per_launch, R))
+        ws = self._workspace(chunk, NI, dev)
+        nchunks = (R + chunk - 1) // chunk
+        stats = torch.zeros((max(nchunks, 1), 4), dtype=torch.int32, device=dev)
+        st = stream_ptr()
+        for ci, r0 in enumerate(range(0, R, chunk)):
+            r1 = min(r0 + chunk, R)
+            a = _lib.RenderArgs()
+            a.grid_ws, a.particles, a.n_particles = ptr(grid.ws), ptr(particles), particles.shape[0]
+            a.rays, a.n_rays = C.c_void_p(rays.data_ptr() + r0 * 24), r1 - r0
+            a.ro = (C.c_float * 3)(*ro_host)
+            a.z_coarse, a.u_importance, a.n_coarse, a.n_importance = ptr(z_tab), ptr(u_tab), S0, NI
+            a.radius, a.K = float(self.raduis), int(self.num_neighbor)
+            a.mode, a.use_mask, a.white_background = int(mode), int(bool(self.cfg.use_mask)), int(bool(white_background))
+            a.dtype = self.operand_dtype
+            a.weights_coarse, a.weights_fine = ptr(wc), ptr(wf)
+
+            def sl(name, per_ray_bytes):
+                t = out.get(name)
+                return None if t is None else C.c_void_p(t.data_ptr() + r0 * per_ray_bytes)
+            a.rgb0, a.depth0, a.opacity0 = sl("rgb0", 12), sl("depth0", 4), sl("opacity0", 4)
+            a.num_nn0, a.mask0 = sl("num_nn_0", 8 * S0), sl("mask_0", 4)
+            a.rgb1, a.depth1, a.opacity1 = sl("rgb1", 12), sl("depth1", 4), sl("opacity1", 4)
+            a.num_nn1, a.mask1 = sl("num_nn_1", 8 * S1), sl("mask_1", 4)
+            a.workspace, a.workspace_bytes = ptr(ws), ws.numel()
+            a.stats = C.c_void_p(stats.data_ptr() + ci * 16)
+            check(lib().nf_render_forward(C.byref(a), st), "nf_render_forward")
+        self.last_stats = stats       # device tensor; .sum(0) = [rows0, rows1, active0, active1]
+        self._keep = (grid, particles, rays)
+        return out
+
+    # ------------------------------------------------------------------ reference API
+    def forward(self, physical_particles, ro, rays, focal=None, c2w=None, use_disp=False, perturb=0, noise_std=0.,
+                white_background=True):
+        """models/renderer.py:211-270.  `focal` and `c2w` are accepted and unused, as in the reference."""
+        return self._run(_lib.NF_RENDER_FORWARD, physical_particles, ro, rays, use_disp, perturb, noise_std,
+                         white_background)
+
+    def coarse_rendering(self, physical_particles, ro, rays, focal=None, c2w=None, use_disp=False, perturb=0,
+                         noise_std=0., white_background=True):
+        """models/renderer.py:273-307."""
+        return self._run(_lib.NF_RENDER_COARSE, physical_particles, ro, rays, use_disp, perturb, noise_std,
+                         white_background)
+
+    def fine_rendering(self, physical_particles, ro, rays, focal=None, c2w=None, use_disp=False, perturb=0,
+                       noise_std=0., white_background=True):
+        """models/renderer.py:310-369 (sigma-only coarse pass, then the fine pass)."""
+        return self._run(_lib.NF_RENDER_FINE, physical_particles, ro, rays, use_disp, perturb, noise_std,
+                         white_background)
+
+
+Renderer = RenderNet      # BASELINE.json's wording
