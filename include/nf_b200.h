@@ -48,6 +48,12 @@ NF_API int nf_version(void);
 NF_API const char* nf_last_error(void);
 /* number of kernel launches issued by this library since process start (bench bookkeeping) */
 NF_API int64_t nf_launch_count(void);
+/* Optional per-stage device timing of nf_render_forward (bench bookkeeping): while enabled every call
+ * records CUDA events on its stream between stages; nf_profile_read() synchronises on them, returns the
+ * summed milliseconds of [ray query coarse, MLP coarse, composite+resample+ray query fine, MLP fine,
+ * composite fine] and the number of calls covered, and clears the record. */
+NF_API int nf_profile_enable(int on);
+NF_API int nf_profile_read(double* stage_ms_host /*[5]*/, int* n_calls_host);
 
 /* ---------------------------------------------------------------------------------------------
  * Spatial grid (shared by both neighbour searches)

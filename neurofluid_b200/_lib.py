@@ -49,6 +49,8 @@ SIGNATURES = {
     "nf_version": (C.c_int, []),
     "nf_last_error": (C.c_char_p, []),
     "nf_launch_count": (_i64, []),
+    "nf_profile_enable": (C.c_int, [C.c_int]),
+    "nf_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "nf_grid_workspace_bytes": (_sz, [C.c_int]),
     "nf_grid_build": (C.c_int, [_vp, C.c_int, _f32, _vp, _sz, _vp]),
     "nf_ballquery_firstk": (C.c_int, [_vp, _vp, C.c_int, _f32, C.c_int, _vp, _vp, _vp]),

@@ -22,6 +22,8 @@
 //            coarse depths (rank merge), then run the ball query again for the merged samples.
 // [MLP]    : fine network.
 // stage FIN: alpha-composite the fine samples -> rgb1/depth1/opacity1/mask_1.
+#include <vector>
+
 #include "nf_common.cuh"
 #include "nf_mlp.cuh"
 
@@ -483,11 +485,57 @@ static int launch_mid(int ns1, int grid, const StageArgs& p, cudaStream_t st) {
     return NF_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// optional per-stage timing with CUDA events recorded on the launching stream (bench.py roofline)
+// ------------------------------------------------------------------------------------------------
+constexpr int NSTAGE_T = 5;   // q0, mlp coarse, mid, mlp fine, fin
+static bool g_prof_on = false;
+static std::vector<cudaEvent_t> g_prof_events;   // (NSTAGE_T + 1) events per profiled call
+
+struct StageTimer {
+    cudaStream_t st;
+    bool on;
+    explicit StageTimer(cudaStream_t s) : st(s), on(g_prof_on) { mark(); }
+    void mark() {
+        if (!on) return;
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) { on = false; return; }
+        cudaEventRecord(e, st);
+        g_prof_events.push_back(e);
+    }
+};
+
 }  // namespace render
 }  // namespace nf
 
 using namespace nf;
 using namespace nf::render;
+
+extern "C" int nf_profile_enable(int on) {
+    for (cudaEvent_t e : g_prof_events) cudaEventDestroy(e);
+    g_prof_events.clear();
+    g_prof_on = on != 0;
+    return NF_OK;
+}
+
+extern "C" int nf_profile_read(double* stage_ms /*[5]*/, int* n_calls) {
+    NF_REQUIRE(stage_ms && n_calls, NF_E_INVALID, "nf_profile_read: null argument");
+    for (int i = 0; i < NSTAGE_T; ++i) stage_ms[i] = 0.0;
+    const size_t per = NSTAGE_T + 1;
+    const size_t calls = g_prof_events.size() / per;
+    for (size_t c = 0; c < calls; ++c) {
+        NF_CUDA_OK(cudaEventSynchronize(g_prof_events[c * per + NSTAGE_T]));
+        for (int i = 0; i < NSTAGE_T; ++i) {
+            float ms = 0.f;
+            NF_CUDA_OK(cudaEventElapsedTime(&ms, g_prof_events[c * per + i], g_prof_events[c * per + i + 1]));
+            stage_ms[i] += ms;
+        }
+    }
+    *n_calls = (int)calls;
+    for (cudaEvent_t e : g_prof_events) cudaEventDestroy(e);
+    g_prof_events.clear();
+    return NF_OK;
+}
 
 extern "C" size_t nf_render_workspace_bytes(int n_rays, int n_coarse, int n_importance) {
     if (n_rays <= 0 || n_coarse <= 0 || n_importance < 0) return 0;
@@ -543,10 +591,12 @@ extern "C" int nf_render_forward(const nf_render_args* a, void* stream_) {
     const int threads = WARPS_PER_BLOCK * 32;
     const int grid = min((a->n_rays + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, num_sms() * 8);
 
+    StageTimer tm(st);
     // ---- stage Q0
     if (L.ns0 == 2) k_stage_q0<2><<<grid, threads, 0, st>>>(p);
     else k_stage_q0<4><<<grid, threads, 0, st>>>(p);
     NF_LAUNCH_OK();
+    tm.mark();
     // ---- coarse network
     mlp::KernelArgs m;
     m.packed = (const uint8_t*)a->weights_coarse;
@@ -556,25 +606,30 @@ extern "C" int nf_render_forward(const nf_render_args* a, void* stream_) {
     m.out4 = p.out0;
     int rc = mlp::launch(m, a->dtype, st);
     if (rc != NF_OK) return rc;
+    tm.mark();
     if (!fine) {
         if (L.ns0 == 2) k_stage_fin<2, true><<<grid, threads, 0, st>>>(p);
         else k_stage_fin<4, true><<<grid, threads, 0, st>>>(p);
         NF_LAUNCH_OK();
+        tm.mark(); tm.mark(); tm.mark();
     } else {
         rc = (L.ns0 == 2) ? launch_mid<2>(L.ns1, grid, p, st) : launch_mid<4>(L.ns1, grid, p, st);
         if (rc != NF_OK) return rc;
+        tm.mark();
         m.packed = (const uint8_t*)a->weights_fine;
         m.records = p.rec1; m.rowid = p.rowid1; m.n_rows_dev = p.counters + 1; m.n_rows_cap = L.cap1;
         m.n_layers = 10;
         m.out4 = p.out1;
         rc = mlp::launch(m, a->dtype, st);
         if (rc != NF_OK) return rc;
+        tm.mark();
         switch (L.ns1) {
             case 4: k_stage_fin<4, false><<<grid, threads, 0, st>>>(p); break;
             case 6: k_stage_fin<6, false><<<grid, threads, 0, st>>>(p); break;
             default: k_stage_fin<8, false><<<grid, threads, 0, st>>>(p); break;
         }
         NF_LAUNCH_OK();
+        tm.mark();
     }
     if (a->stats) NF_CUDA_OK(cudaMemcpyAsync(a->stats, p.counters, 16, cudaMemcpyDeviceToDevice, st));
     return NF_OK;

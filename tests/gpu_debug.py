@@ -53,7 +53,7 @@ def stage_mlp():
         rec[:, 13:16] /= np.linalg.norm(rec[:, 13:16], axis=1, keepdims=True)
         rec = torch.from_numpy(rec)
         ref, ref_sig = mlp_reference(sd, "nerf_coarse", rec)
-        for swap in (0, 1):
+        for swap in (0,):
             os.environ["NF_MLP_DESC_SWAP"] = str(swap)
             for dt, name in ((_lib.NF_DTYPE_F16, "fp16"), (_lib.NF_DTYPE_BF16, "bf16")):
                 packed = ops.pack_nerf_weights([p.to(dev) for p in net.nerf_coarse.ordered_params()], dt)

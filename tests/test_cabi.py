@@ -1,0 +1,62 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol include/nf_b200.h
+declares, size queries work without a device, and the host-side mirror of the reference interface has
+the reference's state-dict layout.  No compute calls (there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import neurofluid_b200 as nb
+from neurofluid_b200 import _lib, scenes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "nf_b200.h")).read()
+    return sorted(set(re.findall(r"NF_API\s+[\w\s\*]+?\b(nf_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = declared_symbols()
+    assert len(names) >= 15
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(L, n), n
+    assert sorted(_lib.SIGNATURES) == names          # the ctypes binding covers the header exactly
+
+
+def test_size_queries_and_version_without_device():
+    L = _lib.lib()
+    assert L.nf_version() == 100
+    assert L.nf_render_packed_weights_bytes() == 154 * 8192 + 20 * 4096 + 3208 * 4
+    assert L.nf_grid_workspace_bytes(1000) > 3 * 64 ** 3 * 4
+    assert L.nf_render_workspace_bytes(1024, 64, 128) > 1024 * 192 * (64 + 16)
+    assert L.nf_render_workspace_bytes(0, 64, 128) == 0
+
+
+def test_struct_layout_matches_header():
+    # nf_render_args: 31 fields; pointers are 8-byte aligned -> size is a multiple of 8 and stable
+    assert ctypes.sizeof(_lib.RenderArgs) % 8 == 0
+    assert _lib.RenderArgs.rays.offset == 24 and _lib.RenderArgs.ro.offset == 36
+    assert _lib.RenderArgs.z_coarse.offset == 48 and _lib.RenderArgs.weights_coarse.offset == 96
+    assert _lib.RenderArgs.workspace.offset == 192 and _lib.RenderArgs.stats.offset == 208
+    assert ctypes.sizeof(_lib.RenderArgs) == 216
+
+
+def test_rendernet_state_dict_layout_and_errors():
+    net = nb.RenderNet(scenes.render_cfg(), scenes.NEAR, scenes.FAR)
+    sd = scenes.init_render_state(0)
+    assert sorted(net.state_dict().keys()) == sorted(sd.keys())
+    net.load_state_dict(sd, strict=True)
+    assert net.nerf_coarse.xyz_encoding_5[0].weight.shape == (256, 454)
+    assert net.nerf_fine.dir_encoding[0].weight.shape == (128, 310)
+    assert nb.Renderer is nb.RenderNet
+    cw = torch.from_numpy(scenes.CAMERA_C2W)
+    assert torch.equal(net.set_ro(cw), cw[:, 3])
+    with pytest.raises(_lib.NFError):                 # CPU tensors never fall back to a CPU path
+        net(torch.zeros(10, 3), cw[:, 3], torch.zeros(4, 6), 1.0, cw)
+    with pytest.raises(_lib.NFError):
+        nb.RenderNet(scenes.render_cfg(var=False), scenes.NEAR, scenes.FAR)
