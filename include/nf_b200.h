@@ -72,7 +72,8 @@ NF_API int nf_grid_build(const float* pos /*(n,3)*/, int n_points, float cell, v
  *   -1 padded (pytorch3d returns the same set in the same order);  count_out (nq) int32 =
  *   min(#in-radius, K).  Squared distances / gathered neighbours are recomputed by the consumer.
  * ------------------------------------------------------------------------------------------- */
-NF_API int nf_ballquery_firstk(const void* grid_ws, const float* queries /*(nq,3)*/, int nq, float radius, int K,
+NF_API int nf_ballquery_firstk(const void* grid_ws, int n_points /* as passed to nf_grid_build */,
+                               const float* queries /*(nq,3)*/, int nq, float radius, int K,
                         int32_t* idx_out, int32_t* count_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -142,8 +143,9 @@ typedef struct nf_render_args {
     /* scratch */
     void* workspace;
     size_t workspace_bytes;
-    /* optional statistics written by the device (may be NULL): int32[4] =
-       {rows evaluated coarse, rows evaluated fine, active samples coarse, active samples fine} */
+    /* optional statistics written by the device (may be NULL): int32[8] =
+       {MLP rows coarse, MLP rows fine, active samples coarse, active samples fine,
+        fine-pass queries answered by the lockstep / row-scan search, their loop iterations / 64} */
     int32_t* stats;
 } nf_render_args;
 

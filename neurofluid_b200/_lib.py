@@ -53,7 +53,7 @@ SIGNATURES = {
     "nf_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "nf_grid_workspace_bytes": (_sz, [C.c_int]),
     "nf_grid_build": (C.c_int, [_vp, C.c_int, _f32, _vp, _sz, _vp]),
-    "nf_ballquery_firstk": (C.c_int, [_vp, _vp, C.c_int, _f32, C.c_int, _vp, _vp, _vp]),
+    "nf_ballquery_firstk": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _f32, C.c_int, _vp, _vp, _vp]),
     "nf_render_packed_weights_bytes": (_sz, []),
     "nf_render_pack_weights": (C.c_int, [C.POINTER(_vp), C.c_int, _vp, _vp]),
     "nf_nerf_mlp_forward": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, _vp, _vp]),

@@ -4,11 +4,12 @@
 // FixedRadiusSearch table build behind open3d ContinuousConv (models/transmodel.py:116,118,125).
 //
 // Layout in HBM (caller workspace, see grid_layout()):
-//   GridHeader | cell_start[ncells+1] | fill[ncells] | occ27[ncells] | sorted float4[n] | cell_of[n]
+//   GridHeader | cell_start[ncells+1] | fill[ncells] | occ27[ncells] | sorted float4[n] | cell_of[n] | unordered[n]
 // `sorted` holds (x,y,z,bit-cast original index) grouped by cell, so a query streams 16-byte records
 // from at most 9 contiguous ranges (the x-neighbours of a (y,z) row are adjacent in memory).
-// Order *inside* a cell is arbitrary (atomic scatter): every consumer either selects by original
-// index (first-K) or sorts its neighbour list, so results do not depend on it.
+// Inside a cell the points are ascending in original index (atomic scatter + rank pass = a stable
+// counting sort), which is what lets the first-K query stop early and makes every neighbour list
+// deterministic.
 #include "nf_common.cuh"
 
 namespace nf {
@@ -80,7 +81,8 @@ __global__ void k_grid_setup(GridHeader* h, int n, float cell) {
 }
 
 __global__ void k_grid_count(const float* __restrict__ pos, int n, const GridHeader* __restrict__ h,
-                             int* __restrict__ counts /* = cell_start + 1 */, int* __restrict__ cell_of) {
+                             int* __restrict__ counts /* = cell_start + 1 */, int* __restrict__ cell_of,
+                             float4* __restrict__ orig4, int* __restrict__ fine_of) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int cx = cell_coord(pos[3 * i], h->origin[0], h->inv_cell, h->dim[0]);
@@ -88,6 +90,14 @@ __global__ void k_grid_count(const float* __restrict__ pos, int n, const GridHea
     const int cz = cell_coord(pos[3 * i + 2], h->origin[2], h->inv_cell, h->dim[2]);
     const int c = (cz * h->dim[1] + cy) * h->dim[0] + cx;
     cell_of[i] = c;
+    {
+        const float inv2 = __fmul_rn(h->inv_cell, 2.0f);
+        const int fx = cell_coord(pos[3 * i], h->origin[0], inv2, 2 * h->dim[0]);
+        const int fy = cell_coord(pos[3 * i + 1], h->origin[1], inv2, 2 * h->dim[1]);
+        const int fz = cell_coord(pos[3 * i + 2], h->origin[2], inv2, 2 * h->dim[2]);
+        fine_of[i] = (fz * 2 * h->dim[1] + fy) * 2 * h->dim[0] + fx;
+    }
+    orig4[i] = make_float4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], __int_as_float(c));
     atomicAdd(counts + c, 1);
 }
 
@@ -126,14 +136,28 @@ __global__ void __launch_bounds__(1024) k_grid_scan(const GridHeader* __restrict
     }
 }
 
-__global__ void k_grid_scatter(const float* __restrict__ pos, int n, const int* __restrict__ cell_of,
-                               const int* __restrict__ cell_start, int* __restrict__ fill,
-                               float4* __restrict__ sorted) {
+__global__ void k_grid_scatter(int n, const int* __restrict__ cell_of, const int* __restrict__ cell_start,
+                               int* __restrict__ fill, int* __restrict__ unordered) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int c = cell_of[i];
-    const int slot = cell_start[c] + atomicAdd(fill + c, 1);
-    sorted[slot] = make_float4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], __int_as_float(i));
+    unordered[cell_start[c] + atomicAdd(fill + c, 1)] = i;
+}
+
+// Make every cell ascending in original index (what a stable counting sort would give): element e of a
+// cell goes to position #{e' in the same cell : e' < e}.  O(cell population) per point; adjacent threads
+// read the same segment, so the loads are L1 broadcasts.
+__global__ void k_grid_rank(const float* __restrict__ pos, int n, const int* __restrict__ cell_of,
+                            const int* __restrict__ cell_start, const int* __restrict__ unordered,
+                            float4* __restrict__ sorted) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int i = unordered[s];
+    const int c = cell_of[i];
+    const int beg = cell_start[c], end = cell_start[c + 1];
+    int rank = 0;
+    for (int t = beg; t < end; ++t) rank += (unordered[t] < i);
+    sorted[beg + rank] = make_float4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], __int_as_float(i));
 }
 
 __global__ void k_grid_occ(const GridHeader* __restrict__ h, const int* __restrict__ cell_start,
@@ -154,12 +178,16 @@ __global__ void k_grid_occ(const GridHeader* __restrict__ h, const int* __restri
 
 __global__ void __launch_bounds__(256) k_ballquery(GridView g, const float* __restrict__ q, int nq, float radius,
                                                    int K, int* __restrict__ idx_out, int* __restrict__ cnt_out) {
+    __shared__ int sm_hits[8][HITBUF];
     const int lane = threadIdx.x & 31;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    int* buf = sm_hits[threadIdx.x >> 5];
     for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nq; i += nwarps) {
         const float qx = q[3 * i], qy = q[3 * i + 1], qz = q[3 * i + 2];
         int best = 0x7fffffff, cnt = 0;
-        if (grid_maybe_nonempty(g, qx, qy, qz, radius)) cnt = warp_first_k(g, qx, qy, qz, radius, K, lane, best);
+        const int occ = grid_occupancy(g, qx, qy, qz, radius);
+        QueryStats qs;
+        if (occ > 0) cnt = warp_first_k(g, qx, qy, qz, radius, K, lane, best, occ, LOCKSTEP_MIN_OCC, qs, buf);
         if (lane < K) idx_out[(size_t)i * K + lane] = lane < cnt ? best : -1;
         if (lane == 0) cnt_out[i] = cnt;
     }
@@ -184,6 +212,11 @@ extern "C" int nf_grid_build(const float* pos, int n, float cell, void* ws, size
     int* occ = (int*)(b + L.off_occ);
     float4* sorted = (float4*)(b + L.off_sorted);
     int* cell_of = (int*)(b + L.off_cellof);
+    int* unordered = (int*)(b + L.off_unordered);
+    float4* orig4 = (float4*)(b + L.off_orig4);
+    int* fine_of = (int*)(b + L.off_fineof);
+    // the tail padding of fine_of (read by 128-wide filter steps) must never match a marked cell
+    NF_CUDA_OK(cudaMemsetAsync(fine_of + n, 0xff, 128 * sizeof(int), st));
     // zero cell_start and fill in one memset (they are adjacent)
     NF_CUDA_OK(cudaMemsetAsync(cell_start, 0, L.off_occ - L.off_start, st));
     k_grid_init<<<1, 32, 0, st>>>(h);
@@ -196,13 +229,15 @@ extern "C" int nf_grid_build(const float* pos, int n, float cell, void* ws, size
     k_grid_setup<<<1, 32, 0, st>>>(h, n, cell);
     NF_LAUNCH_OK();
     if (n > 0) {
-        k_grid_count<<<(n + 255) / 256, 256, 0, st>>>(pos, n, h, cell_start + 1, cell_of);
+        k_grid_count<<<(n + 255) / 256, 256, 0, st>>>(pos, n, h, cell_start + 1, cell_of, orig4, fine_of);
         NF_LAUNCH_OK();
     }
     k_grid_scan<<<1, 1024, 0, st>>>(h, cell_start + 1);
     NF_LAUNCH_OK();
     if (n > 0) {
-        k_grid_scatter<<<(n + 255) / 256, 256, 0, st>>>(pos, n, cell_of, cell_start, fill, sorted);
+        k_grid_scatter<<<(n + 255) / 256, 256, 0, st>>>(n, cell_of, cell_start, fill, unordered);
+        NF_LAUNCH_OK();
+        k_grid_rank<<<(n + 255) / 256, 256, 0, st>>>(pos, n, cell_of, cell_start, unordered, sorted);
         NF_LAUNCH_OK();
     }
     k_grid_occ<<<(GRID_MAX_CELLS + 255) / 256, 256, 0, st>>>(h, cell_start, occ);
@@ -210,14 +245,16 @@ extern "C" int nf_grid_build(const float* pos, int n, float cell, void* ws, size
     return NF_OK;
 }
 
-extern "C" int nf_ballquery_firstk(const void* grid_ws, const float* queries, int nq, float radius, int K,
+extern "C" int nf_ballquery_firstk(const void* grid_ws, int n_points, const float* queries, int nq, float radius, int K,
                                    int32_t* idx_out, int32_t* count_out, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
-    NF_REQUIRE(grid_ws && idx_out && count_out && nq >= 0, NF_E_INVALID, "nf_ballquery_firstk: bad arguments");
     NF_REQUIRE(K >= 1 && K <= 32, NF_E_UNSUPPORTED, "nf_ballquery_firstk: K=%d not in [1,32]", K);
+    NF_REQUIRE(nq >= 0, NF_E_INVALID, "nf_ballquery_firstk: negative query count");
+    if (nq == 0) return NF_OK;
+    NF_REQUIRE(grid_ws && idx_out && count_out, NF_E_INVALID, "nf_ballquery_firstk: null pointer");
     if (nq == 0) return NF_OK;
     NF_REQUIRE(queries != nullptr, NF_E_INVALID, "nf_ballquery_firstk: null queries");
-    const GridView g = grid_view(grid_ws);
+    const GridView g = grid_view(grid_ws, n_points);
     const int nb = min((nq + 7) / 8, 16 * num_sms());
     k_ballquery<<<nb, 256, 0, st>>>(g, queries, nq, radius, K, idx_out, count_out);
     NF_LAUNCH_OK();

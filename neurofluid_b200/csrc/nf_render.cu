@@ -22,6 +22,7 @@
 //            coarse depths (rank merge), then run the ball query again for the merged samples.
 // [MLP]    : fine network.
 // stage FIN: alpha-composite the fine samples -> rgb1/depth1/opacity1/mask_1.
+#include <stdlib.h>
 #include <vector>
 
 #include "nf_common.cuh"
@@ -42,6 +43,7 @@ struct StageArgs {
     float radius;
     int K;
     int use_mask, white_bg, mode;
+    int lockstep_min_occ;
     const float* z_coarse;
     const float* u_imp;
     int S0, n_imp, S1;
@@ -51,7 +53,8 @@ struct StageArgs {
     float *rgb1, *depth1, *opac1, *mask1;
     long long* num_nn1;
     // workspace
-    int* counters;       // [0] rows coarse, [1] rows fine, [2] active coarse, [3] active fine
+    int* counters;       // [0] rows coarse, [1] rows fine, [2] active coarse, [3] active fine,
+                         // [4..7] fine-pass query statistics: lockstep queries, row-scan queries, their iterations (/64)
     unsigned* act0;      // (R, NS0)
     unsigned* act1;      // (R, NS1)
     float* z1;           // (R, S1)
@@ -85,8 +88,9 @@ template <int NS>
 __device__ __forceinline__ void ray_query(const StageArgs& p, int lane, const float (&o)[3], const float (&d)[3],
                                           const float (&z)[NS], int S, RowAlloc& ra, float* rec, int* rowid,
                                           int* row_counter, int* active_counter, int cap, int sample_base,
-                                          unsigned (&fullbits)[NS], int (&cnt)[NS]) {
+                                          unsigned (&fullbits)[NS], int (&cnt)[NS], QueryStats& qs, int* hitbuf) {
     float px[NS], py[NS], pz[NS];
+    int occ[NS];
     unsigned nonempty[NS], todo[NS];
     const int K = p.K;
     const float radius = p.radius;
@@ -98,8 +102,8 @@ __device__ __forceinline__ void ray_query(const StageArgs& p, int lane, const fl
         py[slot] = __fadd_rn(o[1], __fmul_rn(d[1], z[slot]));
         pz[slot] = __fadd_rn(o[2], __fmul_rn(d[2], z[slot]));
         const bool in = s < S;
-        const bool ne = in && grid_maybe_nonempty(p.g, px[slot], py[slot], pz[slot], radius);
-        nonempty[slot] = __ballot_sync(NF_FULL, ne);
+        occ[slot] = in ? grid_occupancy(p.g, px[slot], py[slot], pz[slot], radius) : 0;
+        nonempty[slot] = __ballot_sync(NF_FULL, occ[slot] > 0);
         todo[slot] = p.use_mask ? nonempty[slot] : __ballot_sync(NF_FULL, in);
         cnt[slot] = 0;
         fullbits[slot] = 0u;
@@ -114,8 +118,9 @@ __device__ __forceinline__ void ray_query(const StageArgs& p, int lane, const fl
             const float qx = __shfl_sync(NF_FULL, px[slot], src);
             const float qy = __shfl_sync(NF_FULL, py[slot], src);
             const float qz = __shfl_sync(NF_FULL, pz[slot], src);
+            const int qocc = __shfl_sync(NF_FULL, occ[slot], src);
             int best = 0x7fffffff, nsel = 0;
-            if ((nonempty[slot] >> src) & 1u) nsel = warp_first_k(p.g, qx, qy, qz, radius, K, lane, best);
+            if (qocc > 0) nsel = warp_first_k(p.g, qx, qy, qz, radius, K, lane, best, qocc, p.lockstep_min_occ, qs, hitbuf);
             const bool sel = lane < nsel;
             float nx = 0.f, ny = 0.f, nz = 0.f, d2 = 0.f;
             if (sel) {
@@ -166,6 +171,202 @@ __device__ __forceinline__ void ray_query(const StageArgs& p, int lane, const fl
                     reinterpret_cast<float4*>(rec + (size_t)row * 16)[lane] = v;
                 }
                 if (lane == 0) rowid[row] = sample_base + slot * 32 + src;
+            }
+        }
+    }
+    if (lane == 0 && n_active) atomicAdd(active_counter, n_active);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Group flavour of the neighbour search (used by the fine pass): one LANE per sample, 32 consecutive
+// samples of the ray per step.  The first-K-by-index rule means "scan the particles in original index
+// order and keep the first K inside the ball", so that is what the warp does -- but it only looks at
+// particles whose grid cell can matter to a still-unfinished lane: a per-warp 8192-bit cell bitmap
+// (hashed; false positives are harmless) is the union of the <= 27 neighbourhood cells of the unfinished
+// lanes and is rebuilt whenever their number halves.  Each 32-particle step reads one 128-byte line of
+// cell ids, ballots the bitmap test, and every surviving candidate is fetched once (warp-uniform 16-byte
+// load) and tested by all lanes.  Hits arrive in ascending index order, so a lane just appends until it
+// has K; no sorting, no selection.  The loop ends when every lane is finished.
+// ------------------------------------------------------------------------------------------------
+constexpr int BM_BITS = 16384;
+constexpr int BM_WORDS = BM_BITS / 32;
+
+// The slot loop is deliberately NOT unrolled and keeps no per-slot register arrays: an unrolled copy per slot
+// made the kernel ~190 KB of SASS and 70 % of its stall samples instruction-cache misses.
+__device__ __forceinline__ void ray_query_group(const StageArgs& p, int lane, const float (&o)[3],
+                                             const float (&d)[3], const float* zs /*smem: S sorted depths*/, int S,
+                                             float* rec, int* rowid, int* row_counter, int* active_counter, int cap,
+                                             int ray, long long* num_nn, unsigned* act, int act_stride,
+                                             QueryStats& qs, unsigned* bm, int* sel) {
+    const GridHeader* h = p.g.hdr;
+    const int K = p.K;
+    const float radius = p.radius;
+    const float r2 = __fmul_rn(radius, radius);
+    const float pad = radius * 1.001f + 1e-6f;
+    const int P = h->n;
+    const float ox = h->origin[0], oy = h->origin[1], oz = h->origin[2], inv = h->inv_cell;
+    const int nx = h->dim[0], ny = h->dim[1], nz = h->dim[2];
+    const unsigned lt = (1u << lane) - 1u;
+    int n_active = 0;
+    const int sample_base = ray * S;
+    const int nslots = (S + 31) >> 5;
+#pragma unroll 1
+    for (int slot = 0; slot < nslots; ++slot) {
+        const int s = slot * 32 + lane;
+        const bool in = s < S;
+        const float zv = zs[min(s, S - 1)];
+        const float qx = __fadd_rn(o[0], __fmul_rn(d[0], zv));
+        const float qy = __fadd_rn(o[1], __fmul_rn(d[1], zv));
+        const float qz = __fadd_rn(o[2], __fmul_rn(d[2], zv));
+        const int occ = in ? grid_occupancy(p.g, qx, qy, qz, radius) : 0;
+        const bool search = occ > 0;
+        const bool want = p.use_mask ? search : in;   // use_mask=False: every sample is evaluated, even empty ones
+        if (!__any_sync(NF_FULL, want)) {
+            if (num_nn && in) num_nn[(size_t)sample_base + s] = 0;
+            if (lane == 0) act[(size_t)ray * act_stride + slot] = 0u;
+            continue;
+        }
+        int cnt = 0;
+        if (__any_sync(NF_FULL, search)) {
+            bool done = !search;
+            int built_for = 0;
+            ++qs.n_lock;
+            // half-resolution cell range of this lane's ball (<= 5 fine cells per axis when cell > reach)
+            const float inv2 = __fmul_rn(inv, 2.0f);
+            const float fcell = 0.5f * h->cell;
+            const int fnx = 2 * nx, fny = 2 * ny, fnz = 2 * nz;
+            const int flox = cell_coord(qx - pad, ox, inv2, fnx), fhix = cell_coord(qx + pad, ox, inv2, fnx);
+            const int floy = cell_coord(qy - pad, oy, inv2, fny), fhiy = cell_coord(qy + pad, oy, inv2, fny);
+            const int floz = cell_coord(qz - pad, oz, inv2, fnz), fhiz = cell_coord(qz + pad, oz, inv2, fnz);
+            const float rm = pad + 1e-3f * fcell;          // cull margin covers the rounding of the binning
+            const float rm2 = rm * rm;
+            int cnext[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) cnext[t] = __ldg(p.g.fine_of + 32 * t + lane);   // padded by 128 entries of -1
+            for (int j0 = 0; j0 < P; j0 += 128) {
+                const unsigned pending = __ballot_sync(NF_FULL, !done);
+                if (!pending) break;
+                const int npend = __popc(pending);
+                if (npend * 3 <= built_for || built_for == 0) {
+                    // (re)build the bitmap: fine cells whose box comes within reach of an unfinished lane
+                    __syncwarp();
+                    for (int w = lane; w < BM_WORDS; w += 32) bm[w] = 0u;
+                    __syncwarp();
+                    if (!done) {
+                        for (int cz = floz; cz <= fhiz; ++cz) {
+                            const float bz = oz + (float)cz * fcell;
+                            const float dz = fmaxf(fmaxf(bz - qz, qz - (bz + fcell)), 0.f);
+                            // clamped boundary cells also hold everything beyond them: never cull those
+                            const bool ez = (cz == 0) || (cz == fnz - 1);
+                            for (int cy = floy; cy <= fhiy; ++cy) {
+                                const float by = oy + (float)cy * fcell;
+                                const float dy = fmaxf(fmaxf(by - qy, qy - (by + fcell)), 0.f);
+                                const bool ey = ez || (cy == 0) || (cy == fny - 1);
+                                const float dzy = dz * dz + dy * dy;
+                                for (int cx = flox; cx <= fhix; ++cx) {
+                                    const float bx = ox + (float)cx * fcell;
+                                    const float dx = fmaxf(fmaxf(bx - qx, qx - (bx + fcell)), 0.f);
+                                    const bool e = ey || (cx == 0) || (cx == fnx - 1);
+                                    if (e || dzy + dx * dx < rm2) {
+                                        const int c = (cz * fny + cy) * fnx + cx;
+                                        atomicOr(&bm[(c & (BM_BITS - 1)) >> 5], 1u << (c & 31));
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    built_for = npend;
+                    ++qs.n_rows;      // statistics: bitmap rebuilds
+                }
+                ++qs.it_lock;
+                // this step's cell ids were prefetched; fetch the next step's while we work
+                int c[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) c[t] = cnext[t];
+                if (j0 + 128 < P) {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) cnext[t] = __ldg(p.g.fine_of + j0 + 128 + 32 * t + lane);
+                }
+                // lanes whose particle passes the bitmap fetch it themselves: coalesced, 4 loads in flight
+                float4 pp[4];
+                bool inb[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    inb[t] = (c[t] >= 0) && ((bm[(c[t] & (BM_BITS - 1)) >> 5] >> (c[t] & 31)) & 1u);
+                    pp[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (inb[t]) pp[t] = __ldg(p.g.orig4 + j0 + 32 * t + lane);
+                }
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    unsigned m = __ballot_sync(NF_FULL, inb[t]);
+                    while (m) {
+                        const int b = __ffs(m) - 1;
+                        m &= m - 1;
+                        const float cx = __shfl_sync(NF_FULL, pp[t].x, b);
+                        const float cy = __shfl_sync(NF_FULL, pp[t].y, b);
+                        const float cz = __shfl_sync(NF_FULL, pp[t].z, b);
+                        ++qs.it_rows;     // statistics: candidates tested
+                        if (!done && dist2_exact(qx, qy, qz, cx, cy, cz) < r2) {
+                            sel[cnt * 32 + lane] = j0 + 32 * t + b;
+                            ++cnt;
+                            done = cnt >= K;
+                        }
+                    }
+                }
+            }
+        }
+        // ---- per-lane local geometry over the selected neighbours (ascending index, like the reference);
+        //      one pass: var = (sum v^2 - 2 mean sum v + n mean^2) / n  ==  sum (v - mean)^2 / n
+        float wsum = 0.f, wx = 0.f, wy = 0.f, wz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f, ux = 0.f, uy = 0.f, uz = 0.f;
+        int nvalid = 0;
+#pragma unroll 4
+        for (int k = 0; k < K; ++k) {
+            if (k < cnt) {
+                const float4 pp = __ldg(p.g.orig4 + sel[k * 32 + lane]);
+                const float ex = pp.x - qx, ey = pp.y - qy, ez = pp.z - qz;
+                const float t = sqrtf(ex * ex + ey * ey + ez * ez) / radius;
+                const float w = fmaxf(1.0f - t * t * t, 0.f);
+                wsum += w; wx += w * pp.x; wy += w * pp.y; wz += w * pp.z;
+                if (dist2_exact(qx, qy, qz, pp.x, pp.y, pp.z) != 0.f) {
+                    vx += ex; vy += ey; vz += ez;
+                    ux += ex * ex; uy += ey * ey; uz += ez * ez;
+                    ++nvalid;
+                }
+            }
+        }
+        if (cnt < K) {   // padded slots are zeros = a phantom particle at the origin (models/renderer.py:97-98)
+            const float t = sqrtf(qx * qx + qy * qy + qz * qz) / radius;
+            wsum += (float)(K - cnt) * fmaxf(1.0f - t * t * t, 0.f);
+        }
+        const float nvf = (float)nvalid + 1e-12f;
+        const float mx = vx / nvf, my = vy / nvf, mz = vz / nvf;
+        const float ax = fmaxf(ux - 2.0f * mx * vx + (float)nvalid * mx * mx, 0.f);
+        const float ay = fmaxf(uy - 2.0f * my * vy + (float)nvalid * my * my, 0.f);
+        const float az = fmaxf(uz - 2.0f * mz * vz + (float)nvalid * mz * mz, 0.f);
+        const bool full = in && (nvalid == K);
+        const unsigned fb = __ballot_sync(NF_FULL, full);
+        if (num_nn && in) num_nn[(size_t)sample_base + s] = nvalid;
+        if (lane == 0) act[(size_t)ray * act_stride + slot] = fb;
+        n_active += __popc(fb);
+        const bool eval = want && (p.use_mask ? full : true);
+        const unsigned me = __ballot_sync(NF_FULL, eval);
+        if (me) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(row_counter, __popc(me));
+            base = __shfl_sync(NF_FULL, base, 0);
+            const int row = base + __popc(me & lt);
+            if (eval && row < cap) {
+                const float den = wsum + 1e-12f;
+                const float sx = wx / den, sy = wy / den, sz = wz / den;
+                const float tx = sx - p.ro[0], ty = sy - p.ro[1], tz = sz - p.ro[2];
+                const float tn = sqrtf(tx * tx + ty * ty + tz * tz);
+                float4* dst = reinterpret_cast<float4*>(rec + (size_t)row * 16);
+                dst[0] = make_float4(qx, qy, qz, wsum);
+                dst[1] = make_float4(sx, sy, sz, ax / nvf);
+                dst[2] = make_float4(ay / nvf, az / nvf, d[0], d[1]);
+                dst[3] = make_float4(d[2], tx / tn, ty / tn, tz / tn);
+                rowid[row] = sample_base + s;
             }
         }
     }
@@ -236,6 +437,7 @@ __device__ __forceinline__ void store_counts(long long* num_nn, unsigned* act, i
 // ------------------------------------------------------------------------------------------------
 template <int NS0>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_stage_q0(const StageArgs p) {
+    __shared__ int sm_hits[WARPS_PER_BLOCK][HITBUF];
     const int lane = threadIdx.x & 31;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     RowAlloc ra;
@@ -246,8 +448,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_stage_q0(const StageAr
         for (int slot = 0; slot < NS0; ++slot) z[slot] = __ldg(p.z_coarse + min(slot * 32 + lane, p.S0 - 1));
         unsigned fullbits[NS0];
         int cnt[NS0];
+        QueryStats qs;
         ray_query<NS0>(p, lane, o, d, z, p.S0, ra, p.rec0, p.rowid0, p.counters + 0, p.counters + 2, p.cap0,
-                       ray * p.S0, fullbits, cnt);
+                       ray * p.S0, fullbits, cnt, qs, sm_hits[threadIdx.x >> 5]);
         store_counts<NS0>(p.num_nn0, p.act0, ray, p.S0, lane, cnt, fullbits);
     }
     ra.flush(p.rowid0, p.cap0, lane);
@@ -256,20 +459,26 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_stage_q0(const StageAr
 // ------------------------------------------------------------------------------------------------
 // stage MID
 // ------------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t mid_smem_per_warp(int ns0, int ns1, int K) {
+    return (size_t)(4 * ns0 * 32 + 2 * ns1 * 32) * sizeof(float) + BM_WORDS * sizeof(unsigned) + (size_t)K * 32 * sizeof(int);
+}
+
 template <int NS0, int NS1>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_stage_mid(const StageArgs p) {
-    __shared__ float sm_z0[WARPS_PER_BLOCK][NS0 * 32];
-    __shared__ float sm_w[WARPS_PER_BLOCK][NS0 * 32];      // coarse weights, later the importance samples
-    __shared__ float sm_bins[WARPS_PER_BLOCK][NS0 * 32];
-    __shared__ float sm_cdf[WARPS_PER_BLOCK][NS0 * 32];
-    __shared__ float sm_smp[WARPS_PER_BLOCK][NS1 * 32];
-    __shared__ float sm_z1[WARPS_PER_BLOCK][NS1 * 32];
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int S0 = p.S0, S1 = p.S1, NI = p.n_imp;
-    float* z0s = sm_z0[wib]; float* ws = sm_w[wib]; float* bins = sm_bins[wib]; float* cdf = sm_cdf[wib];
-    float* smp = sm_smp[wib]; float* z1s = sm_z1[wib];
-    RowAlloc ra;
+    float* base = reinterpret_cast<float*>(dyn_smem + wib * mid_smem_per_warp(NS0, NS1, p.K));
+    float* z0s = base;                   // coarse depths
+    float* ws = z0s + NS0 * 32;          // coarse weights
+    float* bins = ws + NS0 * 32;
+    float* cdf = bins + NS0 * 32;
+    float* smp = cdf + NS0 * 32;         // importance samples
+    float* z1s = smp + NS1 * 32;         // merged depths
+    unsigned* bm = reinterpret_cast<unsigned*>(z1s + NS1 * 32);
+    int* sel = reinterpret_cast<int*>(bm + BM_WORDS);
+    QueryStats qs;
     for (int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ray < p.n_rays; ray += nwarps) {
         float o[3], d[3], z0[NS0], w0[NS0];
         float4 c0[NS0];
@@ -378,20 +587,17 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_stage_mid(const StageA
             }
         }
         __syncwarp();
-        float z1[NS1];
-#pragma unroll
-        for (int slot = 0; slot < NS1; ++slot) {
-            const int s = slot * 32 + lane;
-            z1[slot] = z1s[min(s, S1 - 1)];
-            if (s < S1) p.z1[(size_t)ray * S1 + s] = z1[slot];
-        }
-        unsigned fullbits[NS1];
-        int cnt[NS1];
-        ray_query<NS1>(p, lane, o, d, z1, S1, ra, p.rec1, p.rowid1, p.counters + 1, p.counters + 3, p.cap1,
-                       ray * S1, fullbits, cnt);
-        store_counts<NS1>(p.num_nn1, p.act1, ray, S1, lane, cnt, fullbits);
+        for (int s = lane; s < S1; s += 32) p.z1[(size_t)ray * S1 + s] = z1s[s];
+        ray_query_group(p, lane, o, d, z1s, S1, p.rec1, p.rowid1, p.counters + 1, p.counters + 3, p.cap1, ray,
+                        p.num_nn1, p.act1, NS1, qs, bm, sel);
+        __syncwarp();
     }
-    ra.flush(p.rowid1, p.cap1, lane);
+    if (lane == 0) {
+        atomicAdd(p.counters + 4, qs.n_lock);
+        atomicAdd(p.counters + 5, qs.n_rows);
+        atomicAdd(p.counters + 6, qs.it_lock >> 6);
+        atomicAdd(p.counters + 7, qs.it_rows >> 6);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -473,16 +679,27 @@ static WsLayout ws_layout(int R, int S0, int NI) {
     return L;
 }
 
+template <int NS0, int NS1>
+static int launch_mid2(int grid, const StageArgs& p, cudaStream_t st) {
+    const size_t smem = WARPS_PER_BLOCK * mid_smem_per_warp(NS0, NS1, p.K);
+    static size_t configured = 0;
+    if (smem > configured) {
+        NF_CUDA_OK(cudaFuncSetAttribute(k_stage_mid<NS0, NS1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    k_stage_mid<NS0, NS1><<<grid, WARPS_PER_BLOCK * 32, smem, st>>>(p);
+    NF_LAUNCH_OK();
+    return NF_OK;
+}
+
 template <int NS0>
 static int launch_mid(int ns1, int grid, const StageArgs& p, cudaStream_t st) {
     switch (ns1) {
-        case 4: k_stage_mid<NS0, 4><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(p); break;
-        case 6: k_stage_mid<NS0, 6><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(p); break;
-        case 8: k_stage_mid<NS0, 8><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(p); break;
+        case 4: return launch_mid2<NS0, 4>(grid, p, st);
+        case 6: return launch_mid2<NS0, 6>(grid, p, st);
+        case 8: return launch_mid2<NS0, 8>(grid, p, st);
         default: set_error("unsupported fine sample count"); return NF_E_UNSUPPORTED;
     }
-    NF_LAUNCH_OK();
-    return NF_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -565,7 +782,7 @@ extern "C" int nf_render_forward(const nf_render_args* a, void* stream_) {
                a->workspace_bytes, L.total);
     char* b = (char*)a->workspace;
     StageArgs p;
-    p.g = grid_view(a->grid_ws);
+    p.g = grid_view(a->grid_ws, a->n_particles);
     p.particles = a->particles;
     p.rays = a->rays;
     p.n_rays = a->n_rays;
@@ -573,6 +790,10 @@ extern "C" int nf_render_forward(const nf_render_args* a, void* stream_) {
     p.radius = a->radius;
     p.K = a->K;
     p.use_mask = a->use_mask; p.white_bg = a->white_background; p.mode = a->mode;
+    {
+        const char* e = getenv("NF_LOCKSTEP_MIN_OCC");
+        p.lockstep_min_occ = e ? atoi(e) : LOCKSTEP_MIN_OCC;
+    }
     p.z_coarse = a->z_coarse; p.u_imp = a->u_importance;
     p.S0 = a->n_coarse; p.n_imp = NI; p.S1 = a->n_coarse + NI;
     const bool want0 = a->mode != NF_RENDER_FINE;
@@ -631,6 +852,6 @@ extern "C" int nf_render_forward(const nf_render_args* a, void* stream_) {
         NF_LAUNCH_OK();
         tm.mark();
     }
-    if (a->stats) NF_CUDA_OK(cudaMemcpyAsync(a->stats, p.counters, 16, cudaMemcpyDeviceToDevice, st));
+    if (a->stats) NF_CUDA_OK(cudaMemcpyAsync(a->stats, p.counters, 32, cudaMemcpyDeviceToDevice, st));
     return NF_OK;
 }

@@ -36,10 +36,12 @@ def ball_query(queries: torch.Tensor, points: torch.Tensor, K: int, radius: floa
     nq = q.shape[0]
     idx = torch.empty((nq, K), dtype=torch.int32, device=q.device)
     cnt = torch.empty((nq,), dtype=torch.int32, device=q.device)
-    check(lib().nf_ballquery_firstk(ptr(grid.ws), ptr(q), nq, float(radius), int(K), ptr(idx), ptr(cnt), stream_ptr()),
+    check(lib().nf_ballquery_firstk(ptr(grid.ws), grid.n, ptr(q), nq, float(radius), int(K), ptr(idx), ptr(cnt), stream_ptr()),
           "nf_ballquery_firstk")
     idx64 = idx.to(torch.int64)
     valid = idx64 >= 0
+    if grid.n == 0:
+        return torch.zeros((nq, K), device=q.device), idx64, torch.zeros((nq, K, 3), device=q.device)
     nn = grid.points[idx64.clamp(min=0)] * valid.unsqueeze(-1)
     diff = q.unsqueeze(1) - nn
     sq = diff * diff
