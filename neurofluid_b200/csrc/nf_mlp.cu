@@ -238,6 +238,8 @@ __device__ __forceinline__ void emit_encoding(RowWriter<BF16>& w, const float* v
 
 __device__ __forceinline__ int layer_pe_steps(int l) { return (l == 0 || l == 4) ? KX_STEPS : (l == 9 ? KD_STEPS : 0); }
 
+#define NF_TRACE(slot) do { if (a.trace && blockIdx.x == 0 && ti == 2) a.trace[(slot)] = clock64(); } while (0)
+
 template <bool BF16>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp(const KernelArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -294,6 +296,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp(const KernelArgs a)
                     const uint32_t b_lbo = a.desc_swap ? 128u : (uint32_t)n * 16u;
                     const uint32_t b_sbo = a.desc_swap ? (uint32_t)n * 16u : 128u;
                     uint32_t acc = 0;
+                    NF_TRACE(100 + l * 8);
                     const int npe = layer_pe_steps(l);
                     if (npe) {
                         uint32_t abase;
@@ -321,6 +324,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp(const KernelArgs a)
                             if ((j & 3) == 0) {
                                 mbar_wait(bar(B_ACT_READY + (j >> 2)), hidw & 1);
                                 tc_fence_after();
+                                NF_TRACE(100 + l * 8 + 1 + (j >> 2));
                             }
                             mbar_wait(bar(B_WFULL + ws), wph);
                             tc_fence_after();
@@ -333,6 +337,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp(const KernelArgs a)
                         ++hidw;
                     }
                     umma_commit(bar(B_ACC_FULL + (lc & 1)));
+                    NF_TRACE(100 + l * 8 + 5);
                     if (l == 9) umma_commit(bar(B_PEDIR_FREE + (ti & 1)));
                 }
             }
@@ -358,13 +363,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp(const KernelArgs a)
         // ================================================================ epilogue (thread = row)
         const int tr = threadIdx.x;  // 0..127
         uint32_t lc = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int ti = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
             const int row = tile * TILE_M + tr;
             float sigma = 0.f;
             for (int l = 0; l < nl; ++l, ++lc) {
                 const uint32_t buf = lc & 1;
                 mbar_wait(bar(B_ACC_FULL + buf), (lc >> 1) & 1);
                 tc_fence_after();
+                if (tr == 0) NF_TRACE(l * 8);
                 const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 256;
                 if (l < 9) {
                     const bool writes = (l + 1 < nl);
@@ -411,6 +418,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp(const KernelArgs a)
                             tc_fence_before();
                             mbar_arrive(bar(B_ACT_READY + c));
                         }
+                        if (tr == 0) NF_TRACE(l * 8 + 1 + c);
                     }
                     if (l == 7) {
                         sigma += sp[SP_BSIG];
@@ -471,6 +479,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp(const KernelArgs a)
             }
             // xyz-like block: [PE10(x) 63 | PE4(density) 9 | PE10(smoothed) 63 | PE10(variance) 63 | 0 x10]
             mbar_wait(bar(B_PEXYZ_FREE), (ti & 1) ^ 1);
+            if (tp == 0) NF_TRACE(300);
             {
                 RowWriter<BF16> w;
                 w.base = s_pexyz + (uint32_t)tp * 16;
@@ -482,6 +491,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp(const KernelArgs a)
             }
             fence_proxy_async();
             mbar_arrive(bar(B_PEXYZ_READY));
+            if (tp == 0) NF_TRACE(301);
             if (nl == 10) {
                 // dir-like block: [PE4(ray dir) 27 | PE4(smoothed dir) 27 | 0 x10]
                 mbar_wait(bar(B_PEDIR_FREE + (ti & 1)), ((ti >> 1) & 1) ^ 1);
@@ -492,6 +502,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp(const KernelArgs a)
                 static_for<54, 64>([&](auto ci) { w.template put<decltype(ci)::value>(0.f); });
                 fence_proxy_async();
                 mbar_arrive(bar(B_PEDIR_READY + (ti & 1)));
+                if (tp == 0) NF_TRACE(302);
             }
         }
     }
@@ -636,5 +647,6 @@ extern "C" int nf_nerf_mlp_forward(const void* packed, int dtype, const float* r
     a.n_layers = sigma_only ? 8 : 10;
     a.desc_swap = env_int("NF_MLP_DESC_SWAP", 0);
     a.out4 = (float4*)out;
+    a.trace = (long long*)(uintptr_t)strtoull(getenv("NF_MLP_TRACE_PTR") ? getenv("NF_MLP_TRACE_PTR") : "0", nullptr, 0);
     return mlp::launch(a, dtype, st);
 }

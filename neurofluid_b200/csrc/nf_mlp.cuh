@@ -20,6 +20,7 @@ struct KernelArgs {
     int n_layers;            // 10 = full net, 8 = sigma only
     int desc_swap;           // debug: swap LBO/SBO
     float4* out4;
+    long long* trace;        // debug: per-role clock64 timeline of one tile of CTA 0 (NULL = off)
 };
 
 

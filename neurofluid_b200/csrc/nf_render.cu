@@ -10,16 +10,15 @@
 //   sample_pdf / ImportanceSampling  utils/ray_utils.py:178-229
 //   RenderNet.forward / coarse_rendering / fine_rendering   models/renderer.py:211-369
 //
-// One warp owns one ray.  Sample s of a ray lives in lane s%32, register slot s/32, so all per-ray
-// state (depths, weights, counts) stays in registers and the along-ray products are warp scans.
+// One warp owns one ray; inside a ray, sample s lives in lane s%32 of 32-sample step s/32.
 //
-// stage Q0 : coarse depths -> sample positions -> first-K ball query per non-empty sample ->
+// stage Q0 : coarse depths -> sample positions -> first-K ball query (group scan, see ray_query_group) ->
 //            num_nn, "all K slots valid" bitmask, and one 64-byte geometry record per evaluated sample
-//            appended to a compact list (rows are handed out to warps in blocks of 32).
+//            appended to a compact list (rows are handed out per 32-sample step: one atomic, no holes).
 // [MLP]    : nf_mlp.cu over the compact list -> (r,g,b,sigma) scattered to a dense per-sample array.
-// stage MID: alpha-composite the coarse samples (warp scan), emit rgb0/depth0/opacity0/mask_0, build
+// stage MID: alpha-composite the coarse samples (warp scans), emit rgb0/depth0/opacity0/mask_0, build
 //            the piecewise-constant pdf, draw the importance samples by inverse CDF, merge with the
-//            coarse depths (rank merge), then run the ball query again for the merged samples.
+//            coarse depths (rank merge in shared memory), then run the ball query for the merged samples.
 // [MLP]    : fine network.
 // stage FIN: alpha-composite the fine samples -> rgb1/depth1/opacity1/mask_1.
 #include <stdlib.h>
@@ -32,7 +31,6 @@ namespace nf {
 namespace render {
 
 constexpr int WARPS_PER_BLOCK = 8;
-constexpr int ROW_BLOCK = 32;
 
 struct StageArgs {
     GridView g;
@@ -62,123 +60,8 @@ struct StageArgs {
     float* rec1; int* rowid1; float4* out1; int cap1;
 };
 
-struct RowAlloc {
-    int cur = 0, left = 0;
-    __device__ __forceinline__ int take(int* counter, int lane) {
-        if (left == 0) {
-            int b = 0;
-            if (lane == 0) b = atomicAdd(counter, ROW_BLOCK);
-            cur = __shfl_sync(NF_FULL, b, 0);
-            left = ROW_BLOCK;
-        }
-        --left;
-        return cur++;
-    }
-    // unused rows of the last block become holes the MLP skips
-    __device__ __forceinline__ void flush(int* rowid, int cap, int lane) {
-        if (lane < left && cur + lane < cap) rowid[cur + lane] = -1;
-        left = 0;
-    }
-};
-
 // ------------------------------------------------------------------------------------------------
-// neighbour search + local geometry for all samples of one ray
-// ------------------------------------------------------------------------------------------------
-template <int NS>
-__device__ __forceinline__ void ray_query(const StageArgs& p, int lane, const float (&o)[3], const float (&d)[3],
-                                          const float (&z)[NS], int S, RowAlloc& ra, float* rec, int* rowid,
-                                          int* row_counter, int* active_counter, int cap, int sample_base,
-                                          unsigned (&fullbits)[NS], int (&cnt)[NS], QueryStats& qs, int* hitbuf) {
-    float px[NS], py[NS], pz[NS];
-    int occ[NS];
-    unsigned nonempty[NS], todo[NS];
-    const int K = p.K;
-    const float radius = p.radius;
-#pragma unroll
-    for (int slot = 0; slot < NS; ++slot) {
-        const int s = slot * 32 + lane;
-        // xyz = o + d * z, rounded like the eager torch expression (mul, then add)
-        px[slot] = __fadd_rn(o[0], __fmul_rn(d[0], z[slot]));
-        py[slot] = __fadd_rn(o[1], __fmul_rn(d[1], z[slot]));
-        pz[slot] = __fadd_rn(o[2], __fmul_rn(d[2], z[slot]));
-        const bool in = s < S;
-        occ[slot] = in ? grid_occupancy(p.g, px[slot], py[slot], pz[slot], radius) : 0;
-        nonempty[slot] = __ballot_sync(NF_FULL, occ[slot] > 0);
-        todo[slot] = p.use_mask ? nonempty[slot] : __ballot_sync(NF_FULL, in);
-        cnt[slot] = 0;
-        fullbits[slot] = 0u;
-    }
-    int n_active = 0;
-#pragma unroll
-    for (int slot = 0; slot < NS; ++slot) {
-        unsigned m = todo[slot];
-        while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const float qx = __shfl_sync(NF_FULL, px[slot], src);
-            const float qy = __shfl_sync(NF_FULL, py[slot], src);
-            const float qz = __shfl_sync(NF_FULL, pz[slot], src);
-            const int qocc = __shfl_sync(NF_FULL, occ[slot], src);
-            int best = 0x7fffffff, nsel = 0;
-            if (qocc > 0) nsel = warp_first_k(p.g, qx, qy, qz, radius, K, lane, best, qocc, p.lockstep_min_occ, qs, hitbuf);
-            const bool sel = lane < nsel;
-            float nx = 0.f, ny = 0.f, nz = 0.f, d2 = 0.f;
-            if (sel) {
-                nx = __ldg(p.particles + 3 * (size_t)best);
-                ny = __ldg(p.particles + 3 * (size_t)best + 1);
-                nz = __ldg(p.particles + 3 * (size_t)best + 2);
-                d2 = dist2_exact(qx, qy, qz, nx, ny, nz);
-            }
-            // nn_mask = dists.ne(0): a real neighbour at exactly zero distance counts as padding
-            const bool valid = sel && (d2 != 0.f);
-            const int nvalid = __popc(__ballot_sync(NF_FULL, valid));
-            const bool full = (nvalid == K);
-            if (lane == src) cnt[slot] = nvalid;
-            if (full) { fullbits[slot] |= 1u << src; ++n_active; }
-            if (p.use_mask && !full) continue;
-
-            // ---- smoothing_position: every one of the K slots takes part; padded slots are zeros
-            float w = 0.f, wx = 0.f, wy = 0.f, wz = 0.f;
-            if (lane < K) {
-                const float ex = nx - qx, ey = ny - qy, ez = nz - qz;   // nx..nz are 0 on padded slots
-                const float dist = sqrtf(ex * ex + ey * ey + ez * ez);
-                const float t = dist / radius;
-                w = fmaxf(1.0f - t * t * t, 0.f);
-                wx = w * nx; wy = w * ny; wz = w * nz;
-            }
-            const float density = warp_sum(w);
-            const float den = density + 1e-12f;
-            const float sx = warp_sum(wx) / den, sy = warp_sum(wy) / den, sz = warp_sum(wz) / den;
-            // ---- variance of the valid neighbour offsets (two pass)
-            const float nvf = (float)nvalid + 1e-12f;
-            const float vx = valid ? nx - qx : 0.f, vy = valid ? ny - qy : 0.f, vz = valid ? nz - qz : 0.f;
-            const float mx = warp_sum(vx) / nvf, my = warp_sum(vy) / nvf, mz = warp_sum(vz) / nvf;
-            const float ax = valid ? (vx - mx) * (vx - mx) : 0.f;
-            const float ay = valid ? (vy - my) * (vy - my) : 0.f;
-            const float az = valid ? (vz - mz) * (vz - mz) : 0.f;
-            const float varx = warp_sum(ax) / nvf, vary = warp_sum(ay) / nvf, varz = warp_sum(az) / nvf;
-            // ---- direction from the camera to the smoothed position
-            const float tx = sx - p.ro[0], ty = sy - p.ro[1], tz = sz - p.ro[2];
-            const float tn = sqrtf(tx * tx + ty * ty + tz * tz);
-            const int row = ra.take(row_counter, lane);
-            if (row < cap) {
-                if (lane < 4) {
-                    float4 v;
-                    if (lane == 0) v = make_float4(qx, qy, qz, density);
-                    else if (lane == 1) v = make_float4(sx, sy, sz, varx);
-                    else if (lane == 2) v = make_float4(vary, varz, d[0], d[1]);
-                    else v = make_float4(d[2], tx / tn, ty / tn, tz / tn);
-                    reinterpret_cast<float4*>(rec + (size_t)row * 16)[lane] = v;
-                }
-                if (lane == 0) rowid[row] = sample_base + slot * 32 + src;
-            }
-        }
-    }
-    if (lane == 0 && n_active) atomicAdd(active_counter, n_active);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Group flavour of the neighbour search (used by the fine pass): one LANE per sample, 32 consecutive
+// Neighbour search + local geometry for all samples of one ray: one LANE per sample, 32 consecutive
 // samples of the ray per step.  The first-K-by-index rule means "scan the particles in original index
 // order and keep the first K inside the ball", so that is what the warp does -- but it only looks at
 // particles whose grid cell can matter to a still-unfinished lane: a per-warp 8192-bit cell bitmap
@@ -421,39 +304,30 @@ __device__ __forceinline__ void load_ray(const float* rays, int ray, float (&o)[
     d[0] = __ldg(r + 3); d[1] = __ldg(r + 4); d[2] = __ldg(r + 5);
 }
 
-template <int NS>
-__device__ __forceinline__ void store_counts(long long* num_nn, unsigned* act, int ray, int S, int lane,
-                                             const int (&cnt)[NS], const unsigned (&fullbits)[NS]) {
-#pragma unroll
-    for (int slot = 0; slot < NS; ++slot) {
-        const int s = slot * 32 + lane;
-        if (num_nn && s < S) num_nn[(size_t)ray * S + s] = cnt[slot];
-        if (lane == 0) act[(size_t)ray * NS + slot] = fullbits[slot];
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // stage Q0
 // ------------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t q0_smem_per_warp(int K) {
+    return BM_WORDS * sizeof(unsigned) + (size_t)K * 32 * sizeof(int);
+}
+
 template <int NS0>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_stage_q0(const StageArgs p) {
-    __shared__ int sm_hits[WARPS_PER_BLOCK][HITBUF];
-    const int lane = threadIdx.x & 31;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ float sm_z[NS0 * 32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    RowAlloc ra;
+    for (int s = threadIdx.x; s < p.S0; s += blockDim.x) sm_z[s] = __ldg(p.z_coarse + s);
+    __syncthreads();
+    unsigned* bm = reinterpret_cast<unsigned*>(dyn_smem + wib * q0_smem_per_warp(p.K));
+    int* sel = reinterpret_cast<int*>(bm + BM_WORDS);
+    QueryStats qs;
     for (int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ray < p.n_rays; ray += nwarps) {
-        float o[3], d[3], z[NS0];
+        float o[3], d[3];
         load_ray(p.rays, ray, o, d);
-#pragma unroll
-        for (int slot = 0; slot < NS0; ++slot) z[slot] = __ldg(p.z_coarse + min(slot * 32 + lane, p.S0 - 1));
-        unsigned fullbits[NS0];
-        int cnt[NS0];
-        QueryStats qs;
-        ray_query<NS0>(p, lane, o, d, z, p.S0, ra, p.rec0, p.rowid0, p.counters + 0, p.counters + 2, p.cap0,
-                       ray * p.S0, fullbits, cnt, qs, sm_hits[threadIdx.x >> 5]);
-        store_counts<NS0>(p.num_nn0, p.act0, ray, p.S0, lane, cnt, fullbits);
+        ray_query_group(p, lane, o, d, sm_z, p.S0, p.rec0, p.rowid0, p.counters + 0, p.counters + 2, p.cap0, ray,
+                        p.num_nn0, p.act0, NS0, qs, bm, sel);
     }
-    ra.flush(p.rowid0, p.cap0, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -645,8 +519,6 @@ struct WsLayout {
     int cap0, cap1, ns0, ns1;
 };
 
-static int max_stage_warps() { return num_sms() * 8 * WARPS_PER_BLOCK; }
-
 static int pick_ns(int s, const int* opts, int n) {
     for (int i = 0; i < n; ++i)
         if (s <= opts[i] * 32) return opts[i];
@@ -660,9 +532,8 @@ static WsLayout ws_layout(int R, int S0, int NI) {
     static const int o1[] = {4, 6, 8};
     L.ns0 = pick_ns(S0, o0, 2);
     L.ns1 = NI > 0 ? pick_ns(S1, o1, 3) : 4;
-    const size_t slack = (size_t)ROW_BLOCK * max_stage_warps();
-    L.cap0 = (int)((size_t)R * S0 + slack);
-    L.cap1 = (int)((size_t)R * S1 + slack);
+    L.cap0 = (int)((size_t)R * S0);
+    L.cap1 = (int)((size_t)R * S1);
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 256); return r; };
     L.counters = take(64);
@@ -814,9 +685,18 @@ extern "C" int nf_render_forward(const nf_render_args* a, void* stream_) {
 
     StageTimer tm(st);
     // ---- stage Q0
-    if (L.ns0 == 2) k_stage_q0<2><<<grid, threads, 0, st>>>(p);
-    else k_stage_q0<4><<<grid, threads, 0, st>>>(p);
-    NF_LAUNCH_OK();
+    {
+        const size_t smem = WARPS_PER_BLOCK * q0_smem_per_warp(p.K);
+        static size_t configured = 0;
+        if (smem > configured) {
+            NF_CUDA_OK(cudaFuncSetAttribute(k_stage_q0<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            NF_CUDA_OK(cudaFuncSetAttribute(k_stage_q0<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        if (L.ns0 == 2) k_stage_q0<2><<<grid, threads, smem, st>>>(p);
+        else k_stage_q0<4><<<grid, threads, smem, st>>>(p);
+        NF_LAUNCH_OK();
+    }
     tm.mark();
     // ---- coarse network
     mlp::KernelArgs m;
@@ -824,6 +704,7 @@ extern "C" int nf_render_forward(const nf_render_args* a, void* stream_) {
     m.records = p.rec0; m.rowid = p.rowid0; m.n_rows_dev = p.counters + 0; m.n_rows_host = 0; m.n_rows_cap = L.cap0;
     m.n_layers = (a->mode == NF_RENDER_FINE) ? 8 : 10;
     m.desc_swap = 0;
+    m.trace = nullptr;
     m.out4 = p.out0;
     int rc = mlp::launch(m, a->dtype, st);
     if (rc != NF_OK) return rc;
