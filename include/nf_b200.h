@@ -192,18 +192,18 @@ typedef struct nf_transition_args {
        layer; rows outside the shard must be supplied by the caller between layers (see
        neurofluid_b200/distributed.py).  Single GPU: 0, n_fluid. */
     int32_t shard_begin, shard_end;
-    int32_t phase; /* -1: whole step;  >=0: run only phase `phase` (see nf_transition_num_phases) */
+    int32_t phase; /* -1: whole step on all particles;  0..4: run only that phase on [shard_begin, shard_end):
+                      0 integrate + grids + neighbour lists + layer 0,  1..3 conv layers,  4 position update.
+                      Between phases the caller all-gathers the layer outputs (nf_transition_layer_buffer). */
 } nf_transition_args;
 
 NF_API int nf_transition_num_phases(void);
 NF_API int nf_transition_step(const nf_transition_args* args, void* stream);
-
-/* One ContinuousConv layer on its own (parity / debug entry point): fp32 in/out.
- * kernel (4,4,4,cin,cout), bias (cout) or NULL.  counts_out (n_out) int32 may be NULL. */
-NF_API size_t nf_cconv_workspace_bytes(int n_in, int n_out, int cin, int cout);
-NF_API int nf_cconv_forward(const float* in_pos, const float* in_feat, int n_in, int cin, const float* out_pos, int n_out,
-                     float extent, const float* kernel, const float* bias, int cout, int ignore_same_pos, int dtype,
-                     float* out, int32_t* counts_out, void* workspace, size_t workspace_bytes, void* stream);
+/* Location of layer `layer`'s activation matrix (the ReLU'd fp16/bf16 rows the next layer gathers from)
+ * inside a transition workspace: *offset_bytes from the workspace base, *row_bytes per particle.
+ * layer 0: 96 channels, 1 and 2: 64 channels.  Used by the sharded execution to all-gather rows. */
+NF_API int nf_transition_layer_buffer(int n_fluid, int n_box, int layer, size_t* offset_bytes_host,
+                                      size_t* row_bytes_host);
 
 #ifdef __cplusplus
 }

@@ -64,9 +64,7 @@ SIGNATURES = {
     "nf_transition_workspace_bytes": (_sz, [C.c_int, C.c_int]),
     "nf_transition_num_phases": (C.c_int, []),
     "nf_transition_step": (C.c_int, [C.POINTER(TransitionArgs), _vp]),
-    "nf_cconv_workspace_bytes": (_sz, [C.c_int, C.c_int, C.c_int, C.c_int]),
-    "nf_cconv_forward": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int, _f32, _vp, _vp, C.c_int, C.c_int,
-                                    C.c_int, _vp, _vp, _vp, _sz, _vp]),
+    "nf_transition_layer_buffer": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(_sz), C.POINTER(_sz)]),
 }
 
 _lib = None

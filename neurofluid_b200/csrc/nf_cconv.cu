@@ -1,14 +1,837 @@
-// nf_cconv.cu -- transition model kernels (placeholder until the ContinuousConv path lands)
+// nf_cconv.cu -- Lagrangian transition model (hot path 2) on sm_100a.
+//
+// replaces (reference file:line):
+//   ParticleNet.integrate_pos_vel / update_pos_vel      models/transmodel.py:100-104, 144-148
+//   ParticleNet.compute_pose_correction                 models/transmodel.py:106-142
+//     open3d.ml.torch.layers.ContinuousConv.forward x5  (:116, :118, :125)  incl. FixedRadiusSearch,
+//       ball_to_cube_volume_preserving mapping, trilinear 4x4x4 filter interpolation, poly6 window
+//     nn.Linear x4                                      (:117, :126)
+//     ml3d.ops.reduce_subarrays_sum                     (:135-138)  -> neighbour count per particle
+//
+// Structure of one step (all on one stream, no host sync):
+//   k_integrate        gravity half step                                   (N threads)
+//   nf_grid_build      cell-sorted grid of the new positions (+ of the box points)
+//   k_nbr_build        one warp per fluid particle: radius search in the 27-cell block, and for every
+//                      neighbour the 8 trilinear corner (cell, weight*window) pairs of the 4^3 filter.
+//                      The fluid->fluid list is reused by conv0_fluid, conv1, conv2, conv3; the
+//                      fluid->box list by conv0_obstacle.  48-byte records, fixed stride per particle.
+//   k_layer0           conv0_obstacle + conv0_fluid + dense0_fluid (14k MAC/particle): fp32 on CUDA cores
+//   k_cconv_tc<CIN,COUT>  conv_l + dense_l (+ residual) for l = 1..3: per 128-particle tile, for each of the
+//                      16 (z,y) filter rows the (128 x 4*CIN) slab of the patch matrix is accumulated in
+//                      registers straight from the neighbour gather, written to shared memory as the fp16
+//                      A operand (UMMA K-major core-matrix layout) and contracted with the matching filter
+//                      slab by tcgen05.mma into one TMEM accumulator; the dense branch is a 17th slab; bias,
+//                      residual and ReLU happen in the TMEM epilogue.  The (N x 64*CIN) patch matrix never
+//                      exists in HBM.
+//   k_update           pos/vel update
+#include <stdlib.h>
+
 #include "nf_common.cuh"
+
+namespace nf {
+namespace cconv {
+
+constexpr int MAXNBR = 128;           // neighbour slots per particle (fixed stride)
+constexpr int FSIZE = 4;              // filter size per axis
+constexpr int NCELL = 64;
+
+struct __align__(16) Pair {
+    int j;                // neighbour index
+    unsigned char cell[8];  // (z*4+y)*4+x of the 8 trilinear corners
+    int pad;
+    float w[8];           // trilinear weight * window
+};
+static_assert(sizeof(Pair) == 48, "Pair layout");
+
+// ---------------------------------------------------------------- PTX wrappers (same as nf_mlp.cu)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+__device__ __forceinline__ uint32_t umma_idesc(int m, int n, bool bf16) {
+    const uint32_t fmt = bf16 ? 1u : 0u;
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+// filter geometry (open3d ContinuousConv: ball_to_cube_volume_preserving + linear interpolation,
+// align_corners=True)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sgnf(float v) { return (float)((v > 0.f) - (v < 0.f)); }
+
+__device__ __forceinline__ void ball_to_cube(float& X, float& Y, float& Z) {
+    const float sq = X * X + Y * Y + Z * Z;
+    const float n = sqrtf(sq);
+    if (sq < 1e-12f) { X = Y = Z = 0.f; return; }
+    const float xy2 = X * X + Y * Y;
+    if (1.25f * Z * Z > xy2) {
+        const float s = sqrtf(3.0f * n / (n + fabsf(Z)));
+        X *= s; Y *= s; Z = sgnf(Z) * n;
+    } else {
+        const float s = n / sqrtf(xy2);
+        X *= s; Y *= s; Z *= 1.5f;
+    }
+    const float nxy2 = X * X + Y * Y;
+    if (nxy2 < 1e-12f) {
+        X = 0.f; Y = 0.f;
+    } else {
+        const float nxy = sqrtf(nxy2);
+        const float four_over_pi = 1.2732395447351628f;
+        if (fabsf(Y) <= fabsf(X)) {
+            const float t = sgnf(X) * nxy;
+            Y = t * four_over_pi * atanf(Y / X);
+            X = t;
+        } else {
+            const float t = sgnf(Y) * nxy;
+            X = t * four_over_pi * atanf(X / Y);
+            Y = t;
+        }
+    }
+}
+
+__device__ __forceinline__ void filter_corners(float rx, float ry, float rz, float inv_radius, float window, Pair& p) {
+    float x = rx * inv_radius, y = ry * inv_radius, z = rz * inv_radius;
+    ball_to_cube(x, y, z);
+    const float c[3] = {x * 0.5f, y * 0.5f, z * 0.5f};
+    int i0[3], i1[3];
+    float f[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float t = (c[a] + 0.5f) * (float)(FSIZE - 1);
+        const float fl = floorf(t);
+        f[a] = t - fl;
+        i0[a] = min(max((int)fl, 0), FSIZE - 1);
+        i1[a] = min(max((int)fl + 1, 0), FSIZE - 1);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int bx = k & 1, by = (k >> 1) & 1, bz = (k >> 2) & 1;
+        const int ix = bx ? i1[0] : i0[0], iy = by ? i1[1] : i0[1], iz = bz ? i1[2] : i0[2];
+        p.cell[k] = (unsigned char)((iz * FSIZE + iy) * FSIZE + ix);
+        p.w[k] = window * (bx ? f[0] : 1.f - f[0]) * (by ? f[1] : 1.f - f[1]) * (bz ? f[2] : 1.f - f[2]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void k_integrate(const float* __restrict__ pos, const float* __restrict__ vel, int n, float gx, float gy,
+                            float gz, float dt, float* __restrict__ pos_new, float* __restrict__ vel_new) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * 3) return;
+    const int a = i % 3;
+    const float g = a == 0 ? gx : (a == 1 ? gy : gz);
+    const float v = vel[i];
+    const float vn = v + g * dt;                  // models/transmodel.py:102
+    vel_new[i] = vn;
+    pos_new[i] = pos[i] + (v + vn) / 2 * dt;      // :103
+}
+
+__global__ void k_update(const float* __restrict__ pos, const float* __restrict__ pos_new, const float* __restrict__ ans3,
+                         int ld3, int begin, int end, float dt, float* __restrict__ pos_out, float* __restrict__ vel_out,
+                         float* __restrict__ delta_out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = begin + t / 3, a = t % 3;
+    if (i >= end) return;
+    const float delta = ans3[(size_t)i * ld3 + a] * (1.0f / 128);   // :141
+    const float pc = pos_new[3 * i + a] + delta;                     // :146
+    pos_out[3 * i + a] = pc;
+    vel_out[3 * i + a] = (pc - pos[3 * i + a]) / dt;                 // :147
+    if (delta_out) delta_out[3 * i + a] = delta;
+}
+
+// ------------------------------------------------------------------------------------------------
+// neighbour lists: one warp per output particle, row-scan of the <= 9 (y,z) rows of its cell block.
+// d^2 <= r^2 (inclusive), points whose coordinates equal the query's are skipped (ignore_query_point).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_nbr_build(GridView g, const float* __restrict__ out_pos, int begin, int end,
+                                                   float radius, int ignore_same, int use_window,
+                                                   Pair* __restrict__ pairs, int* __restrict__ counts,
+                                                   float* __restrict__ counts_f, int* __restrict__ overflow) {
+    const int lane = threadIdx.x & 31;
+    const int i = begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (i >= end) return;
+    const GridHeader* h = g.hdr;
+    const float qx = out_pos[3 * i], qy = out_pos[3 * i + 1], qz = out_pos[3 * i + 2];
+    const float r2 = __fmul_rn(radius, radius);
+    const float inv_radius = 1.0f / radius;
+    const float pad = radius * 1.001f + 1e-6f;
+    const int nx = h->dim[0], ny = h->dim[1], nz = h->dim[2];
+    const float ox = h->origin[0], oy = h->origin[1], oz = h->origin[2], inv = h->inv_cell;
+    int n = 0;
+    if (h->n > 0) {
+        const int lox = cell_coord(qx - pad, ox, inv, nx), hix = cell_coord(qx + pad, ox, inv, nx);
+        const int loy = cell_coord(qy - pad, oy, inv, ny), hiy = cell_coord(qy + pad, oy, inv, ny);
+        const int loz = cell_coord(qz - pad, oz, inv, nz), hiz = cell_coord(qz + pad, oz, inv, nz);
+        const unsigned lt = (1u << lane) - 1u;
+        Pair* dst = pairs + (size_t)i * MAXNBR;
+        for (int z = loz; z <= hiz; ++z)
+            for (int y = loy; y <= hiy; ++y) {
+                const int row = (z * ny + y) * nx;
+                const int beg = __ldg(g.cell_start + row + lox), endc = __ldg(g.cell_start + row + hix + 1);
+                for (int base = beg; base < endc; base += 32) {
+                    const int t = base + lane;
+                    bool hit = false;
+                    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float d2 = 0.f;
+                    if (t < endc) {
+                        p = __ldg(g.sorted + t);
+                        const float dx = __fsub_rn(p.x, qx), dy = __fsub_rn(p.y, qy), dz = __fsub_rn(p.z, qz);
+                        d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                        hit = d2 <= r2;
+                        if (ignore_same && dx == 0.f && dy == 0.f && dz == 0.f) hit = false;
+                    }
+                    const unsigned m = __ballot_sync(NF_FULL, hit);
+                    if (hit) {
+                        const int slot = n + __popc(m & lt);
+                        if (slot < MAXNBR) {
+                            Pair pr;
+                            pr.j = __float_as_int(p.w);
+                            pr.pad = 0;
+                            float a = 1.f;
+                            if (use_window) {               // models/transmodel.py:73-77 on d^2 / r^2
+                                const float u = 1.0f - d2 / r2;
+                                a = fminf(fmaxf(u * u * u, 0.f), 1.f);
+                            }
+                            filter_corners(p.x - qx, p.y - qy, p.z - qz, inv_radius, a, pr);
+                            dst[slot] = pr;
+                        }
+                    }
+                    n += __popc(m);
+                }
+            }
+    }
+    if (lane == 0) {
+        if (n > MAXNBR) atomicAdd(overflow, 1);
+        counts[i] = min(n, MAXNBR);
+        if (counts_f) counts_f[i] = (float)n;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// layer 0: conv0_obstacle (3->32), conv0_fluid (4->32), dense0_fluid (4->32) -> ans0 (N,96) fp32 and
+// x0 = relu(ans0) as fp16/bf16.   One warp per particle, fp32 CUDA cores.
+// ------------------------------------------------------------------------------------------------
+struct Layer0Args {
+    const Pair* pairs_ff; const int* cnt_ff;
+    const Pair* pairs_fb; const int* cnt_fb;
+    const float* vel_new;        // (N,3): fluid feats = [1, vel]
+    const float* box_normals;    // (M,3)
+    const float* k_fluid;        // (64,4,32)
+    const float* b_fluid;        // (32)
+    const float* k_obst;         // (64,3,32)
+    const float* b_obst;         // (32)
+    const float* w_dense;        // (32,4)
+    const float* b_dense;        // (32)
+    float* ans0;                 // (N,96)
+    void* x0;                    // (N,96) half/bf16
+    int begin, end;
+    int bf16;
+};
+
+__global__ void __launch_bounds__(256) k_layer0(const Layer0Args a) {
+    __shared__ float sm_patch[8][NCELL * 4 + NCELL * 3];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int i = a.begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (i >= a.end) return;
+    float* pf = sm_patch[wib];
+    float* po = pf + NCELL * 4;
+    // lane owns cells 2*lane, 2*lane+1
+    float accf[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    float acco[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+    {
+        const int n = a.cnt_ff[i];
+        const Pair* pr = a.pairs_ff + (size_t)i * MAXNBR;
+        for (int t = 0; t < n; ++t) {
+            const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(pr + t));          // j, cells, pad
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(pr + t) + 1);
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(pr + t) + 2);
+            const int j = (int)h0.x;
+            const float f[4] = {1.0f, __ldg(a.vel_new + 3 * j), __ldg(a.vel_new + 3 * j + 1), __ldg(a.vel_new + 3 * j + 2)};
+            const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const unsigned cell = ((c < 4 ? h0.y : h0.z) >> (8 * (c & 3))) & 0xffu;
+                if ((cell >> 1) == (unsigned)lane) {
+                    const int s = cell & 1;
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch) accf[s][ch] += w[c] * f[ch];
+                }
+            }
+        }
+    }
+    {
+        const int n = a.cnt_fb[i];
+        const Pair* pr = a.pairs_fb + (size_t)i * MAXNBR;
+        for (int t = 0; t < n; ++t) {
+            const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(pr + t));
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(pr + t) + 1);
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(pr + t) + 2);
+            const int j = (int)h0.x;
+            const float f[3] = {__ldg(a.box_normals + 3 * j), __ldg(a.box_normals + 3 * j + 1), __ldg(a.box_normals + 3 * j + 2)};
+            const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const unsigned cell = ((c < 4 ? h0.y : h0.z) >> (8 * (c & 3))) & 0xffu;
+                if ((cell >> 1) == (unsigned)lane) {
+                    const int s = cell & 1;
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) acco[s][ch] += w[c] * f[ch];
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) pf[(2 * lane + s) * 4 + ch] = accf[s][ch];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) po[(2 * lane + s) * 3 + ch] = acco[s][ch];
+    }
+    __syncwarp();
+    // lane = output channel
+    float of = __ldg(a.b_fluid + lane), oo = __ldg(a.b_obst + lane);
+    for (int k = 0; k < NCELL * 4; ++k) of += pf[k] * __ldg(a.k_fluid + k * 32 + lane);
+    for (int k = 0; k < NCELL * 3; ++k) oo += po[k] * __ldg(a.k_obst + k * 32 + lane);
+    float od = __ldg(a.b_dense + lane) + __ldg(a.w_dense + lane * 4);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) od += __ldg(a.vel_new + 3 * i + ch) * __ldg(a.w_dense + lane * 4 + 1 + ch);
+    float* o = a.ans0 + (size_t)i * 96;
+    o[lane] = oo; o[32 + lane] = of; o[64 + lane] = od;       // cat[obstacle, fluid, dense]  (:120)
+    if (a.bf16) {
+        __nv_bfloat16* x = reinterpret_cast<__nv_bfloat16*>(a.x0) + (size_t)i * 96;
+        x[lane] = __float2bfloat16(fmaxf(oo, 0.f)); x[32 + lane] = __float2bfloat16(fmaxf(of, 0.f));
+        x[64 + lane] = __float2bfloat16(fmaxf(od, 0.f));
+    } else {
+        __half* x = reinterpret_cast<__half*>(a.x0) + (size_t)i * 96;
+        x[lane] = __float2half(fmaxf(oo, 0.f)); x[32 + lane] = __float2half(fmaxf(of, 0.f));
+        x[64 + lane] = __float2half(fmaxf(od, 0.f));
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// layers 1..3 on tensor cores
+// ------------------------------------------------------------------------------------------------
+struct ConvArgs {
+    const Pair* pairs; const int* cnt;     // fluid->fluid lists
+    const void* x_in;                      // (N,CIN) fp16/bf16, already ReLU'd
+    const uint8_t* w_packed;               // slabs (16 conv slabs + dense slab) + fp32 bias[COUT] at the end
+    const float* residual;                 // (N, ld_res) fp32 or NULL
+    int ld_res;
+    float* ans;                            // (N, COUT_PAD) fp32
+    void* x_out;                           // (N, COUT_PAD) fp16/bf16 = relu(ans), or NULL
+    int n;                                 // total particles (rows of x_in)
+    int begin, end;                        // rows computed by this launch
+    int cout;                              // real output channels (<= COUT_PAD)
+};
+
+template <int CIN, int COUT_PAD>
+struct ConvCfg {
+    static constexpr int CPL = CIN / 32;                 // channels per lane
+    static constexpr int KSLAB = 4 * CIN;                // columns of a conv slab
+    static constexpr int KSTEPS = KSLAB / 16;
+    static constexpr int KSTEPS_DENSE = CIN / 16;
+    static constexpr int STEP_BYTES = COUT_PAD * 32;     // one K-step of the B operand
+    static constexpr int SLAB_BYTES = KSTEPS * STEP_BYTES;
+    static constexpr int DENSE_BYTES = KSTEPS_DENSE * STEP_BYTES;
+    static constexpr int W_BYTES = 16 * SLAB_BYTES + DENSE_BYTES;
+    static constexpr int PACKED_BYTES = W_BYTES + COUT_PAD * 4;
+    static constexpr int SM_A = 0;                                   // 128 x KSLAB halves
+    static constexpr int SM_W = SM_A + 128 * KSLAB * 2;
+    static constexpr int SM_MASK = SM_W + SLAB_BYTES;                // 128 x MAXNBR uint16
+    static constexpr int SM_BIAS = SM_MASK + 128 * MAXNBR * 2;
+    static constexpr int SM_BAR = SM_BIAS + COUT_PAD * 4;
+    static constexpr int SM_TOTAL = SM_BAR + 64;
+    static_assert(SM_TOTAL <= 232448, "smem budget");
+};
+
+constexpr int CONV_THREADS = 288;   // 8 worker warps + 1 issuer warp
+
+template <int CIN, int COUT_PAD, bool BF16>
+__global__ void __launch_bounds__(CONV_THREADS, 1) k_cconv_tc(const ConvArgs a) {
+    using C = ConvCfg<CIN, COUT_PAD>;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row0 = a.begin + blockIdx.x * 128;
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t s_a = s_base + C::SM_A, s_w = s_base + C::SM_W, s_bar = s_base + C::SM_BAR;
+    unsigned short* masks = reinterpret_cast<unsigned short*>(smem + C::SM_MASK);
+    float* sbias = reinterpret_cast<float*>(smem + C::SM_BIAS);
+    const uint32_t bar_a_ready = s_bar, bar_w_full = s_bar + 8, bar_mma_done = s_bar + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::SM_BAR + 32);
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar_a_ready, 256);
+        mbar_init(bar_w_full, 1);
+        mbar_init(bar_mma_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < COUT_PAD) sbias[threadIdx.x] = __ldg(reinterpret_cast<const float*>(a.w_packed + C::W_BYTES) + threadIdx.x);
+    if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 64);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+    if (warp == 8) {
+        // ============================================================ issuer: weight slabs + MMAs
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc(128, COUT_PAD, BF16);
+            const uint8_t* src = a.w_packed;
+            uint32_t acc = 0;
+            for (int s = 0; s <= 16; ++s) {
+                const uint32_t bytes = (s < 16) ? C::SLAB_BYTES : C::DENSE_BYTES;
+                const int ksteps = (s < 16) ? C::KSTEPS : C::KSTEPS_DENSE;
+                if (s > 0) mbar_wait(bar_mma_done, (s - 1) & 1);      // W buffer free again
+                mbar_arrive_expect_tx(bar_w_full, bytes);
+                bulk_g2s(s_w, src, bytes, bar_w_full);
+                src += bytes;
+                mbar_wait(bar_a_ready, s & 1);
+                mbar_wait(bar_w_full, s & 1);
+                tc_fence_after();
+                for (int j = 0; j < ksteps; ++j) {
+                    umma_f16(tmem_base, umma_desc(s_a + j * 4096, 2048, 128),
+                             umma_desc(s_w + j * C::STEP_BYTES, COUT_PAD * 16, 128), idesc, acc);
+                    acc = 1;
+                }
+                umma_commit(bar_mma_done);
+            }
+        }
+    } else {
+        // ============================================================ workers: slab construction
+        const int rbase = warp * 16;   // 16 rows per warp
+        // which (z,y) filter rows does each neighbour touch?
+        for (int r = 0; r < 16; ++r) {
+            const int row = row0 + rbase + r;
+            const int n = (row < a.end) ? a.cnt[row] : 0;
+            for (int t = lane; t < MAXNBR; t += 32) {
+                unsigned mk = 0;
+                if (t < n) {
+                    const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(a.pairs + (size_t)row * MAXNBR + t));
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const unsigned cell = ((c < 4 ? h0.y : h0.z) >> (8 * (c & 3))) & 0xffu;
+                        mk |= 1u << (cell >> 2);
+                    }
+                }
+                masks[(rbase + r) * MAXNBR + t] = (unsigned short)mk;
+            }
+        }
+        __syncwarp();
+        for (int s = 0; s <= 16; ++s) {
+            for (int r = 0; r < 16; ++r) {
+                const int rl = rbase + r;
+                const int row = row0 + rl;
+                float acc[4][C::CPL];
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int m = 0; m < C::CPL; ++m) acc[x][m] = 0.f;
+                if (s < 16) {
+                    const int n = (row < a.end) ? a.cnt[row] : 0;
+                    const Pair* pr = a.pairs + (size_t)row * MAXNBR;
+                    for (int t0 = 0; t0 < n; t0 += 32) {
+                        const unsigned mk = (t0 + lane < n) ? masks[rl * MAXNBR + t0 + lane] : 0u;
+                        unsigned m = __ballot_sync(NF_FULL, (mk >> s) & 1u);
+                        while (m) {
+                            const int t = t0 + __ffs(m) - 1;
+                            m &= m - 1;
+                            const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(pr + t));
+                            const float4 w0 = __ldg(reinterpret_cast<const float4*>(pr + t) + 1);
+                            const float4 w1 = __ldg(reinterpret_cast<const float4*>(pr + t) + 2);
+                            const int j = (int)h0.x;
+                            float f[C::CPL];
+#pragma unroll
+                            for (int mm = 0; mm < C::CPL; ++mm) {
+                                if (BF16) f[mm] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.x_in)[(size_t)j * CIN + lane + 32 * mm]);
+                                else f[mm] = __half2float(reinterpret_cast<const __half*>(a.x_in)[(size_t)j * CIN + lane + 32 * mm]);
+                            }
+                            const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                const unsigned cell = ((c < 4 ? h0.y : h0.z) >> (8 * (c & 3))) & 0xffu;
+                                if ((int)(cell >> 2) == s) {            // warp-uniform
+                                    const int x = cell & 3;
+#pragma unroll
+                                    for (int xx = 0; xx < 4; ++xx)
+                                        if (xx == x) {
+#pragma unroll
+                                            for (int mm = 0; mm < C::CPL; ++mm) acc[xx][mm] += w[c] * f[mm];
+                                        }
+                                }
+                            }
+                        }
+                    }
+                } else if (row < a.end) {
+                    // dense branch: the particle's own (ReLU'd) features, K = CIN
+#pragma unroll
+                    for (int mm = 0; mm < C::CPL; ++mm) {
+                        if (BF16) acc[0][mm] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.x_in)[(size_t)row * CIN + lane + 32 * mm]);
+                        else acc[0][mm] = __half2float(reinterpret_cast<const __half*>(a.x_in)[(size_t)row * CIN + lane + 32 * mm]);
+                    }
+                }
+                if (r == 0 && s > 0) mbar_wait(bar_mma_done, (s - 1) & 1);   // previous slab consumed
+                const int nx = (s < 16) ? 4 : 1;
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    if (x < nx) {
+#pragma unroll
+                        for (int mm = 0; mm < C::CPL; ++mm) {
+                            const int k = x * CIN + lane + 32 * mm;
+                            const uint32_t addr = s_a + (uint32_t)(k >> 3) * 2048 + (uint32_t)rl * 16 + (uint32_t)(k & 7) * 2;
+                            unsigned short bits;
+                            if (BF16) { __nv_bfloat16 hv = __float2bfloat16(acc[x][mm]); bits = *reinterpret_cast<unsigned short*>(&hv); }
+                            else { __half hv = __float2half(acc[x][mm]); bits = *reinterpret_cast<unsigned short*>(&hv); }
+                            asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(bits) : "memory");
+                        }
+                    }
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(bar_a_ready);
+        }
+        // ============================================================ epilogue (warps 0-3, thread = row)
+        if (warp < 4) {
+            mbar_wait(bar_mma_done, 0);     // 17 commits: the last one completes phase index 16 -> parity 0
+            tc_fence_after();
+            const int rl = warp * 32 + lane;
+            const int row = row0 + rl;
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+            for (int c0 = 0; c0 < COUT_PAD; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(taddr + c0, v);
+                tmem_ld_wait();
+                if (row < a.end) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int c = c0 + i;
+                        float o = __uint_as_float(v[i]) + sbias[c];
+                        if (a.residual && c < a.cout) o += a.residual[(size_t)row * a.ld_res + c];
+                        if (c >= a.cout) o = 0.f;
+                        a.ans[(size_t)row * COUT_PAD + c] = o;
+                        if (a.x_out) {
+                            if (BF16) reinterpret_cast<__nv_bfloat16*>(a.x_out)[(size_t)row * COUT_PAD + c] = __float2bfloat16(fmaxf(o, 0.f));
+                            else reinterpret_cast<__half*>(a.x_out)[(size_t)row * COUT_PAD + c] = __float2half(fmaxf(o, 0.f));
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem_base, 64);
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing: conv kernel (4,4,4,CIN,COUT) + dense (COUT,CIN) -> K-step slabs in UMMA order
+//   conv slab s=(z*4+y): column k = x*CIN + ch   <-  kernel[z][y][x][ch][cout]
+//   dense slab         : column k = ch           <-  dense_w[cout][ch]
+//   K-step bytes: [kc(2)][cout(COUT_PAD)][e(8)] halves
+// ------------------------------------------------------------------------------------------------
+template <int CIN, int COUT_PAD, bool BF16>
+__global__ void k_pack_conv(const float* __restrict__ kern, const float* __restrict__ bconv, const float* __restrict__ wd,
+                            const float* __restrict__ bd, int cout, uint8_t* __restrict__ out) {
+    using C = ConvCfg<CIN, COUT_PAD>;
+    const int total_steps = 16 * C::KSTEPS + C::KSTEPS_DENSE;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;    // one thread per (step, kc, cout)
+    if (t < total_steps * 2 * COUT_PAD) {
+        const int step = t / (2 * COUT_PAD), kc = (t / COUT_PAD) % 2, n = t % COUT_PAD;
+        unsigned short e[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float v = 0.f;
+            if (n < cout) {
+                if (step < 16 * C::KSTEPS) {
+                    const int s = step / C::KSTEPS, k = (step % C::KSTEPS) * 16 + kc * 8 + i;
+                    const int x = k / CIN, ch = k % CIN;
+                    v = kern[((size_t)(s * 4 + x) * CIN + ch) * cout + n];
+                } else {
+                    const int k = (step - 16 * C::KSTEPS) * 16 + kc * 8 + i;
+                    v = wd[(size_t)n * CIN + k];
+                }
+            }
+            if (BF16) { __nv_bfloat16 h = __float2bfloat16(v); e[i] = *reinterpret_cast<unsigned short*>(&h); }
+            else { __half h = __float2half(v); e[i] = *reinterpret_cast<unsigned short*>(&h); }
+        }
+        uint4 pk;
+        pk.x = e[0] | ((unsigned)e[1] << 16); pk.y = e[2] | ((unsigned)e[3] << 16);
+        pk.z = e[4] | ((unsigned)e[5] << 16); pk.w = e[6] | ((unsigned)e[7] << 16);
+        *reinterpret_cast<uint4*>(out + (size_t)step * C::STEP_BYTES + ((size_t)kc * COUT_PAD + n) * 16) = pk;
+    }
+    if (t < COUT_PAD) reinterpret_cast<float*>(out + C::W_BYTES)[t] = t < cout ? bconv[t] + bd[t] : 0.f;
+}
+
+// packed layout of the whole ParticleNet: fp32 layer-0 tensors, then the three tensor-core layers
+struct PackedLayout {
+    size_t k_fluid, b_fluid, k_obst, b_obst, w_dense0, b_dense0, l1, l2, l3, total;
+};
+inline PackedLayout packed_layout() {
+    PackedLayout L;
+    size_t o = 0;
+    auto take = [&](size_t b) { size_t r = o; o += align_up(b, 256); return r; };
+    L.k_fluid = take(64 * 4 * 32 * 4); L.b_fluid = take(32 * 4);
+    L.k_obst = take(64 * 3 * 32 * 4); L.b_obst = take(32 * 4);
+    L.w_dense0 = take(32 * 4 * 4); L.b_dense0 = take(32 * 4);
+    L.l1 = take(ConvCfg<96, 64>::PACKED_BYTES);
+    L.l2 = take(ConvCfg<64, 64>::PACKED_BYTES);
+    L.l3 = take(ConvCfg<64, 16>::PACKED_BYTES);
+    L.total = o;
+    return L;
+}
+
+struct WsLayout {
+    size_t pos_new, vel_new, grid_f, grid_b, pairs_ff, cnt_ff, pairs_fb, cnt_fb, ans0, x0, ans1, x1, ans2, x2, ans3,
+        flags, total;
+};
+inline WsLayout ws_layout(int n, int m) {
+    WsLayout L;
+    size_t o = 0;
+    auto take = [&](size_t b) { size_t r = o; o += align_up(b, 256); return r; };
+    const size_t N = (size_t)(n > 0 ? n : 1);
+    L.pos_new = take(N * 12); L.vel_new = take(N * 12);
+    L.grid_f = take(grid_layout(n).total);
+    L.grid_b = take(grid_layout(m).total);
+    L.pairs_ff = take(N * MAXNBR * sizeof(Pair)); L.cnt_ff = take(N * 4);
+    L.pairs_fb = take(N * MAXNBR * sizeof(Pair)); L.cnt_fb = take(N * 4);
+    L.ans0 = take(N * 96 * 4); L.x0 = take(N * 96 * 2);
+    L.ans1 = take(N * 64 * 4); L.x1 = take(N * 64 * 2);
+    L.ans2 = take(N * 64 * 4); L.x2 = take(N * 64 * 2);
+    L.ans3 = take(N * 16 * 4);
+    L.flags = take(256);
+    L.total = o;
+    return L;
+}
+
+template <int CIN, int COUT_PAD>
+static int launch_conv(const ConvArgs& a, int dtype, cudaStream_t st) {
+    using C = ConvCfg<CIN, COUT_PAD>;
+    if (a.end <= a.begin) return NF_OK;
+    static bool configured = false;
+    if (!configured) {
+        NF_CUDA_OK(cudaFuncSetAttribute(k_cconv_tc<CIN, COUT_PAD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SM_TOTAL));
+        NF_CUDA_OK(cudaFuncSetAttribute(k_cconv_tc<CIN, COUT_PAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SM_TOTAL));
+        configured = true;
+    }
+    const int grid = (a.end - a.begin + 127) / 128;
+    if (dtype == NF_DTYPE_BF16) k_cconv_tc<CIN, COUT_PAD, true><<<grid, CONV_THREADS, C::SM_TOTAL, st>>>(a);
+    else k_cconv_tc<CIN, COUT_PAD, false><<<grid, CONV_THREADS, C::SM_TOTAL, st>>>(a);
+    NF_LAUNCH_OK();
+    return NF_OK;
+}
+
+}  // namespace cconv
+}  // namespace nf
+
 using namespace nf;
-extern "C" size_t nf_transition_packed_weights_bytes(void) { return 0; }
-extern "C" int nf_transition_pack_weights(const float* const*, int, void*, void*) {
-    set_error("transition model not built yet"); return NF_E_UNSUPPORTED; }
-extern "C" size_t nf_transition_workspace_bytes(int, int) { return 0; }
-extern "C" int nf_transition_num_phases(void) { return 0; }
-extern "C" int nf_transition_step(const nf_transition_args*, void*) {
-    set_error("transition model not built yet"); return NF_E_UNSUPPORTED; }
-extern "C" size_t nf_cconv_workspace_bytes(int, int, int, int) { return 0; }
-extern "C" int nf_cconv_forward(const float*, const float*, int, int, const float*, int, float, const float*,
-                                const float*, int, int, int, float*, int32_t*, void*, size_t, void*) {
-    set_error("transition model not built yet"); return NF_E_UNSUPPORTED; }
+using namespace nf::cconv;
+
+extern "C" size_t nf_transition_packed_weights_bytes(void) { return packed_layout().total; }
+
+extern "C" int nf_transition_pack_weights(const float* const* p, int dtype, void* packed_out, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    NF_REQUIRE(p && packed_out, NF_E_INVALID, "nf_transition_pack_weights: null argument");
+    NF_REQUIRE(dtype == NF_DTYPE_F16 || dtype == NF_DTYPE_BF16, NF_E_UNSUPPORTED, "nf_transition_pack_weights: dtype %d", dtype);
+    for (int i = 0; i < 18; ++i) NF_REQUIRE(p[i], NF_E_INVALID, "nf_transition_pack_weights: null parameter %d", i);
+    const PackedLayout L = packed_layout();
+    uint8_t* b = (uint8_t*)packed_out;
+    // order: conv0_fluid.{kernel,bias}, conv0_obstacle.{kernel,bias}, dense0_fluid.{weight,bias},
+    //        conv1.{k,b}, dense1.{w,b}, conv2.{k,b}, dense2.{w,b}, conv3.{k,b}, dense3.{w,b}
+    NF_CUDA_OK(cudaMemcpyAsync(b + L.k_fluid, p[0], 64 * 4 * 32 * 4, cudaMemcpyDeviceToDevice, st));
+    NF_CUDA_OK(cudaMemcpyAsync(b + L.b_fluid, p[1], 32 * 4, cudaMemcpyDeviceToDevice, st));
+    NF_CUDA_OK(cudaMemcpyAsync(b + L.k_obst, p[2], 64 * 3 * 32 * 4, cudaMemcpyDeviceToDevice, st));
+    NF_CUDA_OK(cudaMemcpyAsync(b + L.b_obst, p[3], 32 * 4, cudaMemcpyDeviceToDevice, st));
+    NF_CUDA_OK(cudaMemcpyAsync(b + L.w_dense0, p[4], 32 * 4 * 4, cudaMemcpyDeviceToDevice, st));
+    NF_CUDA_OK(cudaMemcpyAsync(b + L.b_dense0, p[5], 32 * 4, cudaMemcpyDeviceToDevice, st));
+    const bool bf = dtype == NF_DTYPE_BF16;
+    {
+        using C = ConvCfg<96, 64>;
+        const int tot = (16 * C::KSTEPS + C::KSTEPS_DENSE) * 2 * 64;
+        if (bf) k_pack_conv<96, 64, true><<<(tot + 255) / 256, 256, 0, st>>>(p[6], p[7], p[8], p[9], 64, b + L.l1);
+        else k_pack_conv<96, 64, false><<<(tot + 255) / 256, 256, 0, st>>>(p[6], p[7], p[8], p[9], 64, b + L.l1);
+        NF_LAUNCH_OK();
+    }
+    {
+        using C = ConvCfg<64, 64>;
+        const int tot = (16 * C::KSTEPS + C::KSTEPS_DENSE) * 2 * 64;
+        if (bf) k_pack_conv<64, 64, true><<<(tot + 255) / 256, 256, 0, st>>>(p[10], p[11], p[12], p[13], 64, b + L.l2);
+        else k_pack_conv<64, 64, false><<<(tot + 255) / 256, 256, 0, st>>>(p[10], p[11], p[12], p[13], 64, b + L.l2);
+        NF_LAUNCH_OK();
+    }
+    {
+        using C = ConvCfg<64, 16>;
+        const int tot = (16 * C::KSTEPS + C::KSTEPS_DENSE) * 2 * 16;
+        if (bf) k_pack_conv<64, 16, true><<<(tot + 255) / 256, 256, 0, st>>>(p[14], p[15], p[16], p[17], 3, b + L.l3);
+        else k_pack_conv<64, 16, false><<<(tot + 255) / 256, 256, 0, st>>>(p[14], p[15], p[16], p[17], 3, b + L.l3);
+        NF_LAUNCH_OK();
+    }
+    return NF_OK;
+}
+
+extern "C" size_t nf_transition_workspace_bytes(int n_fluid, int n_box) {
+    if (n_fluid < 0 || n_box < 0) return 0;
+    return ws_layout(n_fluid, n_box).total;
+}
+
+// phases: 0 integrate + grids + neighbour lists + layer 0;  1,2,3 conv layers;  4 position/velocity update
+extern "C" int nf_transition_num_phases(void) { return 5; }
+
+extern "C" int nf_transition_layer_buffer(int n_fluid, int n_box, int layer, size_t* off, size_t* row_bytes) {
+    NF_REQUIRE(off && row_bytes && layer >= 0 && layer <= 2, NF_E_INVALID, "nf_transition_layer_buffer: bad arguments");
+    const WsLayout L = ws_layout(n_fluid, n_box);
+    *off = layer == 0 ? L.x0 : (layer == 1 ? L.x1 : L.x2);
+    *row_bytes = (layer == 0 ? 96 : 64) * 2;
+    return NF_OK;
+}
+
+extern "C" int nf_transition_step(const nf_transition_args* a, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    NF_REQUIRE(a != nullptr, NF_E_INVALID, "nf_transition_step: null args");
+    NF_REQUIRE(a->n_fluid >= 0 && a->n_box >= 0, NF_E_INVALID, "nf_transition_step: negative sizes");
+    if (a->n_fluid == 0) return NF_OK;
+    NF_REQUIRE(a->pos && a->vel && a->weights && a->workspace && a->pos_out && a->vel_out, NF_E_INVALID,
+               "nf_transition_step: null pointer");
+    NF_REQUIRE(a->n_box == 0 || (a->box && a->box_normals), NF_E_INVALID, "nf_transition_step: null box");
+    NF_REQUIRE(a->dtype == NF_DTYPE_F16 || a->dtype == NF_DTYPE_BF16, NF_E_UNSUPPORTED, "nf_transition_step: dtype");
+    NF_REQUIRE(a->filter_extent > 2e-3f && a->dt > 0.f, NF_E_INVALID, "nf_transition_step: bad extent/dt");
+    NF_REQUIRE(a->phase >= -1 && a->phase < 5, NF_E_INVALID, "nf_transition_step: phase %d", a->phase);
+    const int N = a->n_fluid, M = a->n_box;
+    const int begin = a->phase == -1 ? 0 : a->shard_begin, end = a->phase == -1 ? N : a->shard_end;
+    NF_REQUIRE(begin >= 0 && end <= N && begin <= end, NF_E_INVALID, "nf_transition_step: bad shard [%d,%d)", begin, end);
+    const WsLayout L = ws_layout(N, M);
+    NF_REQUIRE(a->workspace_bytes >= L.total, NF_E_WORKSPACE, "nf_transition_step: workspace %zu < %zu",
+               a->workspace_bytes, L.total);
+    const PackedLayout PL = packed_layout();
+    char* b = (char*)a->workspace;
+    const uint8_t* w = (const uint8_t*)a->weights;
+    float* pos_new = (float*)(b + L.pos_new);
+    float* vel_new = (float*)(b + L.vel_new);
+    Pair* pairs_ff = (Pair*)(b + L.pairs_ff); int* cnt_ff = (int*)(b + L.cnt_ff);
+    Pair* pairs_fb = (Pair*)(b + L.pairs_fb); int* cnt_fb = (int*)(b + L.cnt_fb);
+    float* ans0 = (float*)(b + L.ans0); void* x0 = b + L.x0;
+    float* ans1 = (float*)(b + L.ans1); void* x1 = b + L.x1;
+    float* ans2 = (float*)(b + L.ans2); void* x2 = b + L.x2;
+    float* ans3 = (float*)(b + L.ans3);
+    int* flags = (int*)(b + L.flags);
+    const float radius = 0.5f * a->filter_extent;
+    const bool all = a->phase == -1;
+    const int nshard = end - begin;
+
+    if (all || a->phase == 0) {
+        NF_CUDA_OK(cudaMemsetAsync(flags, 0, 256, st));
+        k_integrate<<<(3 * N + 255) / 256, 256, 0, st>>>(a->pos, a->vel, N, a->gravity[0], a->gravity[1], a->gravity[2],
+                                                        a->dt, pos_new, vel_new);
+        NF_LAUNCH_OK();
+        int rc = nf_grid_build(pos_new, N, 1.002f * radius, b + L.grid_f, grid_layout(N).total, stream_);
+        if (rc != NF_OK) return rc;
+        rc = nf_grid_build(a->box, M, 1.002f * radius, b + L.grid_b, grid_layout(M).total, stream_);
+        if (rc != NF_OK) return rc;
+        if (nshard > 0) {
+            const int blocks = (nshard + 7) / 8;
+            k_nbr_build<<<blocks, 256, 0, st>>>(grid_view(b + L.grid_f, N), pos_new, begin, end, radius, 1, 1, pairs_ff,
+                                               cnt_ff, a->nnbr_out, flags);
+            NF_LAUNCH_OK();
+            k_nbr_build<<<blocks, 256, 0, st>>>(grid_view(b + L.grid_b, M), pos_new, begin, end, radius, 1, 1, pairs_fb,
+                                               cnt_fb, nullptr, flags + 1);
+            NF_LAUNCH_OK();
+            Layer0Args l0;
+            l0.pairs_ff = pairs_ff; l0.cnt_ff = cnt_ff; l0.pairs_fb = pairs_fb; l0.cnt_fb = cnt_fb;
+            l0.vel_new = vel_new; l0.box_normals = a->box_normals;
+            l0.k_fluid = (const float*)(w + PL.k_fluid); l0.b_fluid = (const float*)(w + PL.b_fluid);
+            l0.k_obst = (const float*)(w + PL.k_obst); l0.b_obst = (const float*)(w + PL.b_obst);
+            l0.w_dense = (const float*)(w + PL.w_dense0); l0.b_dense = (const float*)(w + PL.b_dense0);
+            l0.ans0 = ans0; l0.x0 = x0; l0.begin = begin; l0.end = end; l0.bf16 = a->dtype == NF_DTYPE_BF16;
+            k_layer0<<<blocks, 256, 0, st>>>(l0);
+            NF_LAUNCH_OK();
+            if (a->feats0_out)
+                NF_CUDA_OK(cudaMemcpyAsync(a->feats0_out + (size_t)begin * 96, ans0 + (size_t)begin * 96,
+                                           (size_t)nshard * 96 * 4, cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    ConvArgs c;
+    c.pairs = pairs_ff; c.cnt = cnt_ff; c.n = N; c.begin = begin; c.end = end;
+    if (all || a->phase == 1) {     // conv1 + dense1 : 96 -> 64 (no residual: widths differ, :127-130)
+        c.x_in = x0; c.w_packed = w + PL.l1; c.residual = nullptr; c.ld_res = 0; c.ans = ans1; c.x_out = x1; c.cout = 64;
+        int rc = launch_conv<96, 64>(c, a->dtype, st);
+        if (rc != NF_OK) return rc;
+    }
+    if (all || a->phase == 2) {     // conv2 + dense2 + residual : 64 -> 64
+        c.x_in = x1; c.w_packed = w + PL.l2; c.residual = ans1; c.ld_res = 64; c.ans = ans2; c.x_out = x2; c.cout = 64;
+        int rc = launch_conv<64, 64>(c, a->dtype, st);
+        if (rc != NF_OK) return rc;
+    }
+    if (all || a->phase == 3) {     // conv3 + dense3 : 64 -> 3
+        c.x_in = x2; c.w_packed = w + PL.l3; c.residual = nullptr; c.ld_res = 0; c.ans = ans3; c.x_out = nullptr; c.cout = 3;
+        int rc = launch_conv<64, 16>(c, a->dtype, st);
+        if (rc != NF_OK) return rc;
+    }
+    if ((all || a->phase == 4) && nshard > 0) {
+        k_update<<<(3 * nshard + 255) / 256, 256, 0, st>>>(a->pos, pos_new, ans3, 16, begin, end, a->dt, a->pos_out,
+                                                          a->vel_out, a->delta_out);
+        NF_LAUNCH_OK();
+    }
+    return NF_OK;
+}

@@ -1,0 +1,166 @@
+"""ParticleNet -- drop-in for the reference's `models/transmodel.py:ParticleNet` on B200.
+
+Same constructor signature, same `forward(pos, vel, box, box_feats, feats=None,
+fixed_radius_search_hash_table=None) -> (pos, vel, num_fluid_neighbors)`, same state-dict keys
+(`conv0_fluid.kernel/bias/offset`, `dense0_fluid.weight/bias`, ..., `gravity`).  The arithmetic runs in
+libnf_b200.so (csrc/nf_cconv.cu, nf_grid.cu): fixed-radius neighbour lists on the shared spatial grid,
+layer 0 in fp32, layers 1-3 as fused gather + trilinear-scatter + tcgen05 GEMM kernels.
+No CPU or eager fallback.  Forward only (no autograd graph): see DESIGN.md.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib
+from ._lib import NFError, check, lib, ptr, require_cuda, stream_ptr
+
+
+class ContinuousConvParams(nn.Module):
+    """Parameter container with open3d.ml.torch.layers.ContinuousConv's state layout:
+    `kernel` (*kernel_size, in_channels, filters) ~ U(-0.05, 0.05), `bias` (filters) zeros, buffer `offset` (3)."""
+
+    def __init__(self, in_channels, filters, kernel_size):
+        super().__init__()
+        self.in_channels, self.filters, self.kernel_size = in_channels, filters, list(kernel_size)
+        self.kernel = nn.Parameter(torch.empty(*kernel_size, in_channels, filters).uniform_(-0.05, 0.05))
+        self.bias = nn.Parameter(torch.zeros(filters))
+        self.register_buffer("offset", torch.zeros(3))
+
+    def forward(self, *a, **k):
+        raise NFError("ContinuousConv layers run fused inside ParticleNet.forward (csrc/nf_cconv.cu)")
+
+
+class ParticleNet(nn.Module):
+    def __init__(self, kernel_size=[4, 4, 4], radius_scale=1.5, coordinate_mapping="ball_to_cube_volume_preserving",
+                 interpolation="linear", use_window=True, particle_radius=0.025, timestep=1 / 50,
+                 gravity=(0, -9.81, 0), other_feats_channels=0, operand_dtype: str = "fp16"):
+        super().__init__()
+        if list(kernel_size) != [4, 4, 4] or coordinate_mapping != "ball_to_cube_volume_preserving" \
+                or interpolation != "linear" or not use_window or other_feats_channels != 0:
+            raise NFError("the sm_100a kernels implement the configuration every reference entry point uses: "
+                          "4x4x4 linear filters, ball_to_cube_volume_preserving, poly6 window, no extra features")
+        self.layer_channels = [32, 64, 64, 3]
+        self.kernel_size, self.radius_scale, self.particle_radius = kernel_size, radius_scale, particle_radius
+        self.coordinate_mapping, self.interpolation, self.use_window = coordinate_mapping, interpolation, use_window
+        self.filter_extent = np.float32(6 * radius_scale * particle_radius)       # models/transmodel.py:35
+        self.time_step = timestep
+        self.register_buffer("gravity", torch.FloatTensor(gravity))
+        self.conv0_fluid = ContinuousConvParams(4, 32, kernel_size)
+        self.conv0_obstacle = ContinuousConvParams(3, 32, kernel_size)
+        self.dense0_fluid = nn.Linear(4, 32)
+        nn.init.xavier_uniform_(self.dense0_fluid.weight)
+        nn.init.zeros_(self.dense0_fluid.bias)
+        for i, (cin, cout) in enumerate([(96, 64), (64, 64), (64, 3)], start=1):
+            setattr(self, f"dense{i}", nn.Linear(cin, cout))
+            setattr(self, f"conv{i}", ContinuousConvParams(cin, cout, kernel_size))
+        self.operand_dtype = {"fp16": _lib.NF_DTYPE_F16, "bf16": _lib.NF_DTYPE_BF16}[operand_dtype]
+        self._packed = None
+        self._ws = None
+        self.num_fluid_neighbors = None
+        self.pos_correction = None
+
+    # ------------------------------------------------------------------ internals
+    def ordered_params(self):
+        """nf_transition_pack_weights order."""
+        mods = [self.conv0_fluid, self.conv0_obstacle, self.dense0_fluid, self.conv1, self.dense1, self.conv2,
+                self.dense2, self.conv3, self.dense3]
+        out = []
+        for m in mods:
+            out += [m.kernel if isinstance(m, ContinuousConvParams) else m.weight, m.bias]
+        return out
+
+    def _packed_weights(self):
+        params = self.ordered_params()
+        for m in (self.conv0_fluid, self.conv0_obstacle, self.conv1, self.conv2, self.conv3):
+            if bool((m.offset != 0).any()):
+                raise NFError("non-zero ContinuousConv.offset is not supported (the reference never sets it)")
+        key = tuple((p.data_ptr(), p._version) for p in params) + (self.operand_dtype,)
+        if self._packed is None or self._packed[0] != key:
+            ps = [p.detach().to(torch.float32).contiguous() for p in params]
+            require_cuda(*ps)
+            out = torch.empty(lib().nf_transition_packed_weights_bytes(), dtype=torch.uint8, device=ps[0].device)
+            arr = (C.c_void_p * 18)(*[p.data_ptr() for p in ps])
+            check(lib().nf_transition_pack_weights(arr, self.operand_dtype, ptr(out), stream_ptr()),
+                  "nf_transition_pack_weights")
+            out._keepalive = ps
+            self._packed = (key, out)
+        return self._packed[1]
+
+    def _workspace(self, n, m, device):
+        need = lib().nf_transition_workspace_bytes(n, m)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=device)
+        return self._ws
+
+    def _args(self, pos, vel, box, box_feats, outs, ws, phase=-1, shard=(0, 0), debug=None):
+        a = _lib.TransitionArgs()
+        a.pos, a.vel, a.n_fluid = ptr(pos), ptr(vel), pos.shape[0]
+        a.box, a.box_normals, a.n_box = ptr(box), ptr(box_feats), box.shape[0]
+        a.gravity = (C.c_float * 3)(*[float(v) for v in self._gravity_host])
+        a.dt, a.filter_extent, a.dtype = float(self.time_step), float(self.filter_extent), self.operand_dtype
+        a.weights = ptr(self._packed_weights())
+        a.pos_out, a.vel_out, a.nnbr_out = ptr(outs[0]), ptr(outs[1]), ptr(outs[2])
+        a.feats0_out = ptr(debug["feats0"]) if debug else None
+        a.delta_out = ptr(outs[3])
+        a.workspace, a.workspace_bytes = ptr(ws), ws.numel()
+        a.shard_begin, a.shard_end, a.phase = int(shard[0]), int(shard[1]), int(phase)
+        return a
+
+    def _prepare(self, pos, vel, box, box_feats, feats):
+        if feats is not None:
+            raise NFError("other_feats_channels > 0 is not used by any reference entry point and is not implemented")
+        require_cuda(pos, vel, box, box_feats)
+        f = lambda t: t.detach().to(torch.float32).contiguous()
+        pos, vel, box, box_feats = f(pos), f(vel), f(box), f(box_feats)
+        if not hasattr(self, "_gravity_host") or self._gravity_version != self.gravity._version:
+            self._gravity_host = self.gravity.detach().cpu().tolist()
+            self._gravity_version = self.gravity._version
+        n = pos.shape[0]
+        dev = pos.device
+        outs = (torch.empty((n, 3), device=dev), torch.empty((n, 3), device=dev), torch.empty((n,), device=dev),
+                torch.empty((n, 3), device=dev))
+        return pos, vel, box, box_feats, outs, self._workspace(n, box.shape[0], dev)
+
+    # ------------------------------------------------------------------ reference API
+    def forward(self, pos, vel, box, box_feats, feats=None, fixed_radius_search_hash_table=None, debug=None):
+        """models/transmodel.py:151-163.  `fixed_radius_search_hash_table` is accepted and ignored, as upstream."""
+        pos, vel, box, box_feats, outs, ws = self._prepare(pos, vel, box, box_feats, feats)
+        if debug is not None:
+            debug["feats0"] = torch.empty((pos.shape[0], 96), device=pos.device)
+        a = self._args(pos, vel, box, box_feats, outs, ws, debug=debug)
+        check(lib().nf_transition_step(C.byref(a), stream_ptr()), "nf_transition_step")
+        self.num_fluid_neighbors, self.pos_correction = outs[2], outs[3]
+        self._keep = (pos, vel, box, box_feats)
+        return outs[0], outs[1], outs[2]
+
+    step = forward      # BASELINE.json's wording: TransModel.step
+
+
+TransModel = ParticleNet
+
+
+def smoke_check(dev):
+    """One small step on `dev` checked against the CPU oracle (used by __graft_entry__.smoke)."""
+    from . import scenes
+    from oracle import transition as otrans
+    sd = scenes.init_particle_state(0)
+    net = ParticleNet(gravity=(0.0, 0.0, -9.81))
+    net.load_state_dict(sd)
+    net = net.to(dev)
+    half = 7 / 2 * 0.05
+    pos = torch.from_numpy(scenes.lattice_particles(8, 0, center=(0.0, 0.0, -1 + 0.03 + half)))
+    vel = torch.zeros_like(pos)
+    bp, bn = scenes.box_points(0.1)
+    box, box_n = torch.from_numpy(bp), torch.from_numpy(bn)
+    p1, v1, nn1 = net(pos.to(dev), vel.to(dev), box.to(dev), box_n.to(dev))
+    torch.cuda.synchronize()
+    rp, rv, rn, dbg = otrans.particle_step(sd, pos, vel, box, box_n, debug=True)
+    assert torch.equal(nn1.cpu(), rn), "fluid neighbour counts differ from the oracle"
+    err = float(torch.norm(net.pos_correction.cpu() - dbg["feats"][-1] / 128) / torch.norm(dbg["feats"][-1] / 128))
+    assert err < 5e-3, err
+    assert float(torch.norm(p1.cpu() - rp) / torch.norm(rp)) < 1e-6
+    print("smoke: transition ok (position-correction rel L2 %.2e)" % err)

@@ -112,6 +112,50 @@ def stage_bench():
               f"stats={net.last_stats.sum(0).tolist()} rgb1 mean={out['rgb1'].mean().item():.4f}")
 
 
+
+
+def stage_transition():
+    from helpers import load_transition_case
+    from oracle import transition as otrans
+    for name in ("small", "medium"):
+        c = load_transition_case(name)
+        g = c["g"]
+        net = nb.ParticleNet(gravity=(0.0, 0.0, -9.81))
+        net.load_state_dict(c["sd"])
+        net = net.to(dev)
+        pos, vel = c["pos"].to(dev), c["vel"].to(dev)
+        box, box_n = c["box"].to(dev), c["box_n"].to(dev)
+        for s in range(int(g["steps"])):
+            dbg = {}
+            pos, vel, nn = net(pos, vel, box, box_n, debug=dbg)
+            torch.cuda.synchronize()
+            msg = f"[trans] {name} step {s}: nnbr mism={(nn.cpu().numpy().astype(np.int16) != g[f'nnbr_{s}']).sum()} " \
+                  f"pos={rel_l2(pos.cpu(), g[f'pos_{s}']):.2e} vel={rel_l2(vel.cpu(), g[f'vel_{s}']):.2e}"
+            if s == 0:
+                msg += f" feats0={rel_l2(dbg['feats0'].cpu(), g['feats0']):.2e} delta={rel_l2(net.pos_correction.cpu(), g['delta0']):.2e}"
+            print(msg)
+    # timing at the BASELINE config[2] size
+    n = 31
+    half = (n - 1) / 2 * 0.05
+    pos = torch.from_numpy(scenes.lattice_particles(n, 0, center=(0.0, 0.0, -1 + 0.03 + half))).to(dev)
+    vel = torch.zeros_like(pos)
+    bp, bn = scenes.box_points(0.032)
+    box, box_n = torch.from_numpy(bp).to(dev), torch.from_numpy(bn).to(dev)
+    net = nb.ParticleNet(gravity=(0.0, 0.0, -9.81))
+    net.load_state_dict(scenes.init_particle_state(0))
+    net = net.to(dev)
+    for it in range(3):
+        torch.cuda.synchronize()
+        t0 = time.time()
+        p, v = pos, vel
+        for s in range(10):
+            p, v, nn = net(p, v, box, box_n)
+        torch.cuda.synchronize()
+        dt = (time.time() - t0) / 10
+        print(f"[trans] N={pos.shape[0]} M={box.shape[0]}: {dt * 1e3:.3f} ms/step -> {pos.shape[0] / dt / 1e6:.2f} M particle-steps/s "
+              f"mean nbrs={nn.mean().item():.1f}")
+
+
 if __name__ == "__main__":
     stages = sys.argv[1:] or ["grid", "mlp", "render", "bench"]
     for s in stages:
