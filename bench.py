@@ -37,6 +37,7 @@ H = W = 800
 N_LATTICE = 27            # 27^3 = 19,683 particles
 MLP_FLOP_PER_ROW = 2 * 665984      # SURVEY.md 8d / BASELINE.md: 1,331,968 FLOP per evaluated sample
 CPU_SAMPLE_RAYS = 8192       # ~7-10 s of host work per timing at ~1.2k rays/s
+REF_STEP_RAYS = 2048          # --impl reference: rays per step (keeps K+W steps within a few minutes)
 
 
 def workload():
@@ -112,22 +113,74 @@ def cpu_reference_rays_per_sec(n_rays, repeats=1):
     return n_rays / best, cores, f"{n_rays} rays strided over the {H}x{W} image (same scene, weights and sample counts)"
 
 
+def transition_workload():
+    from neurofluid_b200 import scenes
+    n = 31                                                     # 31^3 = 29,791 particles ("bunny" stand-in)
+    half = (n - 1) / 2 * 0.05
+    pos = torch.from_numpy(scenes.lattice_particles(n, 0, center=(0.0, 0.0, -1 + 0.03 + half)))
+    bp, bn = scenes.box_points(0.032)
+    return pos, torch.zeros_like(pos), torch.from_numpy(bp), torch.from_numpy(bn), scenes.init_particle_state(0)
+
+
+def cpu_reference_particle_steps_per_sec():
+    from oracle import transition as otrans
+    from oracle import third_party_ops as tpo
+    pos, vel, box, box_n, sd = transition_workload()
+    t0 = time.perf_counter()
+    otrans.particle_step(sd, pos, vel, box, box_n)
+    dt = time.perf_counter() - t0
+    return {"value": pos.shape[0] / dt, "unit": "particle-steps/s", "cores": max(torch.get_num_threads(), tpo.max_threads()),
+            "kind": "port", "sample": f"1 full step, {pos.shape[0]} particles + {box.shape[0]} box points"}
+
+
+def bench_transition(dev, world, rank, args, timed, pk):
+    import neurofluid_b200 as nb
+    from neurofluid_b200.distributed import transition_step_sharded
+    pos, vel, box, box_n, sd = transition_workload()
+    net = nb.ParticleNet(gravity=(0.0, 0.0, -9.81))
+    net.load_state_dict(sd)
+    net = net.to(dev)
+    state = {"p": pos.to(dev), "v": vel.to(dev)}
+    box_d, boxn_d = box.to(dev), box_n.to(dev)
+
+    def step():
+        if world > 1:
+            p, v, _ = transition_step_sharded(net, state["p"], state["v"], box_d, boxn_d)
+        else:
+            p, v, _ = net(state["p"], state["v"], box_d, boxn_d)
+        state["p"], state["v"] = p, v
+
+    for _ in range(3):
+        step()
+    steps = 50                                                  # BASELINE config[2]: 50-step rollout
+    state["p"], state["v"] = pos.to(dev), vel.to(dev)
+    ms = timed(step, steps)
+    n = pos.shape[0]
+    val = n * steps / (ms * 1e-3)
+    flops = 2 * 692544 * val / 1e12                             # 692,544 MAC per particle-step
+    return {"metric": "particle_steps_per_sec_rollout_30k", "value": val, "unit": "particle-steps/s", "ms_per_step": ms / steps,
+            "steps": steps, "n_particles": n, "n_box": box.shape[0], "scaling": "strong",
+            "parallelism": f"particle blocks over {world} GPU(s), 4 NCCL all-gathers per step" if world > 1 else "single GPU",
+            "roofline": {"bound": "tensor", "achieved": flops, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": flops / pk["tensor"],
+                         "note": "41 GFLOP per step: launch/latency-bound by construction (SURVEY 8d)"}}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path, all host threads."""
     if rank != 0:
         return
     per_step = []
     for i in range(args.warmup + args.steps):
-        v, cores, sample = cpu_reference_rays_per_sec(CPU_SAMPLE_RAYS)
+        v, cores, sample = cpu_reference_rays_per_sec(REF_STEP_RAYS)
         if i >= args.warmup:
             per_step.append(v)
     val = float(np.mean(per_step))
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * CPU_SAMPLE_RAYS / val, "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": 1e3 * REF_STEP_RAYS / val, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"watercube-like render {H}x{W}, 64+128 samples, {N_LATTICE ** 3} particles "
-                               f"(BASELINE config[1]); each step = {CPU_SAMPLE_RAYS}-ray strided sample on the host CPU"},
+                               f"(BASELINE config[1]); each step = {REF_STEP_RAYS}-ray strided sample on the host CPU"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -270,9 +323,12 @@ def main():
                            "mlp_fine": st[3], "composite_fine": st[4]},
         "samples": {"rows_coarse": stats[0], "rows_fine": stats[1], "active_coarse": stats[2], "active_fine": stats[3]},
     }
+    # ---- second hot path (BASELINE config[2]): transition-model rollout, ~30k particles, reported as an extra block
+    line["transition"] = bench_transition(dev, world, rank, args, timed, pk)
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         v, cores, sample = cpu_reference_rays_per_sec(CPU_SAMPLE_RAYS)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        line["transition"]["cpu_baseline"] = cpu_reference_particle_steps_per_sec()
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -296,13 +296,13 @@ __global__ void __launch_bounds__(256) k_layer0(const Layer0Args a) {
     if (i >= a.end) return;
     float* pf = sm_patch[wib];
     float* po = pf + NCELL * 4;
-    // lane owns cells 2*lane, 2*lane+1
-    float accf[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-    float acco[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+    // scatter: one lane per neighbour (records and features are fetched in parallel), shared-memory atomics
+    for (int k = lane; k < NCELL * 7; k += 32) pf[k] = 0.f;
+    __syncwarp();
     {
         const int n = a.cnt_ff[i];
         const Pair* pr = a.pairs_ff + (size_t)i * MAXNBR;
-        for (int t = 0; t < n; ++t) {
+        for (int t = lane; t < n; t += 32) {
             const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(pr + t));          // j, cells, pad
             const float4 w0 = __ldg(reinterpret_cast<const float4*>(pr + t) + 1);
             const float4 w1 = __ldg(reinterpret_cast<const float4*>(pr + t) + 2);
@@ -312,18 +312,15 @@ __global__ void __launch_bounds__(256) k_layer0(const Layer0Args a) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const unsigned cell = ((c < 4 ? h0.y : h0.z) >> (8 * (c & 3))) & 0xffu;
-                if ((cell >> 1) == (unsigned)lane) {
-                    const int s = cell & 1;
 #pragma unroll
-                    for (int ch = 0; ch < 4; ++ch) accf[s][ch] += w[c] * f[ch];
-                }
+                for (int ch = 0; ch < 4; ++ch) atomicAdd(pf + cell * 4 + ch, w[c] * f[ch]);
             }
         }
     }
     {
         const int n = a.cnt_fb[i];
         const Pair* pr = a.pairs_fb + (size_t)i * MAXNBR;
-        for (int t = 0; t < n; ++t) {
+        for (int t = lane; t < n; t += 32) {
             const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(pr + t));
             const float4 w0 = __ldg(reinterpret_cast<const float4*>(pr + t) + 1);
             const float4 w1 = __ldg(reinterpret_cast<const float4*>(pr + t) + 2);
@@ -333,20 +330,10 @@ __global__ void __launch_bounds__(256) k_layer0(const Layer0Args a) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const unsigned cell = ((c < 4 ? h0.y : h0.z) >> (8 * (c & 3))) & 0xffu;
-                if ((cell >> 1) == (unsigned)lane) {
-                    const int s = cell & 1;
 #pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) acco[s][ch] += w[c] * f[ch];
-                }
+                for (int ch = 0; ch < 3; ++ch) atomicAdd(po + cell * 3 + ch, w[c] * f[ch]);
             }
         }
-    }
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) pf[(2 * lane + s) * 4 + ch] = accf[s][ch];
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) po[(2 * lane + s) * 3 + ch] = acco[s][ch];
     }
     __syncwarp();
     // lane = output channel
@@ -401,12 +388,15 @@ struct ConvCfg {
     static constexpr int SM_W = SM_A + 128 * KSLAB * 2;
     static constexpr int SM_MASK = SM_W + SLAB_BYTES;                // 128 x MAXNBR uint16
     static constexpr int SM_BIAS = SM_MASK + 128 * MAXNBR * 2;
-    static constexpr int SM_BAR = SM_BIAS + COUT_PAD * 4;
+    static constexpr int SM_LIST = SM_BIAS + COUT_PAD * 4;           // per worker warp: MAXNBR x {j, wx[4]}
+    static constexpr int SM_BAR = SM_LIST + 16 * MAXNBR * 20;
     static constexpr int SM_TOTAL = SM_BAR + 64;
     static_assert(SM_TOTAL <= 232448, "smem budget");
 };
 
-constexpr int CONV_THREADS = 288;   // 8 worker warps + 1 issuer warp
+constexpr int WORKER_WARPS = 16;
+constexpr int ROWS_PER_WARP = 128 / WORKER_WARPS;
+constexpr int CONV_THREADS = WORKER_WARPS * 32 + 32;   // worker warps + 1 issuer warp
 
 template <int CIN, int COUT_PAD, bool BF16>
 __global__ void __launch_bounds__(CONV_THREADS, 1) k_cconv_tc(const ConvArgs a) {
@@ -422,19 +412,19 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_cconv_tc(const ConvArgs a) 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::SM_BAR + 32);
 
     if (threadIdx.x == 0) {
-        mbar_init(bar_a_ready, 256);
+        mbar_init(bar_a_ready, WORKER_WARPS * 32);
         mbar_init(bar_w_full, 1);
         mbar_init(bar_mma_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < COUT_PAD) sbias[threadIdx.x] = __ldg(reinterpret_cast<const float*>(a.w_packed + C::W_BYTES) + threadIdx.x);
-    if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 64);
+    if (warp == WORKER_WARPS) tmem_alloc(smem_u32(tmem_slot), 64);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
-    if (warp == 8) {
+    if (warp == WORKER_WARPS) {
         // ============================================================ issuer: weight slabs + MMAs
         if (lane == 0) {
             const uint32_t idesc = umma_idesc(128, COUT_PAD, BF16);
@@ -460,9 +450,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_cconv_tc(const ConvArgs a) 
         }
     } else {
         // ============================================================ workers: slab construction
-        const int rbase = warp * 16;   // 16 rows per warp
+        const int rbase = warp * ROWS_PER_WARP;
+        int* lst_j = reinterpret_cast<int*>(smem + C::SM_LIST + warp * MAXNBR * 20);
+        float* lst_w = reinterpret_cast<float*>(lst_j + MAXNBR);      // [MAXNBR][4]
+        const unsigned lt = (1u << lane) - 1u;
         // which (z,y) filter rows does each neighbour touch?
-        for (int r = 0; r < 16; ++r) {
+        for (int r = 0; r < ROWS_PER_WARP; ++r) {
             const int row = row0 + rbase + r;
             const int n = (row < a.end) ? a.cnt[row] : 0;
             for (int t = lane; t < MAXNBR; t += 32) {
@@ -480,7 +473,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_cconv_tc(const ConvArgs a) 
         }
         __syncwarp();
         for (int s = 0; s <= 16; ++s) {
-            for (int r = 0; r < 16; ++r) {
+            for (int r = 0; r < ROWS_PER_WARP; ++r) {
                 const int rl = rbase + r;
                 const int row = row0 + rl;
                 float acc[4][C::CPL];
@@ -491,35 +484,60 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_cconv_tc(const ConvArgs a) 
                 if (s < 16) {
                     const int n = (row < a.end) ? a.cnt[row] : 0;
                     const Pair* pr = a.pairs + (size_t)row * MAXNBR;
+                    // phase A: lanes fetch the records of the neighbours that touch filter row s in parallel and
+                    // reduce each to {j, weight per x cell}
+                    int ne = 0;
+                    __syncwarp();
                     for (int t0 = 0; t0 < n; t0 += 32) {
-                        const unsigned mk = (t0 + lane < n) ? masks[rl * MAXNBR + t0 + lane] : 0u;
-                        unsigned m = __ballot_sync(NF_FULL, (mk >> s) & 1u);
-                        while (m) {
-                            const int t = t0 + __ffs(m) - 1;
-                            m &= m - 1;
+                        const int t = t0 + lane;
+                        const bool rel = (t < n) && ((masks[rl * MAXNBR + t] >> s) & 1u);
+                        const unsigned m = __ballot_sync(NF_FULL, rel);
+                        if (rel) {
                             const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(pr + t));
                             const float4 w0 = __ldg(reinterpret_cast<const float4*>(pr + t) + 1);
                             const float4 w1 = __ldg(reinterpret_cast<const float4*>(pr + t) + 2);
-                            const int j = (int)h0.x;
-                            float f[C::CPL];
-#pragma unroll
-                            for (int mm = 0; mm < C::CPL; ++mm) {
-                                if (BF16) f[mm] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.x_in)[(size_t)j * CIN + lane + 32 * mm]);
-                                else f[mm] = __half2float(reinterpret_cast<const __half*>(a.x_in)[(size_t)j * CIN + lane + 32 * mm]);
-                            }
                             const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                            float wx[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                             for (int c = 0; c < 8; ++c) {
                                 const unsigned cell = ((c < 4 ? h0.y : h0.z) >> (8 * (c & 3))) & 0xffu;
-                                if ((int)(cell >> 2) == s) {            // warp-uniform
-                                    const int x = cell & 3;
+                                if ((int)(cell >> 2) == s) {
 #pragma unroll
                                     for (int xx = 0; xx < 4; ++xx)
-                                        if (xx == x) {
-#pragma unroll
-                                            for (int mm = 0; mm < C::CPL; ++mm) acc[xx][mm] += w[c] * f[mm];
-                                        }
+                                        if ((int)(cell & 3) == xx) wx[xx] += w[c];
                                 }
+                            }
+                            const int e = ne + __popc(m & lt);
+                            lst_j[e] = (int)h0.x;
+                            *reinterpret_cast<float4*>(lst_w + 4 * e) = make_float4(wx[0], wx[1], wx[2], wx[3]);
+                        }
+                        ne += __popc(m);
+                    }
+                    __syncwarp();
+                    // phase B: gather the neighbours' feature rows (4 in flight) and accumulate the slab row
+                    for (int e0 = 0; e0 < ne; e0 += 4) {
+                        float f[4][C::CPL];
+                        float4 wv[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int e = min(e0 + u, ne - 1);
+                            const int j = lst_j[e];
+                            wv[u] = *reinterpret_cast<const float4*>(lst_w + 4 * e);
+                            if (e0 + u >= ne) wv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                            for (int mm = 0; mm < C::CPL; ++mm) {
+                                if (BF16) f[u][mm] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.x_in)[(size_t)j * CIN + lane + 32 * mm]);
+                                else f[u][mm] = __half2float(reinterpret_cast<const __half*>(a.x_in)[(size_t)j * CIN + lane + 32 * mm]);
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                            for (int mm = 0; mm < C::CPL; ++mm) {
+                                acc[0][mm] += wv[u].x * f[u][mm];
+                                acc[1][mm] += wv[u].y * f[u][mm];
+                                acc[2][mm] += wv[u].z * f[u][mm];
+                                acc[3][mm] += wv[u].w * f[u][mm];
                             }
                         }
                     }
@@ -583,7 +601,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_cconv_tc(const ConvArgs a) 
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, 64);
+    if (warp == WORKER_WARPS) tmem_dealloc(tmem_base, 64);
 }
 
 // ------------------------------------------------------------------------------------------------

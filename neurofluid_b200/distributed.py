@@ -58,3 +58,66 @@ def render_image_sharded(net, particles, ro, rays_hw6: torch.Tensor, focal=None,
     mine = shard_rows(rays_hw6, rank, world).reshape(-1, 6).contiguous()
     out = net(particles, ro, mine, focal, c2w, **kw)[key]
     return gather_image(out.view(-1, W, out.shape[-1]), H, group)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Transition model: particle-block sharding with one all-gather per layer
+# ---------------------------------------------------------------------------------------------------
+def shard_bounds(n: int, rank: int, world: int):
+    """Contiguous, equally sized blocks of particle indices (the last block may be short or empty)."""
+    per = (n + world - 1) // world
+    b = min(rank * per, n)
+    return b, min(b + per, n)
+
+
+def allgather_rows(buf: torch.Tensor, n: int, group=None) -> None:
+    """In-place all-gather of the row blocks of `buf` ((n, C) matrix): rank g owns rows shard_bounds(n, g, G)
+    and receives everybody else's.  Blocks are padded to a common size for the collective."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return
+    rank = dist.get_rank(group)
+    per = (n + world - 1) // world
+    b, e = shard_bounds(n, rank, world)
+    mine = buf.new_zeros((per,) + tuple(buf.shape[1:]))
+    mine[: e - b] = buf[b:e]
+    out = buf.new_empty((world * per,) + tuple(buf.shape[1:]))
+    dist.all_gather_into_tensor(out, mine, group=group)
+    buf[:n] = out[:n]
+
+
+def transition_step_sharded(net, pos, vel, box, box_feats, group=None):
+    """`ParticleNet.forward` with the particles block-sharded over the ranks of `group`.
+
+    Every rank holds the full state (pos, vel).  Per phase each rank computes only its own rows; the
+    ReLU'd fp16 activation rows a layer produces are all-gathered (NCCL over NVLink) before the next layer
+    gathers neighbours from them, and the corrected positions / velocities are all-gathered at the end
+    -- the "position all-gather per step" of BASELINE.json's north_star.  4 small collectives per step."""
+    import ctypes as C
+    from . import _lib
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if world == 1:
+        return net(pos, vel, box, box_feats)
+    p, v, b, bf, outs, ws = net._prepare(pos, vel, box, box_feats, None)
+    n, m = p.shape[0], b.shape[0]
+    lo, hi = shard_bounds(n, rank, world)
+    L = _lib.lib()
+
+    def layer_rows(layer):
+        off, rb = C.c_size_t(0), C.c_size_t(0)
+        _lib.check(L.nf_transition_layer_buffer(n, m, layer, C.byref(off), C.byref(rb)), "nf_transition_layer_buffer")
+        return ws[off.value: off.value + n * rb.value].view(torch.float16).view(n, rb.value // 2)
+
+    for phase in range(5):
+        a = net._args(p, v, b, bf, outs, ws, phase=phase, shard=(lo, hi))
+        _lib.check(L.nf_transition_step(C.byref(a), _lib.stream_ptr()), "nf_transition_step")
+        if phase <= 2:
+            allgather_rows(layer_rows(phase), n, group)       # bit patterns only; dtype view is irrelevant
+    for t in outs[:2]:
+        allgather_rows(t, n, group)
+    allgather_rows(outs[2].view(n, 1), n, group)
+    allgather_rows(outs[3], n, group)
+    net.num_fluid_neighbors, net.pos_correction = outs[2], outs[3]
+    net._keep = (p, v, b, bf)
+    return outs[0], outs[1], outs[2]

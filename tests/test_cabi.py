@@ -60,3 +60,17 @@ def test_rendernet_state_dict_layout_and_errors():
         net(torch.zeros(10, 3), cw[:, 3], torch.zeros(4, 6), 1.0, cw)
     with pytest.raises(_lib.NFError):
         nb.RenderNet(scenes.render_cfg(var=False), scenes.NEAR, scenes.FAR)
+
+
+def test_particlenet_state_dict_layout():
+    net = nb.ParticleNet(gravity=(0.0, 0.0, -9.81))
+    sd = scenes.init_particle_state(0)
+    assert sorted(net.state_dict().keys()) == sorted(sd.keys())
+    net.load_state_dict(sd, strict=True)
+    assert net.conv1.kernel.shape == (4, 4, 4, 96, 64) and net.conv3.kernel.shape == (4, 4, 4, 64, 3)
+    assert net.dense1.weight.shape == (64, 96) and tuple(net.gravity.tolist()) == (0.0, 0.0, pytest.approx(-9.81))
+    assert float(net.filter_extent) == pytest.approx(0.225)
+    L = _lib.lib()
+    assert L.nf_transition_num_phases() == 5
+    assert L.nf_transition_workspace_bytes(1000, 500) > 2 * 1000 * 128 * 48
+    assert ctypes.sizeof(_lib.TransitionArgs) % 8 == 0

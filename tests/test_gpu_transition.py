@@ -1,0 +1,120 @@
+"""GPU parity tests for hot path 2 (transition model), through the C ABI via ParticleNet.
+
+Tolerances: neighbour counts bit-exact (integer work); layer 0 is fp32 (1e-5); layers 1-3 use fp16
+tensor-core operands with fp32 accumulation, so the predicted position correction is compared at 2e-3
+relative L2 and the predicted positions (what north_star bounds at 1e-3) at 1e-6.
+"""
+import numpy as np
+import pytest
+import torch
+
+import neurofluid_b200 as nb
+from neurofluid_b200 import _lib, scenes
+from oracle import transition as otrans
+from helpers import TRANSITION_CASES, load_transition_case, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def make_net(sd, dev, **kw):
+    net = nb.ParticleNet(gravity=(0.0, 0.0, -9.81), **kw)
+    net.load_state_dict(sd, strict=True)
+    return net.to(dev)
+
+
+@pytest.mark.parametrize("name", TRANSITION_CASES)
+def test_rollout_matches_reference_golden(dev, name):
+    c = load_transition_case(name)
+    g = c["g"]
+    net = make_net(c["sd"], dev)
+    pos, vel = c["pos"].to(dev), c["vel"].to(dev)
+    box, box_n = c["box"].to(dev), c["box_n"].to(dev)
+    for s in range(int(g["steps"])):          # free-running rollout, like eval_transmodel.py:87-99
+        dbg = {}
+        pos, vel, nn = net(pos, vel, box, box_n, debug=dbg)
+        assert nn.dtype == torch.float32 and nn.shape == (c["pos"].shape[0],)
+        assert np.array_equal(nn.cpu().numpy().astype(np.int16), g[f"nnbr_{s}"])
+        assert rel_l2(pos.cpu(), g[f"pos_{s}"]) < 1e-6
+        assert rel_l2(vel.cpu(), g[f"vel_{s}"]) < 1e-4
+        if s == 0:
+            assert rel_l2(dbg["feats0"].cpu(), g["feats0"]) < 1e-5
+            assert rel_l2(net.pos_correction.cpu(), g["delta0"]) < 2e-3
+
+
+def test_teacher_forced_step_vs_oracle_with_moving_particles(dev):
+    """Random velocities and a perturbed state (not a lattice at rest): every layer sees generic input."""
+    rng = np.random.RandomState(5)
+    sd = scenes.init_particle_state(3, last_layer_scale=1.0)
+    net = make_net(sd, dev)
+    pos = torch.from_numpy(scenes.lattice_particles(11, 3, jitter=0.02, center=(0.1, -0.2, -0.6)))
+    vel = torch.from_numpy(rng.normal(0, 0.5, pos.shape).astype(np.float32))
+    bp, bn = scenes.box_points(0.06)
+    box, box_n = torch.from_numpy(bp), torch.from_numpy(bn)
+    p, v, nn = net(pos.to(dev), vel.to(dev), box.to(dev), box_n.to(dev))
+    rp, rv, rn, dbg = otrans.particle_step(sd, pos, vel, box, box_n, debug=True)
+    assert torch.equal(nn.cpu(), rn)
+    assert rel_l2(net.pos_correction.cpu(), dbg["feats"][-1] / 128) < 2e-3
+    assert rel_l2(p.cpu(), rp) < 1e-5 and rel_l2(v.cpu(), rv) < 2e-3
+    # bf16 operands: same path, looser numerics
+    netb = make_net(sd, dev, operand_dtype="bf16")
+    pb, vb, nnb = netb(pos.to(dev), vel.to(dev), box.to(dev), box_n.to(dev))
+    assert torch.equal(nnb.cpu(), rn) and rel_l2(netb.pos_correction.cpu(), dbg["feats"][-1] / 128) < 2e-2
+
+
+def test_edge_cases_and_errors(dev):
+    sd = scenes.init_particle_state(0)
+    net = make_net(sd, dev)
+    bp, bn = scenes.box_points(0.1)
+    box, box_n = torch.from_numpy(bp).to(dev), torch.from_numpy(bn).to(dev)
+    # isolated particles far from everything: no neighbours -> pure gravity step + bias-only correction
+    pos = torch.tensor([[0.0, 0.0, 1.0], [0.5, 0.5, 1.5]], device=dev)
+    vel = torch.zeros_like(pos)
+    p, v, nn = net(pos, vel, box, box_n)
+    assert nn.tolist() == [0.0, 0.0] and torch.isfinite(p).all()
+    rp, rv, rn = otrans.particle_step(sd, pos.cpu(), vel.cpu(), box.cpu(), box_n.cpu())
+    assert rel_l2(p.cpu(), rp) < 1e-6
+    # coincident particles are not each other's neighbours (radius_search_ignore_query_points=True)
+    pos2 = torch.tensor([[0.0, 0.0, 0.0], [0.0, 0.0, 0.0], [0.05, 0.0, 0.0]], device=dev)
+    p2, v2, nn2 = net(pos2, torch.zeros_like(pos2), box, box_n)
+    rp2, rv2, rn2 = otrans.particle_step(sd, pos2.cpu(), torch.zeros(3, 3), box.cpu(), box_n.cpu())
+    assert torch.equal(nn2.cpu(), rn2) and nn2.tolist() == [1.0, 1.0, 2.0]
+    # empty fluid, empty box
+    e = net(pos[:0], vel[:0], box, box_n)
+    assert e[0].shape == (0, 3)
+    p3, _, nn3 = net(pos, vel, box[:0], box_n[:0])
+    assert torch.isfinite(p3).all()
+    with pytest.raises(_lib.NFError):
+        net(pos.cpu(), vel.cpu(), box.cpu(), box_n.cpu())       # no CPU fallback
+    with pytest.raises(_lib.NFError):
+        nb.ParticleNet(kernel_size=[3, 3, 3])
+    assert nb.TransModel is nb.ParticleNet and nb.ParticleNet.step is nb.ParticleNet.forward
+
+
+def test_full_size_rollout_properties(dev):
+    """BASELINE config[2]: ~30k particles (31^3), 50-step free-running rollout; physical sanity + spot parity."""
+    n = 31
+    half = (n - 1) / 2 * 0.05
+    sd = scenes.init_particle_state(0)
+    net = make_net(sd, dev)
+    pos0 = torch.from_numpy(scenes.lattice_particles(n, 0, center=(0.0, 0.0, -1 + 0.03 + half)))
+    bp, bn = scenes.box_points(0.032)
+    box, box_n = torch.from_numpy(bp).to(dev), torch.from_numpy(bn).to(dev)
+    pos, vel = pos0.to(dev), torch.zeros_like(pos0).to(dev)
+    for s in range(50):
+        prev = pos
+        pos, vel, nn = net(pos, vel, box, box_n)
+        if s == 0:
+            first = (prev.cpu(), pos.cpu(), vel.cpu(), nn.cpu())
+    assert torch.isfinite(pos).all() and torch.isfinite(vel).all()
+    assert nn.max() < 128 and nn.min() >= 0
+    # velocity is defined from the corrected positions (models/transmodel.py:147)
+    assert torch.allclose(vel, (pos - prev) * 50, atol=1e-4)
+    # step 0 against the CPU oracle at full size
+    rp, rv, rn = otrans.particle_step(sd, first[0], torch.zeros_like(first[0]), box.cpu(), box_n.cpu())
+    assert torch.equal(first[3], rn)
+    assert rel_l2(first[1], rp) < 1e-6 and rel_l2(first[2], rv) < 1e-3
