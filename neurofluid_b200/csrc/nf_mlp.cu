@@ -38,7 +38,6 @@ constexpr int KX_STEPS = 13;   // xyz-like features 198 -> 208 = 13 K-steps of 1
 constexpr int KD_STEPS = 4;    // dir-like features 54 -> 64
 constexpr int KH_STEPS = 16;   // hidden width 256
 constexpr int STAGE_BYTES = 8192;  // one K-step of a 256-row weight slab: 2 k-chunks x 256 rows x 16 B
-constexpr int NSTAGE = 7;
 constexpr int N256_STEPS = 154;
 constexpr int N128_STEPS = 20;
 constexpr int W_BYTES = N256_STEPS * 8192 + N128_STEPS * 4096;
@@ -51,13 +50,24 @@ constexpr int SP_BRGB = 3204;    // [3] (+1 pad)
 constexpr int SP_FLOATS = 3208;
 static_assert(PACKED_BYTES == W_BYTES + SP_FLOATS * 4, "packed size");
 
+// Weight ring: one stage holds a GROUP of up to G consecutive K-steps of one CTA's share of the weight slabs
+// (16 KB): the issuer waits once and commits once per group, not per MMA.
+template <bool PAIR> struct Ring {
+    static constexpr int G = PAIR ? 4 : 2;                            // K-steps per group
+    static constexpr int STEP = PAIR ? STAGE_BYTES / 2 : STAGE_BYTES;  // bytes of one N=256 K-step held by one CTA
+    static constexpr int STAGE = G * STEP;                             // 16 KB
+};
+constexpr int NSTAGE = 4;
+constexpr int RING_BYTES = NSTAGE * 16384;
+
 // shared memory map
 constexpr int SM_HIDDEN = 0;                          // 128 x 256 halves
 constexpr int SM_PEXYZ = SM_HIDDEN + 65536;           // 128 x 208 halves
 constexpr int SM_PEDIR = SM_PEXYZ + 26 * 2048;        // 2 x (128 x 64 halves)
-constexpr int SM_WRING = SM_PEDIR + 2 * 8 * 2048;     // NSTAGE x 8 KB
-constexpr int SM_SPARAM = SM_WRING + NSTAGE * STAGE_BYTES;
-constexpr int SM_BAR = SM_SPARAM + SP_FLOATS * 4;
+constexpr int SM_WRING = SM_PEDIR + 2 * 8 * 2048;     // NSTAGE x 16 KB
+constexpr int SM_SPARAM = SM_WRING + RING_BYTES;
+constexpr int SM_PART = SM_SPARAM + SP_FLOATS * 4;    // 128 x float4: head partial sums of epilogue group B
+constexpr int SM_BAR = SM_PART + 128 * 16;
 constexpr int NUM_BARS = 2 * NSTAGE + 12;
 constexpr int SM_TMEM_SLOT = SM_BAR + NUM_BARS * 8;
 constexpr int SM_TOTAL = SM_TMEM_SLOT + 16;
@@ -76,7 +86,12 @@ enum Bar {
 };
 static_assert(B_ACC_FULL + 2 == NUM_BARS, "barrier count");
 
-constexpr int NUM_THREADS = 320;
+// warp roles
+constexpr int W_EPI = 0;        // warps 0-7: epilogue, two groups of four (TMEM lane quarter = warp & 3)
+constexpr int W_ISSUE = 8;      // MMA issuer (rank 0) / weight relay (rank 1 of a pair)
+constexpr int W_LOAD = 9;       // weight producer
+constexpr int W_PE = 10;        // warps 10-13: positional-encoding producers
+constexpr int NUM_THREADS = 14 * 32;
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -102,6 +117,39 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "memory");
     } while (!ok);
 }
+// ---- cluster (CTA pair) variants
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {  // shared::cta -> shared::cluster of CTA `rank`
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+// Arrive on a barrier anywhere in the cluster window.  Default semantics (release at CTA scope), as in
+// CUTLASS's ClusterBarrier::arrive(cta_id): a cluster-scope release costs ~1000 cycles per arrive (measured),
+// and the data guarded here is this CTA's own shared memory, ordered for the tensor core by fence.proxy.async.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {  // acquire at cluster scope
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
@@ -111,26 +159,56 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+template <bool PAIR>
 __device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {  // executed by the same warp of both CTAs of the pair
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
 }
+template <bool PAIR>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+    if constexpr (PAIR)
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+    else
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem]^T, kind::f16 (fp16 or bf16 operands, fp32 accumulate)
+// PAIR: one instruction drives both SMs of the pair -- M = 256 (128 rows of A and of D per CTA), each CTA
+// supplies half of the N rows of B from its own shared memory (same offsets in both CTAs).
+template <bool PAIR>
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
+    if constexpr (PAIR)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
 }
+// PAIR: the arrive is multicast to the barrier at the same offset in both CTAs.
+template <bool PAIR>
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    if constexpr (PAIR)
+        asm volatile(
+            "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+            "h"((uint16_t)3)
+            : "memory");
+    else
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
     asm volatile(
@@ -159,9 +237,9 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
     d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
     return d;                // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
 }
-__device__ __forceinline__ uint32_t umma_idesc(int n, bool bf16) {
+__device__ __forceinline__ uint32_t umma_idesc(int n, bool bf16, int m) {
     const uint32_t fmt = bf16 ? 1u : 0u;
-    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 template <bool BF16>
@@ -237,37 +315,80 @@ __device__ __forceinline__ void emit_encoding(RowWriter<BF16>& w, const float* v
 }
 
 __device__ __forceinline__ int layer_pe_steps(int l) { return (l == 0 || l == 4) ? KX_STEPS : (l == 9 ? KD_STEPS : 0); }
+// number of weight groups (ring stages) one tile consumes: every layer's PE segment and hidden segment is cut
+// into groups of G K-steps (last group of a segment may be shorter)
+template <int G>
+__device__ __forceinline__ int weight_groups(int nl) {
+    int n = 0;
+    for (int l = 0; l < nl; ++l) n += (layer_pe_steps(l) + G - 1) / G + (l > 0 ? KH_STEPS / G : 0);
+    return n;
+}
 
-#define NF_TRACE(slot) do { if (a.trace && blockIdx.x == 0 && ti == 2) a.trace[(slot)] = clock64(); } while (0)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+template <class T>
+__device__ __forceinline__ T uniform(T v) { return __shfl_sync(0xffffffffu, v, 0); }   // provably warp-uniform copy
 
-template <bool BF16>
+#define NF_TRACE(slot) do { if (tracing) a.trace[(slot)] = clock64(); } while (0)
+
+// PAIR = two CTAs on the two SMs of a TPC run as one unit (cluster of 2, tcgen05 cta_group::2): each CTA owns a
+// 128-row tile (A operand, TMEM accumulator, PE producers, epilogue) and streams only HALF of every weight slab
+// (its half of the N output rows of B), so the L2 -> SM weight traffic per FLOP halves.  CTA rank 0 issues every
+// MMA; "operand ready" barriers live in rank 0 and collect one arrive per producing warp of both CTAs (remote
+// arrives through the cluster window); "accumulator full" / "slot free" commits are multicast to both CTAs.
+//
+// The issuer warp runs converged and elects one lane around the tcgen05 instructions only, so that descriptors
+// and barrier addresses stay in uniform registers; it waits and commits once per GROUP of K-steps (one ring
+// stage), not per MMA.  (Round-1 build: one divergent lane, wait + commit per MMA = ~70 SASS instructions
+// and ~360 cycles per 178-cycle MMA -- the kernel was issue-bound, profiles/r01_notes.md.)
+template <bool BF16, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp(const KernelArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int n_rows = a.n_rows_dev ? min(*a.n_rows_dev, a.n_rows_cap) : a.n_rows_host;
+    constexpr int G = Ring<PAIR>::G;
+    constexpr int STEP = Ring<PAIR>::STEP;
+    constexpr int STAGE = Ring<PAIR>::STAGE;
+    constexpr int TPU = PAIR ? 2 : 1;   // tiles per unit (CTA or CTA pair) per pass
+    const int warp = uniform((int)(threadIdx.x >> 5)), lane = threadIdx.x & 31;
+    const uint32_t crank = PAIR ? uniform(cluster_ctarank()) : 0u;
+    const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int nunits = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int n_rows = uniform(a.n_rows_dev ? min(*a.n_rows_dev, a.n_rows_cap) : a.n_rows_host);
     const int ntiles = (n_rows + TILE_M - 1) / TILE_M;
-    if ((int)blockIdx.x >= ntiles) return;
+    const int npass = (ntiles + TPU - 1) / TPU;
+    if (unit >= npass) return;          // both CTAs of a pair leave together
     const int nl = a.n_layers;
+    const bool no_weights = (a.desc_swap & 16) != 0;   // debug: do not stream / wait for weights (timing only)
 
     const uint32_t s_base = smem_u32(smem);
     const uint32_t s_hidden = s_base + SM_HIDDEN, s_pexyz = s_base + SM_PEXYZ, s_pedir = s_base + SM_PEDIR;
     const uint32_t s_wring = s_base + SM_WRING, s_bar = s_base + SM_BAR;
     float* sp = reinterpret_cast<float*>(smem + SM_SPARAM);
+    float4* part = reinterpret_cast<float4*>(smem + SM_PART);
     auto bar = [&](int i) { return s_bar + 8u * (uint32_t)i; };
+    // "operand ready" barriers are consumed by the issuer in CTA rank 0
+    auto ready_bar = [&](int i) { return PAIR ? mapa_rank(bar(i), 0) : bar(i); };
+    constexpr uint32_t READY_COUNT = PAIR ? 8 : 4;   // PE tiles: one arrive per producing warp (4 per CTA)
+    constexpr uint32_t ACT_COUNT = PAIR ? 16 : 8;    // activation chunks: all 8 epilogue warps of a CTA
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSTAGE; ++i) {
-            mbar_init(bar(B_WFULL + i), 1);
+            mbar_init(bar(B_WFULL + i), (PAIR && crank == 0) ? 2 : 1);   // own bulk copies (+ the peer's relay)
             mbar_init(bar(B_WEMPTY + i), 1);
         }
-        mbar_init(bar(B_PEXYZ_READY), 128);
+        mbar_init(bar(B_PEXYZ_READY), READY_COUNT);
         mbar_init(bar(B_PEXYZ_FREE), 1);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(bar(B_PEDIR_READY + i), 128);
+            mbar_init(bar(B_PEDIR_READY + i), READY_COUNT);
             mbar_init(bar(B_PEDIR_FREE + i), 1);
             mbar_init(bar(B_ACC_FULL + i), 1);
         }
-        for (int i = 0; i < 4; ++i) mbar_init(bar(B_ACT_READY + i), 128);
+        for (int i = 0; i < 4; ++i) mbar_init(bar(B_ACT_READY + i), ACT_COUNT);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     {   // small params -> smem
@@ -275,130 +396,192 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp(const KernelArgs a)
         float4* dst = reinterpret_cast<float4*>(sp);
         for (int i = threadIdx.x; i < SP_FLOATS / 4; i += NUM_THREADS) dst[i] = __ldg(src + i);
     }
-    if (warp == 4) tmem_alloc(s_base + SM_TMEM_SLOT, 512);
+    if (warp == W_ISSUE) tmem_alloc<PAIR>(s_base + SM_TMEM_SLOT, 512);
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();
     tc_fence_after();
-    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM_SLOT);
+    const uint32_t tmem_base = uniform(*reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM_SLOT));
 
-    const uint32_t a_lbo = a.desc_swap ? 128u : 2048u, a_sbo = a.desc_swap ? 2048u : 128u;
-
-    if (warp == 4) {
-        // ================================================================ MMA issuer
-        if (lane == 0) {
+    if (warp == W_ISSUE) {
+        if (crank == 0) {
+            // ================================================================ MMA issuer (rank 0; converged warp)
+            const uint64_t adesc_hidden = umma_desc(s_hidden, 2048u, 128u);
+            const uint64_t adesc_pexyz = umma_desc(s_pexyz, 2048u, 128u);
+            const uint64_t adesc_pedir = umma_desc(s_pedir, 2048u, 128u);
+            const uint32_t idesc256 = umma_idesc(256, BF16, PAIR ? 2 * TILE_M : TILE_M);
+            const uint32_t idesc128 = umma_idesc(128, BF16, PAIR ? 2 * TILE_M : TILE_M);
+            const uint64_t bdesc256 = umma_desc(s_wring, (PAIR ? 128u : 256u) * 16u, 128u);
+            const uint64_t bdesc128 = umma_desc(s_wring, (PAIR ? 64u : 128u) * 16u, 128u);
             uint32_t ws = 0, wph = 0, hidw = 0, lc = 0;
             int ti = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+            for (int pass = unit; pass < npass; pass += nunits, ++ti) {
+                const bool tracing = a.trace && blockIdx.x == 0 && ti == 2 && lane == 0;
                 for (int l = 0; l < nl; ++l, ++lc) {
                     const uint32_t d_tmem = tmem_base + (lc & 1) * 256;
-                    const int n = (l == 9) ? 128 : 256;
-                    const uint32_t idesc = umma_idesc(n, BF16);
-                    const uint32_t b_lbo = a.desc_swap ? 128u : (uint32_t)n * 16u;
-                    const uint32_t b_sbo = a.desc_swap ? (uint32_t)n * 16u : 128u;
+                    const bool n128 = (l == 9);
+                    const uint32_t idesc = n128 ? idesc128 : idesc256;
+                    const uint64_t bdesc0 = n128 ? bdesc128 : bdesc256;
+                    const uint32_t bstep = (n128 ? STEP / 2 : STEP) >> 4;      // descriptor units (16 B) per K-step
                     uint32_t acc = 0;
                     NF_TRACE(100 + l * 8);
                     const int npe = layer_pe_steps(l);
                     if (npe) {
-                        uint32_t abase;
+                        uint64_t adesc;
                         if (l == 9) {
                             mbar_wait(bar(B_PEDIR_READY + (ti & 1)), (ti >> 1) & 1);
-                            abase = s_pedir + (ti & 1) * (8 * 2048);
+                            adesc = adesc_pedir + (uint64_t)((ti & 1) * ((8 * 2048) >> 4));
                         } else {
                             mbar_wait(bar(B_PEXYZ_READY), ti & 1);
-                            abase = s_pexyz;
+                            adesc = adesc_pexyz;
                         }
-                        tc_fence_after();
-                        for (int j = 0; j < npe; ++j) {
-                            mbar_wait(bar(B_WFULL + ws), wph);
+                        for (int j0 = 0; j0 < npe; j0 += G) {
+                            const int g = min(G, npe - j0);
+                            if (!no_weights) mbar_wait(bar(B_WFULL + ws), wph);
                             tc_fence_after();
-                            umma_f16(d_tmem, umma_desc(abase + j * 4096, a_lbo, a_sbo),
-                                     umma_desc(s_wring + ws * STAGE_BYTES, b_lbo, b_sbo), idesc, acc);
+                            if (elect_one()) {
+                                const uint64_t bd = bdesc0 + (uint64_t)(ws * (STAGE >> 4));
+#pragma unroll
+                                for (int j = 0; j < G; ++j) {
+                                    if (j < g) {
+                                        umma_f16<PAIR>(d_tmem, adesc + (uint64_t)((j0 + j) * (4096 >> 4)), bd + (uint64_t)(j * bstep),
+                                                       idesc, acc);
+                                        acc = 1;
+                                    }
+                                }
+                                umma_commit<PAIR>(bar(B_WEMPTY + ws));
+                            }
+                            __syncwarp();
                             acc = 1;
-                            umma_commit(bar(B_WEMPTY + ws));
                             if (++ws == NSTAGE) { ws = 0; wph ^= 1; }
                         }
-                        if (l == 4) umma_commit(bar(B_PEXYZ_FREE));
+                        if (l == 4 && elect_one()) umma_commit<PAIR>(bar(B_PEXYZ_FREE));
+                        __syncwarp();
                     }
                     if (l > 0) {
-                        for (int j = 0; j < KH_STEPS; ++j) {
-                            if ((j & 3) == 0) {
-                                mbar_wait(bar(B_ACT_READY + (j >> 2)), hidw & 1);
-                                tc_fence_after();
-                                NF_TRACE(100 + l * 8 + 1 + (j >> 2));
+                        for (int j0 = 0; j0 < KH_STEPS; j0 += G) {
+                            if ((j0 & 3) == 0) {
+                                mbar_wait(bar(B_ACT_READY + (j0 >> 2)), hidw & 1);
+                                NF_TRACE(100 + l * 8 + 1 + (j0 >> 2));
                             }
-                            mbar_wait(bar(B_WFULL + ws), wph);
+                            if (!no_weights) mbar_wait(bar(B_WFULL + ws), wph);
                             tc_fence_after();
-                            umma_f16(d_tmem, umma_desc(s_hidden + j * 4096, a_lbo, a_sbo),
-                                     umma_desc(s_wring + ws * STAGE_BYTES, b_lbo, b_sbo), idesc, acc);
+                            if (elect_one()) {
+                                const uint64_t bd = bdesc0 + (uint64_t)(ws * (STAGE >> 4));
+#pragma unroll
+                                for (int j = 0; j < G; ++j) {
+                                    umma_f16<PAIR>(d_tmem, adesc_hidden + (uint64_t)((j0 + j) * (4096 >> 4)), bd + (uint64_t)(j * bstep),
+                                                   idesc, acc);
+                                    acc = 1;
+                                }
+                                umma_commit<PAIR>(bar(B_WEMPTY + ws));
+                            }
+                            __syncwarp();
                             acc = 1;
-                            umma_commit(bar(B_WEMPTY + ws));
                             if (++ws == NSTAGE) { ws = 0; wph ^= 1; }
                         }
                         ++hidw;
                     }
-                    umma_commit(bar(B_ACC_FULL + (lc & 1)));
+                    if (elect_one()) {
+                        umma_commit<PAIR>(bar(B_ACC_FULL + (lc & 1)));
+                        if (l == 9) umma_commit<PAIR>(bar(B_PEDIR_FREE + (ti & 1)));
+                    }
+                    __syncwarp();
                     NF_TRACE(100 + l * 8 + 5);
-                    if (l == 9) umma_commit(bar(B_PEDIR_FREE + (ti & 1)));
                 }
             }
-        }
-    } else if (warp == 5) {
-        // ================================================================ weight producer
-        if (lane == 0) {
+        } else if (PAIR && lane == 0 && !no_weights) {
+            // ================================================================ relay (rank 1): tells the issuer
+            // that this CTA's share of a weight group has landed
             uint32_t ws = 0, wph = 0;
-            const int nsteps = (nl == 10) ? (N256_STEPS + N128_STEPS) : 138;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const uint8_t* src = a.packed;
-                for (int s = 0; s < nsteps; ++s) {
-                    const uint32_t bytes = (s < N256_STEPS) ? 8192u : 4096u;
-                    mbar_wait(bar(B_WEMPTY + ws), wph ^ 1);
-                    mbar_arrive_expect_tx(bar(B_WFULL + ws), bytes);
-                    bulk_g2s(s_wring + ws * STAGE_BYTES, src, bytes, bar(B_WFULL + ws));
-                    src += bytes;
+            const int ngroups = weight_groups<G>(nl);
+            const uint32_t remote0 = mapa_rank(bar(B_WFULL), 0);
+            for (int pass = unit; pass < npass; pass += nunits) {
+                for (int s = 0; s < ngroups; ++s) {
+                    mbar_wait(bar(B_WFULL + ws), wph);
+                    mbar_arrive_cluster(remote0 + 8u * ws);
                     if (++ws == NSTAGE) { ws = 0; wph ^= 1; }
                 }
             }
         }
-    } else if (warp < 4) {
-        // ================================================================ epilogue (thread = row)
-        const int tr = threadIdx.x;  // 0..127
+    } else if (warp == W_LOAD) {
+        // ================================================================ weight producer
+        if (lane == 0 && !no_weights) {
+            uint32_t ws = 0, wph = 0;
+            for (int pass = unit; pass < npass; pass += nunits) {
+                const uint8_t* src = a.packed;
+                for (int l = 0; l < nl; ++l) {
+                    const uint32_t full = (l == 9) ? 4096u : 8192u;          // bytes of one K-step of this layer
+                    const uint32_t mine = PAIR ? full / 2 : full;            // PAIR layout: [half][k-chunk][row][8]
+                    const int npe = layer_pe_steps(l);
+                    for (int seg = 0; seg < 2; ++seg) {
+                        const int nsteps = seg == 0 ? npe : (l > 0 ? KH_STEPS : 0);
+                        for (int j0 = 0; j0 < nsteps; j0 += G) {
+                            const int g = min(G, nsteps - j0);
+                            mbar_wait(bar(B_WEMPTY + ws), wph ^ 1);
+                            mbar_arrive_expect_tx(bar(B_WFULL + ws), (uint32_t)g * mine);
+                            for (int j = 0; j < g; ++j)
+                                bulk_g2s(s_wring + ws * STAGE + j * mine, src + (size_t)j * full + (PAIR ? crank * mine : 0u), mine,
+                                         bar(B_WFULL + ws));
+                            src += (size_t)g * full;
+                            if (++ws == NSTAGE) { ws = 0; wph ^= 1; }
+                        }
+                    }
+                }
+            }
+            if constexpr (PAIR) {   // every multicast "slot free" arrive has landed before this CTA may exit
+                for (int i = 0; i < NSTAGE; ++i) {
+                    mbar_wait(bar(B_WEMPTY + ws), wph ^ 1);
+                    if (++ws == NSTAGE) { ws = 0; wph ^= 1; }
+                }
+            }
+        }
+    } else if (warp < W_ISSUE) {
+        // ================================================================ epilogue: thread = (row, column half)
+        // both groups drain every 64-column chunk together: group g (warps 4g..4g+3) owns columns [64c+32g, +32)
+        // of chunk c; the TMEM load of chunk c+1 is in flight while chunk c is processed.
+        const int grp = warp >> 2;
+        const int tr = (warp & 3) * 32 + lane;   // row of the tile = TMEM lane
         uint32_t lc = 0;
         int ti = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
-            const int row = tile * TILE_M + tr;
+        const uint32_t act_ready0 = ready_bar(B_ACT_READY);
+        for (int pass = unit; pass < npass; pass += nunits, ++ti) {
+            const bool tracing = a.trace && blockIdx.x == 0 && ti == 2 && (tr == 0);
+            const int row = (pass * TPU + (int)crank) * TILE_M + tr;
             float sigma = 0.f;
             for (int l = 0; l < nl; ++l, ++lc) {
                 const uint32_t buf = lc & 1;
                 mbar_wait(bar(B_ACC_FULL + buf), (lc >> 1) & 1);
                 tc_fence_after();
-                if (tr == 0) NF_TRACE(l * 8);
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 256;
+                if (grp == 0) NF_TRACE(l * 8);
+                const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + buf * 256 + grp * 32;
                 if (l < 9) {
                     const bool writes = (l + 1 < nl);
-                    const float* bias = sp + SP_BIAS + l * 256;
-#pragma unroll 1
-                    for (int c = 0; c < 4; ++c) {
-                        uint32_t v[64];
-                        tmem_ld32(taddr + c * 64, v);
-                        tmem_ld32(taddr + c * 64 + 32, v + 32);
-                        tmem_ld_wait();
-                        float f[64];
+                    const float* bias = sp + SP_BIAS + l * 256 + grp * 32;
+                    uint32_t v[2][32];
+                    tmem_ld32(taddr, v[0]);
 #pragma unroll
-                        for (int i = 0; i < 64; i += 4) {
+                    for (int c = 0; c < 4; ++c) {
+                        tmem_ld_wait();
+                        if (c < 3) tmem_ld32(taddr + (c + 1) * 64, v[(c + 1) & 1]);
+                        const uint32_t* vc = v[c & 1];
+                        float f[32];
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
                             const float4 b4 = *reinterpret_cast<const float4*>(bias + c * 64 + i);
-                            f[i] = __uint_as_float(v[i]) + b4.x;
-                            f[i + 1] = __uint_as_float(v[i + 1]) + b4.y;
-                            f[i + 2] = __uint_as_float(v[i + 2]) + b4.z;
-                            f[i + 3] = __uint_as_float(v[i + 3]) + b4.w;
+                            f[i] = __uint_as_float(vc[i]) + b4.x;
+                            f[i + 1] = __uint_as_float(vc[i + 1]) + b4.y;
+                            f[i + 2] = __uint_as_float(vc[i + 2]) + b4.z;
+                            f[i + 3] = __uint_as_float(vc[i + 3]) + b4.w;
                         }
                         if (l != 8) {
 #pragma unroll
-                            for (int i = 0; i < 64; ++i) f[i] = fmaxf(f[i], 0.f);
+                            for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
                         }
                         if (l == 7) {
-                            const float* wsig = sp + SP_WSIG + c * 64;
+                            const float* wsig = sp + SP_WSIG + c * 64 + grp * 32;
 #pragma unroll
-                            for (int i = 0; i < 64; i += 4) {
+                            for (int i = 0; i < 32; i += 4) {
                                 const float4 w4 = *reinterpret_cast<const float4*>(wsig + i);
                                 sigma = fmaf(f[i], w4.x, sigma);
                                 sigma = fmaf(f[i + 1], w4.y, sigma);
@@ -407,64 +590,77 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp(const KernelArgs a)
                             }
                         }
                         if (writes) {
-                            const uint32_t dst = s_hidden + (uint32_t)(c * 8) * 2048 + (uint32_t)tr * 16;
+                            const uint32_t dst = s_hidden + (uint32_t)(c * 8 + grp * 4) * 2048 + (uint32_t)tr * 16;
 #pragma unroll
-                            for (int q = 0; q < 8; ++q)
+                            for (int q = 0; q < 4; ++q)
                                 st_shared_v4(dst + q * 2048, pack2<BF16>(f[8 * q], f[8 * q + 1]),
                                              pack2<BF16>(f[8 * q + 2], f[8 * q + 3]),
                                              pack2<BF16>(f[8 * q + 4], f[8 * q + 5]),
                                              pack2<BF16>(f[8 * q + 6], f[8 * q + 7]));
                             fence_proxy_async();
                             tc_fence_before();
-                            mbar_arrive(bar(B_ACT_READY + c));
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_cluster(act_ready0 + 8u * c);
                         }
-                        if (tr == 0) NF_TRACE(l * 8 + 1 + c);
+                        if (grp == 0) NF_TRACE(l * 8 + 1 + c);
                     }
-                    if (l == 7) {
-                        sigma += sp[SP_BSIG];
-                        if (!writes && row < n_rows) {  // sigma-only network
+                    if (l == 7 && !writes) {  // sigma-only network: combine the two column halves and emit
+                        tc_fence_before();
+                        if (grp == 1) part[tr] = make_float4(0.f, 0.f, 0.f, sigma);
+                        named_bar_sync(1, 256);
+                        if (grp == 0 && row < n_rows) {
                             const int dst = a.rowid ? a.rowid[row] : row;
-                            if (dst >= 0) a.out4[dst] = make_float4(0.f, 0.f, 0.f, sigma);
+                            if (dst >= 0) a.out4[dst] = make_float4(0.f, 0.f, 0.f, sigma + part[tr].w + sp[SP_BSIG]);
                         }
+                        named_bar_sync(2, 256);   // part[] may be rewritten by the next tile only after it was read
                     }
                 } else {
+                    // rgb head on the 128-wide dir layer: group g owns columns [64c + 32g, +32), c = 0, 1
                     float rgb[3] = {0.f, 0.f, 0.f};
-                    const float* bias = sp + SP_BIAS + 9 * 256;
-#pragma unroll 1
-                    for (int c = 0; c < 2; ++c) {
-                        uint32_t v[64];
-                        tmem_ld32(taddr + c * 64, v);
-                        tmem_ld32(taddr + c * 64 + 32, v + 32);
-                        tmem_ld_wait();
+                    const float* bias = sp + SP_BIAS + 9 * 256 + grp * 32;
+                    const float* wrgb = sp + SP_WRGB + grp * 32;
+                    uint32_t v[2][32];
+                    tmem_ld32(taddr, v[0]);
+                    tmem_ld32(taddr + 64, v[1]);
+                    tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 64; ++i) {
-                            const float f = fmaxf(__uint_as_float(v[i]) + bias[c * 64 + i], 0.f);
-                            rgb[0] = fmaf(f, sp[SP_WRGB + c * 64 + i], rgb[0]);
-                            rgb[1] = fmaf(f, sp[SP_WRGB + 128 + c * 64 + i], rgb[1]);
-                            rgb[2] = fmaf(f, sp[SP_WRGB + 256 + c * 64 + i], rgb[2]);
+                    for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float f = fmaxf(__uint_as_float(v[c][i]) + bias[c * 64 + i], 0.f);
+                            rgb[0] = fmaf(f, wrgb[c * 64 + i], rgb[0]);
+                            rgb[1] = fmaf(f, wrgb[128 + c * 64 + i], rgb[1]);
+                            rgb[2] = fmaf(f, wrgb[256 + c * 64 + i], rgb[2]);
                         }
                     }
                     tc_fence_before();
-                    if (row < n_rows) {
+                    if (grp == 1) part[tr] = make_float4(rgb[0], rgb[1], rgb[2], sigma);
+                    named_bar_sync(1, 256);
+                    if (grp == 0 && row < n_rows) {
                         const int dst = a.rowid ? a.rowid[row] : row;
                         if (dst >= 0) {
+                            const float4 pb = part[tr];
                             float4 o;
-                            o.x = 1.0f / (1.0f + expf(-(rgb[0] + sp[SP_BRGB])));
-                            o.y = 1.0f / (1.0f + expf(-(rgb[1] + sp[SP_BRGB + 1])));
-                            o.z = 1.0f / (1.0f + expf(-(rgb[2] + sp[SP_BRGB + 2])));
-                            o.w = sigma;
+                            o.x = 1.0f / (1.0f + expf(-(rgb[0] + pb.x + sp[SP_BRGB])));
+                            o.y = 1.0f / (1.0f + expf(-(rgb[1] + pb.y + sp[SP_BRGB + 1])));
+                            o.z = 1.0f / (1.0f + expf(-(rgb[2] + pb.z + sp[SP_BRGB + 2])));
+                            o.w = sigma + pb.w + sp[SP_BSIG];
                             a.out4[dst] = o;
                         }
                     }
+                    named_bar_sync(2, 256);
                 }
             }
         }
     } else {
-        // ================================================================ PE producers (warps 6-9)
-        const int tp = threadIdx.x - 192;  // 0..127
+        // ================================================================ PE producers (warps 10-13)
+        const int tp = threadIdx.x - W_PE * 32;  // 0..127
         int ti = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
-            const int row = tile * TILE_M + tp;
+        const uint32_t pexyz_ready = ready_bar(B_PEXYZ_READY);
+        const uint32_t pedir_ready0 = ready_bar(B_PEDIR_READY), pedir_ready1 = ready_bar(B_PEDIR_READY + 1);
+        for (int pass = unit; pass < npass; pass += nunits, ++ti) {
+            const bool tracing = a.trace && blockIdx.x == 0 && ti == 2 && tp == 0;
+            const int row = (pass * TPU + (int)crank) * TILE_M + tp;
             float r[16];
             if (row < n_rows) {
                 const float4* src = reinterpret_cast<const float4*>(a.records + (size_t)row * 16);
@@ -479,7 +675,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp(const KernelArgs a)
             }
             // xyz-like block: [PE10(x) 63 | PE4(density) 9 | PE10(smoothed) 63 | PE10(variance) 63 | 0 x10]
             mbar_wait(bar(B_PEXYZ_FREE), (ti & 1) ^ 1);
-            if (tp == 0) NF_TRACE(300);
+            NF_TRACE(300);
             {
                 RowWriter<BF16> w;
                 w.base = s_pexyz + (uint32_t)tp * 16;
@@ -490,8 +686,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp(const KernelArgs a)
                 static_for<198, 208>([&](auto ci) { w.template put<decltype(ci)::value>(0.f); });
             }
             fence_proxy_async();
-            mbar_arrive(bar(B_PEXYZ_READY));
-            if (tp == 0) NF_TRACE(301);
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(pexyz_ready);
+            NF_TRACE(301);
             if (nl == 10) {
                 // dir-like block: [PE4(ray dir) 27 | PE4(smoothed dir) 27 | 0 x10]
                 mbar_wait(bar(B_PEDIR_FREE + (ti & 1)), ((ti >> 1) & 1) ^ 1);
@@ -501,15 +698,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp(const KernelArgs a)
                 emit_encoding<BF16, 27, 3, 4>(w, r + 13);
                 static_for<54, 64>([&](auto ci) { w.template put<decltype(ci)::value>(0.f); });
                 fence_proxy_async();
-                mbar_arrive(bar(B_PEDIR_READY + (ti & 1)));
-                if (tp == 0) NF_TRACE(302);
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster((ti & 1) ? pedir_ready1 : pedir_ready0);
+                NF_TRACE(302);
             }
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem_base, 512);
+    if constexpr (PAIR) cluster_sync_all();
+    if (warp == W_ISSUE) tmem_dealloc<PAIR>(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -535,8 +734,9 @@ __device__ __forceinline__ void step_source(int s, int& layer, int& k0, int& src
     else { layer = 9; k0 = (s - 158) * 16; src_off = 0; src_valid = 256; ld = 310; }
 }
 
+// pair != 0: rows of every slab are split in two halves, one per CTA of a pair: [half][kc][n % (nrows/2)][e]
 template <bool BF16>
-__global__ void k_pack_weights(PackArgs p, uint8_t* out) {
+__global__ void k_pack_weights(PackArgs p, uint8_t* out, int pair) {
     // one thread per (step, kc, n): writes 8 halves (16 B)
     const int total = N256_STEPS * 2 * 256 + N128_STEPS * 2 * 128;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -562,7 +762,8 @@ __global__ void k_pack_weights(PackArgs p, uint8_t* out) {
             const float vb = kb < src_valid ? W[(size_t)n * ld + src_off + kb] : 0.f;
             pk[e >> 1] = pack2<BF16>(va, vb);
         }
-        uint4* dst = reinterpret_cast<uint4*>(out + byte_off + ((size_t)kc * nrows + n) * 16);
+        const int nh = pair ? nrows / 2 : nrows;
+        uint4* dst = reinterpret_cast<uint4*>(out + byte_off + ((size_t)((n / nh) * 2 + kc) * nh + (n % nh)) * 16);
         *dst = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
     // small params
@@ -580,23 +781,43 @@ __global__ void k_pack_weights(PackArgs p, uint8_t* out) {
     }
 }
 
-int launch(const KernelArgs& a, int dtype, cudaStream_t st) {
-    static bool attr_set[2] = {false, false};
-    const int di = dtype == NF_DTYPE_BF16 ? 1 : 0;
-    if (!attr_set[di]) {
-        if (di)
-            NF_CUDA_OK(cudaFuncSetAttribute(k_nerf_mlp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-        else
-            NF_CUDA_OK(cudaFuncSetAttribute(k_nerf_mlp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-        attr_set[di] = true;
+bool pair_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* v = getenv("NF_MLP_PAIR");
+        mode = v ? (atoi(v) != 0) : 1;
     }
-    const int grid = num_sms();
-    if (di)
-        k_nerf_mlp<true><<<grid, NUM_THREADS, SM_TOTAL, st>>>(a);
-    else
-        k_nerf_mlp<false><<<grid, NUM_THREADS, SM_TOTAL, st>>>(a);
-    NF_LAUNCH_OK();
+    return mode != 0;
+}
+
+template <bool BF16, bool PAIR>
+static int launch_t(const KernelArgs& a, cudaStream_t st) {
+    static bool attr_set = false;
+    auto* kern = k_nerf_mlp<BF16, PAIR>;
+    if (!attr_set) {
+        NF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(num_sms() & ~1), 1, 1);
+    cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = SM_TOTAL;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    NF_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, a));
     return NF_OK;
+}
+
+int launch(const KernelArgs& a, int dtype, cudaStream_t st) {
+    const bool bf = dtype == NF_DTYPE_BF16;
+    if (pair_mode()) return bf ? launch_t<true, true>(a, st) : launch_t<false, true>(a, st);
+    return bf ? launch_t<true, false>(a, st) : launch_t<false, false>(a, st);
 }
 
 }  // namespace mlp
@@ -618,9 +839,9 @@ extern "C" int nf_render_pack_weights(const float* const* params, int dtype, voi
     }
     const int total = mlp::N256_STEPS * 512 + mlp::N128_STEPS * 256;
     if (dtype == NF_DTYPE_BF16)
-        mlp::k_pack_weights<true><<<(total + 255) / 256, 256, 0, st>>>(p, (uint8_t*)packed_out);
+        mlp::k_pack_weights<true><<<(total + 255) / 256, 256, 0, st>>>(p, (uint8_t*)packed_out, mlp::pair_mode());
     else
-        mlp::k_pack_weights<false><<<(total + 255) / 256, 256, 0, st>>>(p, (uint8_t*)packed_out);
+        mlp::k_pack_weights<false><<<(total + 255) / 256, 256, 0, st>>>(p, (uint8_t*)packed_out, mlp::pair_mode());
     NF_LAUNCH_OK();
     return NF_OK;
 }
