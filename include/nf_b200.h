@@ -143,9 +143,10 @@ typedef struct nf_render_args {
     /* scratch */
     void* workspace;
     size_t workspace_bytes;
-    /* optional statistics written by the device (may be NULL): int32[8] =
+    /* optional statistics written by the device (may be NULL): int32[16] =
        {MLP rows coarse, MLP rows fine, active samples coarse, active samples fine,
-        fine-pass queries answered by the lockstep / row-scan search, their loop iterations / 64} */
+        fine pass: group scans, solo row-scan queries, scan steps / 64, candidates tested / 64,
+        coarse pass: the same four, 4 reserved} */
     int32_t* stats;
 } nf_render_args;
 

@@ -35,13 +35,16 @@ constexpr int WARPS_PER_BLOCK = 8;
 struct StageArgs {
     GridView g;
     const float* particles;
+    int n_points;
     const float* rays;
     int n_rays;
     float ro[3];
     float radius;
     int K;
     int use_mask, white_bg, mode;
-    int lockstep_min_occ;
+    int search_mode;                           // 0 = index-order stream, 1 = sorted-candidate sweep
+    float sub_span;                            // sweep: max depth span of one sub-group
+    int solo_max_occ, peel_lanes, peel_from;   // stream: tuning, see search_stream
     const float* z_coarse;
     const float* u_imp;
     int S0, n_imp, S1;
@@ -52,7 +55,8 @@ struct StageArgs {
     long long* num_nn1;
     // workspace
     int* counters;       // [0] rows coarse, [1] rows fine, [2] active coarse, [3] active fine,
-                         // [4..7] fine-pass query statistics: lockstep queries, row-scan queries, their iterations (/64)
+                         // [4..7] fine-pass search statistics: group scans, solo (row-scan) queries, scan steps / 64,
+                         // candidates tested + row-scan iterations / 64; [8..11] the same for the coarse pass
     unsigned* act0;      // (R, NS0)
     unsigned* act1;      // (R, NS1)
     float* z1;           // (R, S1)
@@ -61,26 +65,17 @@ struct StageArgs {
 };
 
 // ------------------------------------------------------------------------------------------------
-// Neighbour search + local geometry for all samples of one ray: one LANE per sample, 32 consecutive
-// samples of the ray per step.  The first-K-by-index rule means "scan the particles in original index
-// order and keep the first K inside the ball", so that is what the warp does -- but it only looks at
-// particles whose grid cell can matter to a still-unfinished lane: a per-warp 8192-bit cell bitmap
-// (hashed; false positives are harmless) is the union of the <= 27 neighbourhood cells of the unfinished
-// lanes and is rebuilt whenever their number halves.  Each 32-particle step reads one 128-byte line of
-// cell ids, ballots the bitmap test, and every surviving candidate is fetched once (warp-uniform 16-byte
-// load) and tested by all lanes.  Hits arrive in ascending index order, so a lane just appends until it
-// has K; no sorting, no selection.  The loop ends when every lane is finished.
+// Search flavour 1, "index-order stream" (any P).  One LANE per sample: the warp streams the particle set in
+// original index order, 128 per step, through a per-warp bitmap over half-resolution grid cells (the union of
+// the cells within reach of a still-unfinished lane), broadcasts the survivors and every lane appends its hits
+// until it has K.  Lanes with a sparse cell neighbourhood, and stragglers, are answered one at a time by the
+// warp-cooperative row scan (warp_first_k_rows).  smem: bm[BM_WORDS] | hitbuf[HITBUF].
 // ------------------------------------------------------------------------------------------------
 constexpr int BM_BITS = 16384;
 constexpr int BM_WORDS = BM_BITS / 32;
 
-// The slot loop is deliberately NOT unrolled and keeps no per-slot register arrays: an unrolled copy per slot
-// made the kernel ~190 KB of SASS and 70 % of its stall samples instruction-cache misses.
-__device__ __forceinline__ void ray_query_group(const StageArgs& p, int lane, const float (&o)[3],
-                                             const float (&d)[3], const float* zs /*smem: S sorted depths*/, int S,
-                                             float* rec, int* rowid, int* row_counter, int* active_counter, int cap,
-                                             int ray, long long* num_nn, unsigned* act, int act_stride,
-                                             QueryStats& qs, unsigned* bm, int* sel) {
+__device__ __forceinline__ int search_stream(const StageArgs& p, int lane, float qx, float qy, float qz, bool search,
+                                             int occ, QueryStats& qs, unsigned* bm, int* hitbuf, int* sel) {
     const GridHeader* h = p.g.hdr;
     const int K = p.K;
     const float radius = p.radius;
@@ -89,6 +84,292 @@ __device__ __forceinline__ void ray_query_group(const StageArgs& p, int lane, co
     const int P = h->n;
     const float ox = h->origin[0], oy = h->origin[1], oz = h->origin[2], inv = h->inv_cell;
     const int nx = h->dim[0], ny = h->dim[1], nz = h->dim[2];
+    int cnt = 0;
+    // Sparse neighbourhoods (few points in the 3x3x3 cell block) cannot fill K quickly in an index-order
+    // stream -- a lane with fewer than K neighbours would drag the whole group through all P particles --
+    // so those lanes skip the group scan and are answered one at a time by the warp-cooperative row scan
+    // below, as are stragglers still unfinished when the scan has gone PEEL_STEPS steps.
+    bool solo = search && occ < p.solo_max_occ;
+    if (__any_sync(NF_FULL, search && !solo)) {
+        bool done = !search || solo;
+        int built_for = 0;
+        ++qs.n_lock;
+        // half-resolution cell range of this lane's ball (<= 5 fine cells per axis when cell > reach)
+        const float inv2 = __fmul_rn(inv, 2.0f);
+        const float fcell = 0.5f * h->cell;
+        const int fnx = 2 * nx, fny = 2 * ny, fnz = 2 * nz;
+        const int flox = cell_coord(qx - pad, ox, inv2, fnx), fhix = cell_coord(qx + pad, ox, inv2, fnx);
+        const int floy = cell_coord(qy - pad, oy, inv2, fny), fhiy = cell_coord(qy + pad, oy, inv2, fny);
+        const int floz = cell_coord(qz - pad, oz, inv2, fnz), fhiz = cell_coord(qz + pad, oz, inv2, fnz);
+        const float rm = pad + 1e-3f * fcell;          // cull margin covers the rounding of the binning
+        const float rm2 = rm * rm;
+        int cnext[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) cnext[t] = __ldg(p.g.fine_of + 32 * t + lane);   // padded by 128 entries of -1
+        for (int j0 = 0; j0 < P; j0 += 128) {
+            const unsigned pending = __ballot_sync(NF_FULL, !done);
+            if (!pending) break;
+            const int npend = __popc(pending);
+            if (npend <= p.peel_lanes && j0 >= p.peel_from) {
+                solo = solo || !done;
+                break;
+            }
+            if (npend * 3 <= built_for || built_for == 0) {
+                // (re)build the bitmap: fine cells whose box comes within reach of an unfinished lane
+                __syncwarp();
+                for (int w = lane; w < BM_WORDS; w += 32) bm[w] = 0u;
+                __syncwarp();
+                if (!done) {
+                    for (int cz = floz; cz <= fhiz; ++cz) {
+                        const float bz = oz + (float)cz * fcell;
+                        const float dz = fmaxf(fmaxf(bz - qz, qz - (bz + fcell)), 0.f);
+                        // clamped boundary cells also hold everything beyond them: never cull those
+                        const bool ez = (cz == 0) || (cz == fnz - 1);
+                        for (int cy = floy; cy <= fhiy; ++cy) {
+                            const float by = oy + (float)cy * fcell;
+                            const float dy = fmaxf(fmaxf(by - qy, qy - (by + fcell)), 0.f);
+                            const bool ey = ez || (cy == 0) || (cy == fny - 1);
+                            const float dzy = dz * dz + dy * dy;
+                            for (int cx = flox; cx <= fhix; ++cx) {
+                                const float bx = ox + (float)cx * fcell;
+                                const float dx = fmaxf(fmaxf(bx - qx, qx - (bx + fcell)), 0.f);
+                                const bool e = ey || (cx == 0) || (cx == fnx - 1);
+                                if (e || dzy + dx * dx < rm2) {
+                                    const int c = (cz * fny + cy) * fnx + cx;
+                                    atomicOr(&bm[(c & (BM_BITS - 1)) >> 5], 1u << (c & 31));
+                                }
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                built_for = npend;
+            }
+            ++qs.it_lock;
+            // this step's cell ids were prefetched; fetch the next step's while we work
+            int c[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) c[t] = cnext[t];
+            if (j0 + 128 < P) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) cnext[t] = __ldg(p.g.fine_of + j0 + 128 + 32 * t + lane);
+            }
+            // lanes whose particle passes the bitmap fetch it themselves: coalesced, 4 loads in flight
+            float4 pp[4];
+            bool inb[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                inb[t] = (c[t] >= 0) && ((bm[(c[t] & (BM_BITS - 1)) >> 5] >> (c[t] & 31)) & 1u);
+                pp[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (inb[t]) pp[t] = __ldg(p.g.orig4 + j0 + 32 * t + lane);
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                unsigned m = __ballot_sync(NF_FULL, inb[t]);
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    const float cx = __shfl_sync(NF_FULL, pp[t].x, b);
+                    const float cy = __shfl_sync(NF_FULL, pp[t].y, b);
+                    const float cz = __shfl_sync(NF_FULL, pp[t].z, b);
+                    ++qs.it_rows;     // statistics: candidates tested
+                    if (!done && dist2_exact(qx, qy, qz, cx, cy, cz) < r2) {
+                        sel[cnt * 32 + lane] = j0 + 32 * t + b;
+                        ++cnt;
+                        done = cnt >= K;
+                    }
+                }
+            }
+        }
+    }
+    // ---- solo lanes: exact first-K by the whole warp over the <= 9 cell rows around that one sample
+    {
+        unsigned ms = __ballot_sync(NF_FULL, solo);
+        while (ms) {
+            const int b = __ffs(ms) - 1;
+            ms &= ms - 1;
+            const float sx = __shfl_sync(NF_FULL, qx, b), sy = __shfl_sync(NF_FULL, qy, b), sz = __shfl_sync(NF_FULL, qz, b);
+            int best = 0x7fffffff;
+            ++qs.n_rows;
+            const int n = warp_first_k_rows(p.g, sx, sy, sz, radius, K, lane, best, qs.it_rows, hitbuf);
+            if (lane < n) sel[lane * 32 + b] = best;
+            if (lane == b) cnt = n;
+        }
+        __syncwarp();
+    }
+    return cnt;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Search flavour 2, "sorted-candidate sweep" (P <= SCS_MAX_POINTS; the default).  The first-K-by-index rule
+// wants each sample's in-ball particles in ascending original index.  Consecutive samples of a ray whose depths
+// span <= sub_span form a sub-group; the warp
+//   1. gathers every particle within reach of the sub-group's segment (capsule test) from the <= 4x4 cell rows
+//      around it (coalesced 16-byte records of the cell-sorted copy) and sets bit[index] in a per-warp
+//      shared-memory bitmap over the index space -- a counting sort by index, for free;
+//   2. walks the bitmap in ascending order, 1024 indices per batch, compacting set bits into a small ring
+//      (ballot-free: popc + warp scan), and
+//   3. takes 32 candidates at a time (one per LANE, position in registers) and sweeps the still-unfinished
+//      samples over them: broadcast the sample, exact distance test, ballot; hit lanes write their index to the
+//      sample's next free slots.  A sample retires at K hits, the walk stops when all have retired.
+// Work is proportional to the candidates near the segment, not to P, and a sample with fewer than K neighbours
+// costs one pass over its own neighbourhood only.  smem: ibm[ceil(P/32)] | ring[SCS_RING] (u16).
+// ------------------------------------------------------------------------------------------------
+constexpr int SCS_MAX_POINTS = 65536;
+constexpr int SCS_RING = 1024 + 32;
+
+__host__ __device__ inline size_t scs_smem_bytes(int P) {
+    return (size_t)((P + 1023) / 1024) * 128 + SCS_RING * sizeof(unsigned short);
+}
+
+__device__ __forceinline__ int search_scs(const StageArgs& p, int lane, float zv, float qx, float qy, float qz,
+                                          bool search, QueryStats& qs, unsigned* ibm, int* sel) {
+    const GridHeader* h = p.g.hdr;
+    const int K = p.K;
+    const float radius = p.radius;
+    const float r2 = __fmul_rn(radius, radius);
+    const float pad = radius * 1.001f + 1e-5f;
+    const float pad2 = pad * pad;
+    const int P = h->n;
+    const int nwords = ((P + 1023) >> 10) << 5;          // multiple of 32 words
+    unsigned short* ring = reinterpret_cast<unsigned short*>(ibm + nwords);
+    const float ox = h->origin[0], oy = h->origin[1], oz = h->origin[2], inv = h->inv_cell;
+    const int nx = h->dim[0], ny = h->dim[1], nz = h->dim[2];
+    const unsigned lt = (1u << lane) - 1u;
+    int cnt = 0;
+    unsigned todo = __ballot_sync(NF_FULL, search);
+    while (todo) {
+        // ---- next sub-group: consecutive searching lanes within sub_span of the first one (depths ascend)
+        const int a = __ffs(todo) - 1;
+        const float za = __shfl_sync(NF_FULL, zv, a);
+        const unsigned sub = __ballot_sync(NF_FULL, search && lane >= a && (zv - za) <= p.sub_span) & todo;
+        todo &= ~sub;
+        const int b = 31 - __clz(sub);
+        const float ax = __shfl_sync(NF_FULL, qx, a), ay = __shfl_sync(NF_FULL, qy, a), az = __shfl_sync(NF_FULL, qz, a);
+        const float ex = __shfl_sync(NF_FULL, qx, b) - ax, ey = __shfl_sync(NF_FULL, qy, b) - ay,
+                    ez = __shfl_sync(NF_FULL, qz, b) - az;
+        const float len2 = ex * ex + ey * ey + ez * ez;
+        const float inv_len2 = len2 > 0.f ? 1.0f / len2 : 0.f;
+        const int lox = cell_coord(fminf(ax, ax + ex) - pad, ox, inv, nx), hix = cell_coord(fmaxf(ax, ax + ex) + pad, ox, inv, nx);
+        const int loy = cell_coord(fminf(ay, ay + ey) - pad, oy, inv, ny), hiy = cell_coord(fmaxf(ay, ay + ey) + pad, oy, inv, ny);
+        const int loz = cell_coord(fminf(az, az + ez) - pad, oz, inv, nz), hiz = cell_coord(fmaxf(az, az + ez) + pad, oz, inv, nz);
+        const int wy = hiy - loy + 1;
+        const int nrows = (hiz - loz + 1) * wy;
+        ++qs.n_lock;
+        __syncwarp();
+        for (int w = lane; w < nwords; w += 32) ibm[w] = 0u;
+        __syncwarp();
+        // ---- 1. gather: bit[index] for every particle within reach of the segment
+        for (int row0 = 0; row0 < nrows; row0 += 32) {
+            const int r = row0 + lane;
+            int beg = 0, end = 0;
+            if (r < nrows) {
+                const int rowbase = ((loz + r / wy) * ny + (loy + r % wy)) * nx;
+                beg = __ldg(p.g.cell_start + rowbase + lox);
+                end = __ldg(p.g.cell_start + rowbase + hix + 1);
+            }
+            const int nr = min(32, nrows - row0);
+            for (int t = 0; t < nr; ++t) {
+                const int rb = __shfl_sync(NF_FULL, beg, t), re = __shfl_sync(NF_FULL, end, t);
+                for (int i = rb + lane; i < re; i += 32) {
+                    const float4 c = __ldg(p.g.sorted + i);
+                    const float vx = c.x - ax, vy = c.y - ay, vz = c.z - az;
+                    const float tt = fminf(fmaxf((vx * ex + vy * ey + vz * ez) * inv_len2, 0.f), 1.f);
+                    const float wx = vx - tt * ex, wy_ = vy - tt * ey, wz = vz - tt * ez;
+                    if (wx * wx + wy_ * wy_ + wz * wz < pad2) {
+                        const int idx = __float_as_int(c.w);
+                        atomicOr(&ibm[idx >> 5], 1u << (idx & 31));
+                    }
+                }
+                ++qs.it_lock;
+            }
+        }
+        __syncwarp();
+        // ---- 2 + 3. walk the bitmap in index order, sweep unfinished samples over 32 candidates at a time
+        unsigned pend = sub;
+        int tail = 0;
+        auto sweep = [&](int idx, bool valid) {
+            float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) c = __ldg(p.g.orig4 + idx);
+            for (unsigned m = pend; m;) {
+                const int s = __ffs(m) - 1;
+                m &= m - 1;
+                const float sx = __shfl_sync(NF_FULL, qx, s), sy = __shfl_sync(NF_FULL, qy, s), sz = __shfl_sync(NF_FULL, qz, s);
+                const int n = __shfl_sync(NF_FULL, cnt, s);
+                const bool hit = valid && dist2_exact(sx, sy, sz, c.x, c.y, c.z) < r2;
+                const unsigned hm = __ballot_sync(NF_FULL, hit);
+                ++qs.it_rows;
+                if (hm) {
+                    const int slot = n + __popc(hm & lt);
+                    if (hit && slot < K) sel[slot * 32 + s] = idx;
+                    const int n2 = min(n + __popc(hm), K);
+                    if (lane == s) cnt = n2;
+                    if (n2 >= K) pend &= ~(1u << s);
+                }
+            }
+        };
+        for (int w0 = 0; w0 < nwords && pend; w0 += 32) {
+            unsigned w = ibm[w0 + lane];
+            const int c = __popc(w);
+            int incl = c;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int t = __shfl_up_sync(NF_FULL, incl, off);
+                if (lane >= off) incl += t;
+            }
+            const int tot = __shfl_sync(NF_FULL, incl, 31);
+            if (!tot) continue;
+            int pos = tail + incl - c;
+            const int base = (w0 + lane) << 5;
+            while (w) {
+                ring[pos++] = (unsigned short)(base + __ffs(w) - 1);
+                w &= w - 1;
+            }
+            tail += tot;
+            __syncwarp();
+            int head = 0;
+            while (tail - head >= 32 && pend) {
+                sweep((int)ring[head + lane], true);   // head + 31 < tail
+                head += 32;
+            }
+            if (head > 0) {       // move the < 32 left-over candidates to the front
+                const int left = tail - head;
+                const unsigned short v = ring[min(head + lane, SCS_RING - 1)];
+                __syncwarp();
+                if (lane < left) ring[lane] = v;
+                tail = left;
+                __syncwarp();
+            }
+        }
+        if (pend && tail > 0) {
+            for (int head = 0; head < tail && pend; head += 32) sweep((int)ring[min(head + lane, SCS_RING - 1)], head + lane < tail);
+        }
+        __syncwarp();
+    }
+    return cnt;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Neighbour search + local geometry for all samples of one ray: sample s lives in lane s%32 of 32-sample
+// step s/32.  The search (one of the two flavours above) leaves each lane's <= K neighbour indices, ascending,
+// in sel[k*32 + lane]; local geometry is then one per-lane pass over them in that order -- the reference's
+// summation order.  smem per warp: sel[K*32] | scratch[search_smem_bytes(P)].
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t search_smem_bytes(int P) {
+    const size_t a = BM_WORDS * sizeof(unsigned) + HITBUF * sizeof(int);
+    const size_t b = P <= SCS_MAX_POINTS ? scs_smem_bytes(P) : 0;
+    return a > b ? a : b;
+}
+
+// The slot loop is deliberately NOT unrolled and keeps no per-slot register arrays: an unrolled copy per slot
+// made the kernel ~190 KB of SASS and 70 % of its stall samples instruction-cache misses.
+__device__ __forceinline__ void ray_query_group(const StageArgs& p, int lane, const float (&o)[3],
+                                             const float (&d)[3], const float* zs /*smem: S sorted depths*/, int S,
+                                             float* rec, int* rowid, int* row_counter, int* active_counter, int cap,
+                                             int ray, long long* num_nn, unsigned* act, int act_stride,
+                                             QueryStats& qs, int* sel, unsigned* scratch) {
+    const int K = p.K;
+    const float radius = p.radius;
     const unsigned lt = (1u << lane) - 1u;
     int n_active = 0;
     const int sample_base = ray * S;
@@ -109,96 +390,9 @@ __device__ __forceinline__ void ray_query_group(const StageArgs& p, int lane, co
             if (lane == 0) act[(size_t)ray * act_stride + slot] = 0u;
             continue;
         }
-        int cnt = 0;
-        if (__any_sync(NF_FULL, search)) {
-            bool done = !search;
-            int built_for = 0;
-            ++qs.n_lock;
-            // half-resolution cell range of this lane's ball (<= 5 fine cells per axis when cell > reach)
-            const float inv2 = __fmul_rn(inv, 2.0f);
-            const float fcell = 0.5f * h->cell;
-            const int fnx = 2 * nx, fny = 2 * ny, fnz = 2 * nz;
-            const int flox = cell_coord(qx - pad, ox, inv2, fnx), fhix = cell_coord(qx + pad, ox, inv2, fnx);
-            const int floy = cell_coord(qy - pad, oy, inv2, fny), fhiy = cell_coord(qy + pad, oy, inv2, fny);
-            const int floz = cell_coord(qz - pad, oz, inv2, fnz), fhiz = cell_coord(qz + pad, oz, inv2, fnz);
-            const float rm = pad + 1e-3f * fcell;          // cull margin covers the rounding of the binning
-            const float rm2 = rm * rm;
-            int cnext[4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) cnext[t] = __ldg(p.g.fine_of + 32 * t + lane);   // padded by 128 entries of -1
-            for (int j0 = 0; j0 < P; j0 += 128) {
-                const unsigned pending = __ballot_sync(NF_FULL, !done);
-                if (!pending) break;
-                const int npend = __popc(pending);
-                if (npend * 3 <= built_for || built_for == 0) {
-                    // (re)build the bitmap: fine cells whose box comes within reach of an unfinished lane
-                    __syncwarp();
-                    for (int w = lane; w < BM_WORDS; w += 32) bm[w] = 0u;
-                    __syncwarp();
-                    if (!done) {
-                        for (int cz = floz; cz <= fhiz; ++cz) {
-                            const float bz = oz + (float)cz * fcell;
-                            const float dz = fmaxf(fmaxf(bz - qz, qz - (bz + fcell)), 0.f);
-                            // clamped boundary cells also hold everything beyond them: never cull those
-                            const bool ez = (cz == 0) || (cz == fnz - 1);
-                            for (int cy = floy; cy <= fhiy; ++cy) {
-                                const float by = oy + (float)cy * fcell;
-                                const float dy = fmaxf(fmaxf(by - qy, qy - (by + fcell)), 0.f);
-                                const bool ey = ez || (cy == 0) || (cy == fny - 1);
-                                const float dzy = dz * dz + dy * dy;
-                                for (int cx = flox; cx <= fhix; ++cx) {
-                                    const float bx = ox + (float)cx * fcell;
-                                    const float dx = fmaxf(fmaxf(bx - qx, qx - (bx + fcell)), 0.f);
-                                    const bool e = ey || (cx == 0) || (cx == fnx - 1);
-                                    if (e || dzy + dx * dx < rm2) {
-                                        const int c = (cz * fny + cy) * fnx + cx;
-                                        atomicOr(&bm[(c & (BM_BITS - 1)) >> 5], 1u << (c & 31));
-                                    }
-                                }
-                            }
-                        }
-                    }
-                    __syncwarp();
-                    built_for = npend;
-                    ++qs.n_rows;      // statistics: bitmap rebuilds
-                }
-                ++qs.it_lock;
-                // this step's cell ids were prefetched; fetch the next step's while we work
-                int c[4];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) c[t] = cnext[t];
-                if (j0 + 128 < P) {
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) cnext[t] = __ldg(p.g.fine_of + j0 + 128 + 32 * t + lane);
-                }
-                // lanes whose particle passes the bitmap fetch it themselves: coalesced, 4 loads in flight
-                float4 pp[4];
-                bool inb[4];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    inb[t] = (c[t] >= 0) && ((bm[(c[t] & (BM_BITS - 1)) >> 5] >> (c[t] & 31)) & 1u);
-                    pp[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (inb[t]) pp[t] = __ldg(p.g.orig4 + j0 + 32 * t + lane);
-                }
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    unsigned m = __ballot_sync(NF_FULL, inb[t]);
-                    while (m) {
-                        const int b = __ffs(m) - 1;
-                        m &= m - 1;
-                        const float cx = __shfl_sync(NF_FULL, pp[t].x, b);
-                        const float cy = __shfl_sync(NF_FULL, pp[t].y, b);
-                        const float cz = __shfl_sync(NF_FULL, pp[t].z, b);
-                        ++qs.it_rows;     // statistics: candidates tested
-                        if (!done && dist2_exact(qx, qy, qz, cx, cy, cz) < r2) {
-                            sel[cnt * 32 + lane] = j0 + 32 * t + b;
-                            ++cnt;
-                            done = cnt >= K;
-                        }
-                    }
-                }
-            }
-        }
+        int cnt;
+        if (p.search_mode == 1) cnt = search_scs(p, lane, zv, qx, qy, qz, search, qs, scratch, sel);
+        else cnt = search_stream(p, lane, qx, qy, qz, search, occ, qs, scratch, reinterpret_cast<int*>(scratch + BM_WORDS), sel);
         // ---- per-lane local geometry over the selected neighbours (ascending index, like the reference);
         //      one pass: var = (sum v^2 - 2 mean sum v + n mean^2) / n  ==  sum (v - mean)^2 / n
         float wsum = 0.f, wx = 0.f, wy = 0.f, wz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f, ux = 0.f, uy = 0.f, uz = 0.f;
@@ -307,8 +501,8 @@ __device__ __forceinline__ void load_ray(const float* rays, int ray, float (&o)[
 // ------------------------------------------------------------------------------------------------
 // stage Q0
 // ------------------------------------------------------------------------------------------------
-__host__ __device__ inline size_t q0_smem_per_warp(int K) {
-    return BM_WORDS * sizeof(unsigned) + (size_t)K * 32 * sizeof(int);
+__host__ __device__ inline size_t q0_smem_per_warp(int K, int P) {
+    return (size_t)K * 32 * sizeof(int) + search_smem_bytes(P);
 }
 
 template <int NS0>
@@ -319,22 +513,28 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_stage_q0(const StageAr
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int s = threadIdx.x; s < p.S0; s += blockDim.x) sm_z[s] = __ldg(p.z_coarse + s);
     __syncthreads();
-    unsigned* bm = reinterpret_cast<unsigned*>(dyn_smem + wib * q0_smem_per_warp(p.K));
-    int* sel = reinterpret_cast<int*>(bm + BM_WORDS);
+    int* sel = reinterpret_cast<int*>(dyn_smem + wib * q0_smem_per_warp(p.K, p.n_points));
+    unsigned* scratch = reinterpret_cast<unsigned*>(sel + p.K * 32);
     QueryStats qs;
     for (int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ray < p.n_rays; ray += nwarps) {
         float o[3], d[3];
         load_ray(p.rays, ray, o, d);
         ray_query_group(p, lane, o, d, sm_z, p.S0, p.rec0, p.rowid0, p.counters + 0, p.counters + 2, p.cap0, ray,
-                        p.num_nn0, p.act0, NS0, qs, bm, sel);
+                        p.num_nn0, p.act0, NS0, qs, sel, scratch);
+    }
+    if (lane == 0) {
+        atomicAdd(p.counters + 8, qs.n_lock);
+        atomicAdd(p.counters + 9, qs.n_rows);
+        atomicAdd(p.counters + 10, qs.it_lock >> 6);
+        atomicAdd(p.counters + 11, qs.it_rows >> 6);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // stage MID
 // ------------------------------------------------------------------------------------------------
-__host__ __device__ inline size_t mid_smem_per_warp(int ns0, int ns1, int K) {
-    return (size_t)(4 * ns0 * 32 + 2 * ns1 * 32) * sizeof(float) + BM_WORDS * sizeof(unsigned) + (size_t)K * 32 * sizeof(int);
+__host__ __device__ inline size_t mid_smem_per_warp(int ns0, int ns1, int K, int P) {
+    return (size_t)(4 * ns0 * 32 + 2 * ns1 * 32) * sizeof(float) + (size_t)K * 32 * sizeof(int) + search_smem_bytes(P);
 }
 
 template <int NS0, int NS1>
@@ -343,15 +543,15 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_stage_mid(const StageA
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int S0 = p.S0, S1 = p.S1, NI = p.n_imp;
-    float* base = reinterpret_cast<float*>(dyn_smem + wib * mid_smem_per_warp(NS0, NS1, p.K));
+    float* base = reinterpret_cast<float*>(dyn_smem + wib * mid_smem_per_warp(NS0, NS1, p.K, p.n_points));
     float* z0s = base;                   // coarse depths
     float* ws = z0s + NS0 * 32;          // coarse weights
     float* bins = ws + NS0 * 32;
     float* cdf = bins + NS0 * 32;
     float* smp = cdf + NS0 * 32;         // importance samples
     float* z1s = smp + NS1 * 32;         // merged depths
-    unsigned* bm = reinterpret_cast<unsigned*>(z1s + NS1 * 32);
-    int* sel = reinterpret_cast<int*>(bm + BM_WORDS);
+    int* sel = reinterpret_cast<int*>(z1s + NS1 * 32);
+    unsigned* scratch = reinterpret_cast<unsigned*>(sel + p.K * 32);
     QueryStats qs;
     for (int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ray < p.n_rays; ray += nwarps) {
         float o[3], d[3], z0[NS0], w0[NS0];
@@ -463,7 +663,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_stage_mid(const StageA
         __syncwarp();
         for (int s = lane; s < S1; s += 32) p.z1[(size_t)ray * S1 + s] = z1s[s];
         ray_query_group(p, lane, o, d, z1s, S1, p.rec1, p.rowid1, p.counters + 1, p.counters + 3, p.cap1, ray,
-                        p.num_nn1, p.act1, NS1, qs, bm, sel);
+                        p.num_nn1, p.act1, NS1, qs, sel, scratch);
         __syncwarp();
     }
     if (lane == 0) {
@@ -514,6 +714,11 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_stage_fin(const StageA
     }
 }
 
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
 struct WsLayout {
     size_t counters, act0, act1, z1, rec0, rowid0, out0, rec1, rowid1, out1, total;
     int cap0, cap1, ns0, ns1;
@@ -552,7 +757,7 @@ static WsLayout ws_layout(int R, int S0, int NI) {
 
 template <int NS0, int NS1>
 static int launch_mid2(int grid, const StageArgs& p, cudaStream_t st) {
-    const size_t smem = WARPS_PER_BLOCK * mid_smem_per_warp(NS0, NS1, p.K);
+    const size_t smem = WARPS_PER_BLOCK * mid_smem_per_warp(NS0, NS1, p.K, p.n_points);
     static size_t configured = 0;
     if (smem > configured) {
         NF_CUDA_OK(cudaFuncSetAttribute(k_stage_mid<NS0, NS1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -655,6 +860,7 @@ extern "C" int nf_render_forward(const nf_render_args* a, void* stream_) {
     StageArgs p;
     p.g = grid_view(a->grid_ws, a->n_particles);
     p.particles = a->particles;
+    p.n_points = a->n_particles;
     p.rays = a->rays;
     p.n_rays = a->n_rays;
     p.ro[0] = a->ro[0]; p.ro[1] = a->ro[1]; p.ro[2] = a->ro[2];
@@ -662,8 +868,12 @@ extern "C" int nf_render_forward(const nf_render_args* a, void* stream_) {
     p.K = a->K;
     p.use_mask = a->use_mask; p.white_bg = a->white_background; p.mode = a->mode;
     {
-        const char* e = getenv("NF_LOCKSTEP_MIN_OCC");
-        p.lockstep_min_occ = e ? atoi(e) : LOCKSTEP_MIN_OCC;
+        const int tune[3] = {env_int("NF_SOLO_MAX_OCC", 600), env_int("NF_PEEL_LANES", 4), env_int("NF_PEEL_FROM", 1536)};
+        p.solo_max_occ = tune[0]; p.peel_lanes = tune[1]; p.peel_from = tune[2];
+        const char* mode = getenv("NF_SEARCH");             // "stream" forces flavour 1 (tests cover both)
+        p.search_mode = (a->n_particles <= SCS_MAX_POINTS && !(mode && mode[0] == 's' && mode[1] == 't')) ? 1 : 0;
+        const char* span = getenv("NF_SUB_SPAN");
+        p.sub_span = span ? (float)atof(span) : 1.75f * a->radius;
     }
     p.z_coarse = a->z_coarse; p.u_imp = a->u_importance;
     p.S0 = a->n_coarse; p.n_imp = NI; p.S1 = a->n_coarse + NI;
@@ -686,7 +896,7 @@ extern "C" int nf_render_forward(const nf_render_args* a, void* stream_) {
     StageTimer tm(st);
     // ---- stage Q0
     {
-        const size_t smem = WARPS_PER_BLOCK * q0_smem_per_warp(p.K);
+        const size_t smem = WARPS_PER_BLOCK * q0_smem_per_warp(p.K, p.n_points);
         static size_t configured = 0;
         if (smem > configured) {
             NF_CUDA_OK(cudaFuncSetAttribute(k_stage_q0<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -733,6 +943,6 @@ extern "C" int nf_render_forward(const nf_render_args* a, void* stream_) {
         NF_LAUNCH_OK();
         tm.mark();
     }
-    if (a->stats) NF_CUDA_OK(cudaMemcpyAsync(a->stats, p.counters, 32, cudaMemcpyDeviceToDevice, st));
+    if (a->stats) NF_CUDA_OK(cudaMemcpyAsync(a->stats, p.counters, 64, cudaMemcpyDeviceToDevice, st));
     return NF_OK;
 }

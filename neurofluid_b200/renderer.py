@@ -123,7 +123,7 @@ class RenderNet(nn.Module):
         chunk = max(1, min(self.max_rays_per_launch, R))
         ws = self._workspace(chunk, NI, dev)
         nchunks = (R + chunk - 1) // chunk
-        stats = torch.zeros((max(nchunks, 1), 8), dtype=torch.int32, device=dev)
+        stats = torch.zeros((max(nchunks, 1), 16), dtype=torch.int32, device=dev)
         st = stream_ptr()
         for ci, r0 in enumerate(range(0, R, chunk)):
             r1 = min(r0 + chunk, R)
@@ -145,7 +145,7 @@ class RenderNet(nn.Module):
             a.rgb1, a.depth1, a.opacity1 = sl("rgb1", 12), sl("depth1", 4), sl("opacity1", 4)
             a.num_nn1, a.mask1 = sl("num_nn_1", 8 * S1), sl("mask_1", 4)
             a.workspace, a.workspace_bytes = ptr(ws), ws.numel()
-            a.stats = C.c_void_p(stats.data_ptr() + ci * 32)
+            a.stats = C.c_void_p(stats.data_ptr() + ci * 64)
             check(lib().nf_render_forward(C.byref(a), st), "nf_render_forward")
         self.last_stats = stats       # device tensor; .sum(0) = [rows0, rows1, active0, active1]
         self._keep = (grid, particles, rays)

@@ -10,8 +10,14 @@ particles = torch.from_numpy(scenes.lattice_particles(27, 0))
 net = nb.RenderNet(scenes.render_cfg(), scenes.NEAR, scenes.FAR); net.load_state_dict(scenes.init_render_state(0, 5.0)); net = net.to(dev)
 rays_d, p_d, ro = rays.to(dev), particles.to(dev), cw[:, 3].to(dev)
 L = _lib.lib()
-for occ in sys.argv[1:]:
-    os.environ["NF_LOCKSTEP_MIN_OCC"] = occ
+for occ in sys.argv[1:]:        # "stream:solo_max_occ,peel_lanes,peel_from" or "scs:sub_span"
+    mode, arg = occ.split(":")
+    os.environ["NF_SEARCH"] = mode
+    if mode == "stream":
+        a, b, c = arg.split(",")
+        os.environ["NF_SOLO_MAX_OCC"], os.environ["NF_PEEL_LANES"], os.environ["NF_PEEL_FROM"] = a, b, c
+    else:
+        os.environ["NF_SUB_SPAN"] = arg
     for it in range(2):
         net(p_d, ro, rays_d, focal, cw)
     L.nf_profile_enable(1)
@@ -20,5 +26,6 @@ for occ in sys.argv[1:]:
     torch.cuda.synchronize(); dt = time.time() - t0
     ms = (ctypes.c_double * 5)(); n = ctypes.c_int(0); L.nf_profile_read(ms, ctypes.byref(n)); L.nf_profile_enable(0)
     st = net.last_stats.sum(0).tolist()
-    print(f"min_occ={occ}: {dt*1e3:.1f} ms stages={[round(x,1) for x in ms]} lock_q={st[4]} rows_q={st[5]} "
-          f"steps/group={64*st[6]/max(st[4],1):.1f} rebuilds/group={st[5]/max(st[4],1):.2f} cands/group={64*st[7]/max(st[4],1):.1f}", flush=True)
+    print(f"tune={occ}: {dt*1e3:.1f} ms stages={[round(x,1) for x in ms]} fine: groups={st[4]} solo={st[5]} "
+          f"steps/group={64*st[6]/max(st[4],1):.1f} tests/group={64*st[7]/max(st[4],1):.1f} | coarse: groups={st[8]} solo={st[9]} "
+          f"steps/group={64*st[10]/max(st[8],1):.1f} tests/group={64*st[11]/max(st[8],1):.1f} rgb1={out['rgb1'].double().sum().item():.6f}", flush=True)
