@@ -106,6 +106,10 @@ NF_API int nf_nerf_mlp_forward(const void* packed_weights, int dtype, const floa
 #define NF_RENDER_COARSE 1  /* coarse only                                     */
 #define NF_RENDER_FINE 2    /* sigma-only coarse pass, then fine               */
 
+#define NF_SEARCH_AUTO 0   /* sweep when n_particles <= 65536, else stream    */
+#define NF_SEARCH_STREAM 1 /* index-order stream through a cell bitmap (any P) */
+#define NF_SEARCH_SWEEP 2  /* capsule gather -> index bitmap -> candidate sweep */
+
 typedef struct nf_render_args {
     /* scene */
     const void* grid_ws;    /* nf_grid_build() of `particles` with cell >= 1.002*radius        */
@@ -122,6 +126,7 @@ typedef struct nf_render_args {
     /* search */
     float radius;
     int32_t K;
+    int32_t search;     /* NF_SEARCH_*: first-K search flavour                                  */
     /* behaviour */
     int32_t mode;       /* NF_RENDER_*                                                         */
     int32_t use_mask;   /* cfg.use_mask                                                        */

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libnf_b200.so")
 
 NF_DTYPE_F16, NF_DTYPE_BF16 = 0, 1
 NF_RENDER_FORWARD, NF_RENDER_COARSE, NF_RENDER_FINE = 0, 1, 2
+NF_SEARCH_AUTO, NF_SEARCH_STREAM, NF_SEARCH_SWEEP = 0, 1, 2
 
 _vp, _i32, _f32, _sz, _i64 = C.c_void_p, C.c_int32, C.c_float, C.c_size_t, C.c_int64
 
@@ -22,7 +23,7 @@ class RenderArgs(C.Structure):
         ("grid_ws", _vp), ("particles", _vp), ("n_particles", _i32),
         ("rays", _vp), ("n_rays", _i32), ("ro", _f32 * 3),
         ("z_coarse", _vp), ("u_importance", _vp), ("n_coarse", _i32), ("n_importance", _i32),
-        ("radius", _f32), ("K", _i32),
+        ("radius", _f32), ("K", _i32), ("search", _i32),
         ("mode", _i32), ("use_mask", _i32), ("white_background", _i32), ("dtype", _i32),
         ("weights_coarse", _vp), ("weights_fine", _vp),
         ("rgb0", _vp), ("depth0", _vp), ("opacity0", _vp), ("num_nn0", _vp), ("mask0", _vp),

@@ -58,6 +58,8 @@ struct StageArgs {
                          // [4..7] fine-pass search statistics: group scans, solo (row-scan) queries, scan steps / 64,
                          // candidates tested + row-scan iterations / 64; [8..11] the same for the coarse pass
     unsigned* act0;      // (R, NS0)
+    int* base0;          // (R, NS0) first row of each 32-sample coarse step in rec0
+    unsigned char* cnt0; // (R, S0) neighbour count of every coarse sample
     unsigned* act1;      // (R, NS1)
     float* z1;           // (R, S1)
     float* rec0; int* rowid0; float4* out0; int cap0;
@@ -71,6 +73,9 @@ struct StageArgs {
 // until it has K.  Lanes with a sparse cell neighbourhood, and stragglers, are answered one at a time by the
 // warp-cooperative row scan (warp_first_k_rows).  smem: bm[BM_WORDS] | hitbuf[HITBUF].
 // ------------------------------------------------------------------------------------------------
+__host__ __device__ inline int sel_stride(int K) { return K | 1; }
+__host__ __device__ inline size_t sel_bytes(int K) { return (size_t)32 * sel_stride(K) * sizeof(int); }
+
 constexpr int BM_BITS = 16384;
 constexpr int BM_WORDS = BM_BITS / 32;
 
@@ -174,7 +179,7 @@ __device__ __forceinline__ int search_stream(const StageArgs& p, int lane, float
                     const float cz = __shfl_sync(NF_FULL, pp[t].z, b);
                     ++qs.it_rows;     // statistics: candidates tested
                     if (!done && dist2_exact(qx, qy, qz, cx, cy, cz) < r2) {
-                        sel[cnt * 32 + lane] = j0 + 32 * t + b;
+                        sel[lane * sel_stride(K) + cnt] = j0 + 32 * t + b;
                         ++cnt;
                         done = cnt >= K;
                     }
@@ -192,7 +197,7 @@ __device__ __forceinline__ int search_stream(const StageArgs& p, int lane, float
             int best = 0x7fffffff;
             ++qs.n_rows;
             const int n = warp_first_k_rows(p.g, sx, sy, sz, radius, K, lane, best, qs.it_rows, hitbuf);
-            if (lane < n) sel[lane * 32 + b] = best;
+            if (lane < n) sel[b * sel_stride(K) + lane] = best;
             if (lane == b) cnt = n;
         }
         __syncwarp();
@@ -222,13 +227,14 @@ __host__ __device__ inline size_t scs_smem_bytes(int P) {
     return (size_t)((P + 1023) / 1024) * 128 + SCS_RING * sizeof(unsigned short);
 }
 
-__device__ __forceinline__ int search_scs(const StageArgs& p, int lane, float zv, float qx, float qy, float qz,
-                                          bool search, QueryStats& qs, unsigned* ibm, int* sel) {
+__device__ __forceinline__ int search_scs(const StageArgs& p, int lane, const float (&o)[3], const float (&d)[3],
+                                          float zv, float qx, float qy, float qz, bool search, float& gz0, float& gz1,
+                                          QueryStats& qs, unsigned* ibm, int* sel) {
     const GridHeader* h = p.g.hdr;
     const int K = p.K;
     const float radius = p.radius;
     const float r2 = __fmul_rn(radius, radius);
-    const float pad = radius * 1.001f + 1e-5f;
+    const float pad = radius * 1.001f + 1e-4f;      // also absorbs the rounding of o + d*z along the segment
     const float pad2 = pad * pad;
     const int P = h->n;
     const int nwords = ((P + 1023) >> 10) << 5;          // multiple of 32 words
@@ -236,18 +242,23 @@ __device__ __forceinline__ int search_scs(const StageArgs& p, int lane, float zv
     const float ox = h->origin[0], oy = h->origin[1], oz = h->origin[2], inv = h->inv_cell;
     const int nx = h->dim[0], ny = h->dim[1], nz = h->dim[2];
     const unsigned lt = (1u << lane) - 1u;
+    const int KP = sel_stride(K);
     int cnt = 0;
     unsigned todo = __ballot_sync(NF_FULL, search);
     while (todo) {
-        // ---- next sub-group: consecutive searching lanes within sub_span of the first one (depths ascend)
+        // ---- next sub-group: the searching lanes inside the depth interval [gz0, gz1] whose candidates the
+        //      bitmap holds; when the first pending lane lies outside it, gather a new interval of sub_span
+        //      starting there (it also serves the following 32-sample steps of this ray: importance samples
+        //      cluster, so several steps usually share one gather)
         const int a = __ffs(todo) - 1;
         const float za = __shfl_sync(NF_FULL, zv, a);
-        const unsigned sub = __ballot_sync(NF_FULL, search && lane >= a && (zv - za) <= p.sub_span) & todo;
+        const bool fresh = !(za >= gz0 && za <= gz1);
+        if (fresh) { gz0 = za; gz1 = za + p.sub_span; }
+        const unsigned sub = __ballot_sync(NF_FULL, search && lane >= a && zv <= gz1) & todo;
         todo &= ~sub;
-        const int b = 31 - __clz(sub);
+        if (fresh) {
         const float ax = __shfl_sync(NF_FULL, qx, a), ay = __shfl_sync(NF_FULL, qy, a), az = __shfl_sync(NF_FULL, qz, a);
-        const float ex = __shfl_sync(NF_FULL, qx, b) - ax, ey = __shfl_sync(NF_FULL, qy, b) - ay,
-                    ez = __shfl_sync(NF_FULL, qz, b) - az;
+        const float ex = d[0] * p.sub_span, ey = d[1] * p.sub_span, ez = d[2] * p.sub_span;
         const float len2 = ex * ex + ey * ey + ez * ez;
         const float inv_len2 = len2 > 0.f ? 1.0f / len2 : 0.f;
         const int lox = cell_coord(fminf(ax, ax + ex) - pad, ox, inv, nx), hix = cell_coord(fmaxf(ax, ax + ex) + pad, ox, inv, nx);
@@ -271,18 +282,24 @@ __device__ __forceinline__ int search_scs(const StageArgs& p, int lane, float zv
             const int nr = min(32, nrows - row0);
             for (int t = 0; t < nr; ++t) {
                 const int rb = __shfl_sync(NF_FULL, beg, t), re = __shfl_sync(NF_FULL, end, t);
-                for (int i = rb + lane; i < re; i += 32) {
-                    const float4 c = __ldg(p.g.sorted + i);
-                    const float vx = c.x - ax, vy = c.y - ay, vz = c.z - az;
-                    const float tt = fminf(fmaxf((vx * ex + vy * ey + vz * ez) * inv_len2, 0.f), 1.f);
-                    const float wx = vx - tt * ex, wy_ = vy - tt * ey, wz = vz - tt * ez;
-                    if (wx * wx + wy_ * wy_ + wz * wz < pad2) {
-                        const int idx = __float_as_int(c.w);
-                        atomicOr(&ibm[idx >> 5], 1u << (idx & 31));
+                for (int i = rb + lane; i < re; i += 128) {          // 4 independent 16-byte loads in flight
+                    float4 c[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) c[u] = __ldg(p.g.sorted + min(i + 32 * u, re - 1));
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float vx = c[u].x - ax, vy = c[u].y - ay, vz = c[u].z - az;
+                        const float tt = fminf(fmaxf((vx * ex + vy * ey + vz * ez) * inv_len2, 0.f), 1.f);
+                        const float wx = vx - tt * ex, wy_ = vy - tt * ey, wz = vz - tt * ez;
+                        if (i + 32 * u < re && wx * wx + wy_ * wy_ + wz * wz < pad2) {
+                            const int idx = __float_as_int(c[u].w);
+                            atomicOr(&ibm[idx >> 5], 1u << (idx & 31));
+                        }
                     }
                 }
                 ++qs.it_lock;
             }
+        }
         }
         __syncwarp();
         // ---- 2 + 3. walk the bitmap in index order, sweep unfinished samples over 32 candidates at a time
@@ -301,7 +318,7 @@ __device__ __forceinline__ int search_scs(const StageArgs& p, int lane, float zv
                 ++qs.it_rows;
                 if (hm) {
                     const int slot = n + __popc(hm & lt);
-                    if (hit && slot < K) sel[slot * 32 + s] = idx;
+                    if (hit && slot < K) sel[s * KP + slot] = idx;
                     const int n2 = min(n + __popc(hm), K);
                     if (lane == s) cnt = n2;
                     if (n2 >= K) pend &= ~(1u << s);
@@ -352,8 +369,9 @@ __device__ __forceinline__ int search_scs(const StageArgs& p, int lane, float zv
 // ------------------------------------------------------------------------------------------------
 // Neighbour search + local geometry for all samples of one ray: sample s lives in lane s%32 of 32-sample
 // step s/32.  The search (one of the two flavours above) leaves each lane's <= K neighbour indices, ascending,
-// in sel[k*32 + lane]; local geometry is then one per-lane pass over them in that order -- the reference's
-// summation order.  smem per warp: sel[K*32] | scratch[search_smem_bytes(P)].
+// in sel[lane*sel_stride(K) + k] (odd stride: the k-th hits of 32 samples and the consecutive hits of one sample
+// both fall in distinct banks); local geometry is then one per-lane pass over them in that order -- the
+// reference's summation order.  smem per warp: sel[32*sel_stride(K)] | scratch[search_smem_bytes(P)].
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t search_smem_bytes(int P) {
     const size_t a = BM_WORDS * sizeof(unsigned) + HITBUF * sizeof(int);
@@ -367,9 +385,18 @@ __device__ __forceinline__ void ray_query_group(const StageArgs& p, int lane, co
                                              const float (&d)[3], const float* zs /*smem: S sorted depths*/, int S,
                                              float* rec, int* rowid, int* row_counter, int* active_counter, int cap,
                                              int ray, long long* num_nn, unsigned* act, int act_stride,
-                                             QueryStats& qs, int* sel, unsigned* scratch) {
+                                             QueryStats& qs, int* sel, unsigned* scratch,
+                                             const short* src /*smem or null: coarse index of each merged sample*/) {
+    // Fine pass: a merged sample that IS one of the coarse samples (same depth, same position, bit for bit) was
+    // already searched by stage Q0 -- its neighbour count comes from cnt0 and its geometry record is copied from
+    // rec0 instead of being searched and built again (the coarse samples are the ones spread through the whole
+    // fluid; the importance samples cluster).
+    const bool coarse_pass = src == nullptr;
+    const int act_stride0 = (p.S0 + 31) >> 5 <= 2 ? 2 : 4;      // NS0 of the coarse pass (pick_ns)
     const int K = p.K;
+    const int KP = sel_stride(K);
     const float radius = p.radius;
+    float gz0 = 1.f, gz1 = 0.f;      // sweep: depth interval whose candidates the index bitmap currently holds
     const unsigned lt = (1u << lane) - 1u;
     int n_active = 0;
     const int sample_base = ray * S;
@@ -382,16 +409,21 @@ __device__ __forceinline__ void ray_query_group(const StageArgs& p, int lane, co
         const float qx = __fadd_rn(o[0], __fmul_rn(d[0], zv));
         const float qy = __fadd_rn(o[1], __fmul_rn(d[1], zv));
         const float qz = __fadd_rn(o[2], __fmul_rn(d[2], zv));
-        const int occ = in ? grid_occupancy(p.g, qx, qy, qz, radius) : 0;
+        const int from = (!coarse_pass && in) ? (int)src[s] : -1;
+        const bool reused = from >= 0;
+        const int pre = reused ? (int)p.cnt0[(size_t)ray * p.S0 + from] : 0;
+        const int occ = (in && !reused) ? grid_occupancy(p.g, qx, qy, qz, radius) : 0;
         const bool search = occ > 0;
-        const bool want = p.use_mask ? search : in;   // use_mask=False: every sample is evaluated, even empty ones
-        if (!__any_sync(NF_FULL, want)) {
-            if (num_nn && in) num_nn[(size_t)sample_base + s] = 0;
+        // use_mask=False: every sample is evaluated, even empty ones
+        const bool want = p.use_mask ? (reused ? pre == p.K : search) : in;
+        if (!__any_sync(NF_FULL, want || search)) {
+            if (num_nn && in) num_nn[(size_t)sample_base + s] = pre;
+            if (coarse_pass && in) p.cnt0[(size_t)ray * p.S0 + s] = 0;
             if (lane == 0) act[(size_t)ray * act_stride + slot] = 0u;
             continue;
         }
         int cnt;
-        if (p.search_mode == 1) cnt = search_scs(p, lane, zv, qx, qy, qz, search, qs, scratch, sel);
+        if (p.search_mode == 1) cnt = search_scs(p, lane, o, d, zv, qx, qy, qz, search, gz0, gz1, qs, scratch, sel);
         else cnt = search_stream(p, lane, qx, qy, qz, search, occ, qs, scratch, reinterpret_cast<int*>(scratch + BM_WORDS), sel);
         // ---- per-lane local geometry over the selected neighbours (ascending index, like the reference);
         //      one pass: var = (sum v^2 - 2 mean sum v + n mean^2) / n  ==  sum (v - mean)^2 / n
@@ -400,7 +432,7 @@ __device__ __forceinline__ void ray_query_group(const StageArgs& p, int lane, co
 #pragma unroll 4
         for (int k = 0; k < K; ++k) {
             if (k < cnt) {
-                const float4 pp = __ldg(p.g.orig4 + sel[k * 32 + lane]);
+                const float4 pp = __ldg(p.g.orig4 + sel[lane * KP + k]);
                 const float ex = pp.x - qx, ey = pp.y - qy, ez = pp.z - qz;
                 const float t = sqrtf(ex * ex + ey * ey + ez * ez) / radius;
                 const float w = fmaxf(1.0f - t * t * t, 0.f);
@@ -421,31 +453,44 @@ __device__ __forceinline__ void ray_query_group(const StageArgs& p, int lane, co
         const float ax = fmaxf(ux - 2.0f * mx * vx + (float)nvalid * mx * mx, 0.f);
         const float ay = fmaxf(uy - 2.0f * my * vy + (float)nvalid * my * my, 0.f);
         const float az = fmaxf(uz - 2.0f * mz * vz + (float)nvalid * mz * mz, 0.f);
+        if (reused) nvalid = pre;
         const bool full = in && (nvalid == K);
         const unsigned fb = __ballot_sync(NF_FULL, full);
         if (num_nn && in) num_nn[(size_t)sample_base + s] = nvalid;
+        if (coarse_pass && in) p.cnt0[(size_t)ray * p.S0 + s] = (unsigned char)nvalid;
         if (lane == 0) act[(size_t)ray * act_stride + slot] = fb;
         n_active += __popc(fb);
         const bool eval = want && (p.use_mask ? full : true);
         const unsigned me = __ballot_sync(NF_FULL, eval);
+        int base = 0;
         if (me) {
-            int base = 0;
             if (lane == 0) base = atomicAdd(row_counter, __popc(me));
             base = __shfl_sync(NF_FULL, base, 0);
             const int row = base + __popc(me & lt);
             if (eval && row < cap) {
-                const float den = wsum + 1e-12f;
-                const float sx = wx / den, sy = wy / den, sz = wz / den;
-                const float tx = sx - p.ro[0], ty = sy - p.ro[1], tz = sz - p.ro[2];
-                const float tn = sqrtf(tx * tx + ty * ty + tz * tz);
                 float4* dst = reinterpret_cast<float4*>(rec + (size_t)row * 16);
-                dst[0] = make_float4(qx, qy, qz, wsum);
-                dst[1] = make_float4(sx, sy, sz, ax / nvf);
-                dst[2] = make_float4(ay / nvf, az / nvf, d[0], d[1]);
-                dst[3] = make_float4(d[2], tx / tn, ty / tn, tz / tn);
+                if (reused) {
+                    // row of this sample in the coarse list: base of its 32-sample step + rank among the evaluated
+                    const int slot0 = from >> 5, nin = min(32, p.S0 - slot0 * 32);
+                    const unsigned ev0 = p.use_mask ? p.act0[(size_t)ray * act_stride0 + slot0]
+                                                    : (nin == 32 ? NF_FULL : ((1u << nin) - 1u));
+                    const int row0 = p.base0[(size_t)ray * act_stride0 + slot0] + __popc(ev0 & ((1u << (from & 31)) - 1u));
+                    const float4* sp = reinterpret_cast<const float4*>(p.rec0 + (size_t)row0 * 16);
+                    dst[0] = sp[0]; dst[1] = sp[1]; dst[2] = sp[2]; dst[3] = sp[3];
+                } else {
+                    const float den = wsum + 1e-12f;
+                    const float sx = wx / den, sy = wy / den, sz = wz / den;
+                    const float tx = sx - p.ro[0], ty = sy - p.ro[1], tz = sz - p.ro[2];
+                    const float tn = sqrtf(tx * tx + ty * ty + tz * tz);
+                    dst[0] = make_float4(qx, qy, qz, wsum);
+                    dst[1] = make_float4(sx, sy, sz, ax / nvf);
+                    dst[2] = make_float4(ay / nvf, az / nvf, d[0], d[1]);
+                    dst[3] = make_float4(d[2], tx / tn, ty / tn, tz / tn);
+                }
                 rowid[row] = sample_base + s;
             }
         }
+        if (coarse_pass && lane == 0) p.base0[(size_t)ray * act_stride + slot] = base;
     }
     if (lane == 0 && n_active) atomicAdd(active_counter, n_active);
 }
@@ -502,7 +547,7 @@ __device__ __forceinline__ void load_ray(const float* rays, int ray, float (&o)[
 // stage Q0
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t q0_smem_per_warp(int K, int P) {
-    return (size_t)K * 32 * sizeof(int) + search_smem_bytes(P);
+    return sel_bytes(K) + search_smem_bytes(P);
 }
 
 template <int NS0>
@@ -514,13 +559,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_stage_q0(const StageAr
     for (int s = threadIdx.x; s < p.S0; s += blockDim.x) sm_z[s] = __ldg(p.z_coarse + s);
     __syncthreads();
     int* sel = reinterpret_cast<int*>(dyn_smem + wib * q0_smem_per_warp(p.K, p.n_points));
-    unsigned* scratch = reinterpret_cast<unsigned*>(sel + p.K * 32);
+    unsigned* scratch = reinterpret_cast<unsigned*>(sel + 32 * sel_stride(p.K));
     QueryStats qs;
     for (int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ray < p.n_rays; ray += nwarps) {
         float o[3], d[3];
         load_ray(p.rays, ray, o, d);
         ray_query_group(p, lane, o, d, sm_z, p.S0, p.rec0, p.rowid0, p.counters + 0, p.counters + 2, p.cap0, ray,
-                        p.num_nn0, p.act0, NS0, qs, sel, scratch);
+                        p.num_nn0, p.act0, NS0, qs, sel, scratch, nullptr);
     }
     if (lane == 0) {
         atomicAdd(p.counters + 8, qs.n_lock);
@@ -534,7 +579,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_stage_q0(const StageAr
 // stage MID
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t mid_smem_per_warp(int ns0, int ns1, int K, int P) {
-    return (size_t)(4 * ns0 * 32 + 2 * ns1 * 32) * sizeof(float) + (size_t)K * 32 * sizeof(int) + search_smem_bytes(P);
+    return (size_t)(4 * ns0 * 32 + 2 * ns1 * 32) * sizeof(float) + (size_t)ns1 * 32 * sizeof(short) + sel_bytes(K) +
+           search_smem_bytes(P);
 }
 
 template <int NS0, int NS1>
@@ -551,7 +597,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_stage_mid(const StageA
     float* smp = cdf + NS0 * 32;         // importance samples
     float* z1s = smp + NS1 * 32;         // merged depths
     int* sel = reinterpret_cast<int*>(z1s + NS1 * 32);
-    unsigned* scratch = reinterpret_cast<unsigned*>(sel + p.K * 32);
+    unsigned* scratch = reinterpret_cast<unsigned*>(sel + 32 * sel_stride(p.K));
+    short* src1 = reinterpret_cast<short*>(reinterpret_cast<unsigned char*>(scratch) + search_smem_bytes(p.n_points));
     QueryStats qs;
     for (int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ray < p.n_rays; ray += nwarps) {
         float o[3], d[3], z0[NS0], w0[NS0];
@@ -649,6 +696,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_stage_mid(const StageA
                 int lo = 0, hi = NI;            // # samples < v
                 while (lo < hi) { const int mid = (lo + hi) >> 1; if (smp[mid] < v) lo = mid + 1; else hi = mid; }
                 z1s[i + lo] = v;
+                src1[i + lo] = (short)i;
             }
         }
         for (int j0 = 0; j0 < NI; j0 += 32) {
@@ -658,12 +706,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_stage_mid(const StageA
                 int lo = 0, hi = S0;            // # coarse depths <= v
                 while (lo < hi) { const int mid = (lo + hi) >> 1; if (z0s[mid] <= v) lo = mid + 1; else hi = mid; }
                 z1s[j + lo] = v;
+                src1[j + lo] = (short)-1;
             }
         }
         __syncwarp();
         for (int s = lane; s < S1; s += 32) p.z1[(size_t)ray * S1 + s] = z1s[s];
         ray_query_group(p, lane, o, d, z1s, S1, p.rec1, p.rowid1, p.counters + 1, p.counters + 3, p.cap1, ray,
-                        p.num_nn1, p.act1, NS1, qs, sel, scratch);
+                        p.num_nn1, p.act1, NS1, qs, sel, scratch, src1);
         __syncwarp();
     }
     if (lane == 0) {
@@ -720,7 +769,7 @@ static int env_int(const char* name, int dflt) {
 }
 
 struct WsLayout {
-    size_t counters, act0, act1, z1, rec0, rowid0, out0, rec1, rowid1, out1, total;
+    size_t counters, act0, act1, base0, cnt0, z1, rec0, rowid0, out0, rec1, rowid1, out1, total;
     int cap0, cap1, ns0, ns1;
 };
 
@@ -744,6 +793,8 @@ static WsLayout ws_layout(int R, int S0, int NI) {
     L.counters = take(64);
     L.act0 = take(sizeof(unsigned) * (size_t)R * 4);
     L.act1 = take(sizeof(unsigned) * (size_t)R * 8);
+    L.base0 = take(sizeof(int) * (size_t)R * 4);
+    L.cnt0 = take((size_t)R * S0);
     L.z1 = take(sizeof(float) * (size_t)R * S1);
     L.rec0 = take(sizeof(float) * 16 * (size_t)L.cap0);
     L.rowid0 = take(sizeof(int) * (size_t)L.cap0);
@@ -870,8 +921,10 @@ extern "C" int nf_render_forward(const nf_render_args* a, void* stream_) {
     {
         const int tune[3] = {env_int("NF_SOLO_MAX_OCC", 600), env_int("NF_PEEL_LANES", 4), env_int("NF_PEEL_FROM", 1536)};
         p.solo_max_occ = tune[0]; p.peel_lanes = tune[1]; p.peel_from = tune[2];
-        const char* mode = getenv("NF_SEARCH");             // "stream" forces flavour 1 (tests cover both)
-        p.search_mode = (a->n_particles <= SCS_MAX_POINTS && !(mode && mode[0] == 's' && mode[1] == 't')) ? 1 : 0;
+        NF_REQUIRE(a->search >= NF_SEARCH_AUTO && a->search <= NF_SEARCH_SWEEP, NF_E_INVALID, "nf_render_forward: search %d", a->search);
+        NF_REQUIRE(a->search != NF_SEARCH_SWEEP || a->n_particles <= SCS_MAX_POINTS, NF_E_UNSUPPORTED,
+                   "nf_render_forward: NF_SEARCH_SWEEP needs n_particles <= %d", SCS_MAX_POINTS);
+        p.search_mode = (a->search == NF_SEARCH_STREAM || a->n_particles > SCS_MAX_POINTS) ? 0 : 1;
         const char* span = getenv("NF_SUB_SPAN");
         p.sub_span = span ? (float)atof(span) : 1.75f * a->radius;
     }
@@ -885,6 +938,7 @@ extern "C" int nf_render_forward(const nf_render_args* a, void* stream_) {
     p.num_nn1 = (long long*)a->num_nn1;
     p.counters = (int*)(b + L.counters);
     p.act0 = (unsigned*)(b + L.act0); p.act1 = (unsigned*)(b + L.act1);
+    p.base0 = (int*)(b + L.base0); p.cnt0 = (unsigned char*)(b + L.cnt0);
     p.z1 = (float*)(b + L.z1);
     p.rec0 = (float*)(b + L.rec0); p.rowid0 = (int*)(b + L.rowid0); p.out0 = (float4*)(b + L.out0); p.cap0 = L.cap0;
     p.rec1 = (float*)(b + L.rec1); p.rowid1 = (int*)(b + L.rowid1); p.out1 = (float4*)(b + L.out1); p.cap1 = L.cap1;

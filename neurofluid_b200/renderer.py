@@ -26,7 +26,8 @@ from .ops import CELL_SCALE, Grid, pack_nerf_weights
 
 
 class RenderNet(nn.Module):
-    def __init__(self, cfg, near, far, operand_dtype: str = "fp16", max_rays_per_launch: int = 131072):
+    def __init__(self, cfg, near, far, operand_dtype: str = "fp16", max_rays_per_launch: int = 131072,
+                 search: str = "auto"):
         super().__init__()
         self.cfg = cfg
         self.near, self.far = near, far
@@ -50,6 +51,7 @@ class RenderNet(nn.Module):
         self.nerf_fine = NeRF(in_channels_xyz=in_xyz, in_channels_dir=in_dir)
         self.operand_dtype = {"fp16": _lib.NF_DTYPE_F16, "bf16": _lib.NF_DTYPE_BF16}[operand_dtype]
         self.max_rays_per_launch = int(max_rays_per_launch)
+        self.search = {"auto": _lib.NF_SEARCH_AUTO, "stream": _lib.NF_SEARCH_STREAM, "sweep": _lib.NF_SEARCH_SWEEP}[search]
         self._packed = {}      # net name -> (version key, packed tensor)
         self._ws = None
         self._tables = {}
@@ -132,7 +134,7 @@ class RenderNet(nn.Module):
             a.rays, a.n_rays = C.c_void_p(rays.data_ptr() + r0 * 24), r1 - r0
             a.ro = (C.c_float * 3)(*ro_host)
             a.z_coarse, a.u_importance, a.n_coarse, a.n_importance = ptr(z_tab), ptr(u_tab), S0, NI
-            a.radius, a.K = float(self.raduis), int(self.num_neighbor)
+            a.radius, a.K, a.search = float(self.raduis), int(self.num_neighbor), self.search
             a.mode, a.use_mask, a.white_background = int(mode), int(bool(self.cfg.use_mask)), int(bool(white_background))
             a.dtype = self.operand_dtype
             a.weights_coarse, a.weights_fine = ptr(wc), ptr(wf)

@@ -12,7 +12,7 @@ rays_d, p_d, ro = rays.to(dev), particles.to(dev), cw[:, 3].to(dev)
 L = _lib.lib()
 for occ in sys.argv[1:]:        # "stream:solo_max_occ,peel_lanes,peel_from" or "scs:sub_span"
     mode, arg = occ.split(":")
-    os.environ["NF_SEARCH"] = mode
+    net.search = {"stream": _lib.NF_SEARCH_STREAM, "scs": _lib.NF_SEARCH_SWEEP}[mode]
     if mode == "stream":
         a, b, c = arg.split(",")
         os.environ["NF_SOLO_MAX_OCC"], os.environ["NF_PEEL_LANES"], os.environ["NF_PEEL_FROM"] = a, b, c

@@ -38,12 +38,12 @@ def test_size_queries_and_version_without_device():
 
 
 def test_struct_layout_matches_header():
-    # nf_render_args: 31 fields; pointers are 8-byte aligned -> size is a multiple of 8 and stable
+    # nf_render_args: 32 fields; pointers are 8-byte aligned -> size is a multiple of 8 and stable
     assert ctypes.sizeof(_lib.RenderArgs) % 8 == 0
     assert _lib.RenderArgs.rays.offset == 24 and _lib.RenderArgs.ro.offset == 36
-    assert _lib.RenderArgs.z_coarse.offset == 48 and _lib.RenderArgs.weights_coarse.offset == 96
-    assert _lib.RenderArgs.workspace.offset == 192 and _lib.RenderArgs.stats.offset == 208
-    assert ctypes.sizeof(_lib.RenderArgs) == 216
+    assert _lib.RenderArgs.z_coarse.offset == 48 and _lib.RenderArgs.weights_coarse.offset == 104
+    assert _lib.RenderArgs.workspace.offset == 200 and _lib.RenderArgs.stats.offset == 216
+    assert ctypes.sizeof(_lib.RenderArgs) == 224
 
 
 def test_rendernet_state_dict_layout_and_errors():

@@ -136,6 +136,22 @@ def test_render_chunking_and_ray_order_invariance(dev):
         assert torch.equal(shuf[k].cpu(), big[k].cpu()[perm]), k    # rays are independent
 
 
+@pytest.mark.parametrize("name", ["small_boost", "small_nomask", "cfg0_sub"])
+def test_render_search_flavours_agree_bitwise(dev, name):
+    """The index-order stream (any P) and the sorted-candidate sweep (P <= 65536) are two routes to the same
+    first-K-by-index sets: every output must match bit for bit."""
+    c = load_render_case(name)
+    args = (c["particles"].to(dev), c["ro"].to(dev), c["rays"].to(dev), 0.0, c["cw"].to(dev))
+    a = make_net(c["cfg"], c["sd"], dev, search="stream")(*args)
+    b = make_net(c["cfg"], c["sd"], dev, search="sweep")(*args)
+    assert set(a) == set(b)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    # the stream flavour alone against the reference golden
+    assert np.array_equal(a["num_nn_0"].cpu().numpy().astype(np.int8), c["g"]["forward.num_nn_0"])
+    assert rel_l2(a["rgb1"].cpu(), c["g"]["forward.rgb1"]) < RGB_TOL
+
+
 def test_render_operand_dtype_switch_and_errors(dev):
     c = load_render_case("small_boost")
     net = make_net(c["cfg"], c["sd"], dev, operand_dtype="bf16")
