@@ -214,14 +214,15 @@ __device__ __forceinline__ int search_stream(const StageArgs& p, int lane, float
 //      shared-memory bitmap over the index space -- a counting sort by index, for free;
 //   2. walks the bitmap in ascending order, 1024 indices per batch, compacting set bits into a small ring
 //      (ballot-free: popc + warp scan), and
-//   3. takes 32 candidates at a time (one per LANE, position in registers) and sweeps the still-unfinished
-//      samples over them: broadcast the sample, exact distance test, ballot; hit lanes write their index to the
-//      sample's next free slots.  A sample retires at K hits, the walk stops when all have retired.
+//   3. takes 128 candidates at a time (four per LANE, positions in registers) and sweeps the still-unfinished
+//      samples over them: broadcast the sample, exact distance tests, ballots; hit lanes write their index to
+//      the sample's next free slots.  A sample retires at K hits, the walk stops when all have retired.
 // Work is proportional to the candidates near the segment, not to P, and a sample with fewer than K neighbours
 // costs one pass over its own neighbourhood only.  smem: ibm[ceil(P/32)] | ring[SCS_RING] (u16).
 // ------------------------------------------------------------------------------------------------
 constexpr int SCS_MAX_POINTS = 65536;
-constexpr int SCS_RING = 1024 + 32;
+constexpr int SCS_BLOCK = 128;                  // candidates per sweep (4 per lane)
+constexpr int SCS_RING = 1024 + 2 * SCS_BLOCK;  // left-over (< block) + one 1024-index batch + read slack
 
 __host__ __device__ inline size_t scs_smem_bytes(int P) {
     return (size_t)((P + 1023) / 1024) * 128 + SCS_RING * sizeof(unsigned short);
@@ -302,27 +303,39 @@ __device__ __forceinline__ int search_scs(const StageArgs& p, int lane, const fl
         }
         }
         __syncwarp();
-        // ---- 2 + 3. walk the bitmap in index order, sweep unfinished samples over 32 candidates at a time
+        // ---- 2 + 3. walk the bitmap in index order; sweep the unfinished samples over blocks of <= 128
+        //      candidates (4 per lane, positions in registers): per sample one broadcast, four distance tests
         unsigned pend = sub;
         int tail = 0;
-        auto sweep = [&](int idx, bool valid) {
-            float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid) c = __ldg(p.g.orig4 + idx);
+        auto sweep = [&](int head, int navail) {
+            float4 c[SCS_BLOCK / 32];
+            int id[SCS_BLOCK / 32];
+#pragma unroll
+            for (int u = 0; u < SCS_BLOCK / 32; ++u) {
+                const int i = 32 * u + lane;
+                id[u] = (int)ring[head + i];                 // head + i < SCS_RING always
+                c[u] = make_float4(3.0e18f, 3.0e18f, 3.0e18f, 0.f);
+                if (i < navail) c[u] = __ldg(p.g.orig4 + id[u]);
+            }
             for (unsigned m = pend; m;) {
                 const int s = __ffs(m) - 1;
                 m &= m - 1;
                 const float sx = __shfl_sync(NF_FULL, qx, s), sy = __shfl_sync(NF_FULL, qy, s), sz = __shfl_sync(NF_FULL, qz, s);
-                const int n = __shfl_sync(NF_FULL, cnt, s);
-                const bool hit = valid && dist2_exact(sx, sy, sz, c.x, c.y, c.z) < r2;
-                const unsigned hm = __ballot_sync(NF_FULL, hit);
-                ++qs.it_rows;
-                if (hm) {
+                int n = __shfl_sync(NF_FULL, cnt, s);
+                bool hit[SCS_BLOCK / 32];
+#pragma unroll
+                for (int u = 0; u < SCS_BLOCK / 32; ++u) hit[u] = dist2_exact(sx, sy, sz, c[u].x, c[u].y, c[u].z) < r2;
+#pragma unroll
+                for (int u = 0; u < SCS_BLOCK / 32; ++u) {
+                    const unsigned hm = __ballot_sync(NF_FULL, hit[u]);
                     const int slot = n + __popc(hm & lt);
-                    if (hit && slot < K) sel[s * KP + slot] = idx;
-                    const int n2 = min(n + __popc(hm), K);
-                    if (lane == s) cnt = n2;
-                    if (n2 >= K) pend &= ~(1u << s);
+                    if (hit[u] && slot < K) sel[s * KP + slot] = id[u];
+                    n += __popc(hm);
                 }
+                ++qs.it_rows;
+                n = min(n, K);
+                if (lane == s) cnt = n;
+                if (n >= K) pend &= ~(1u << s);
             }
         };
         for (int w0 = 0; w0 < nwords && pend; w0 += 32) {
@@ -343,24 +356,27 @@ __device__ __forceinline__ int search_scs(const StageArgs& p, int lane, const fl
                 w &= w - 1;
             }
             tail += tot;
+            if (tail < SCS_BLOCK) continue;
             __syncwarp();
             int head = 0;
-            while (tail - head >= 32 && pend) {
-                sweep((int)ring[head + lane], true);   // head + 31 < tail
-                head += 32;
+            while (tail - head >= SCS_BLOCK && pend) {
+                sweep(head, SCS_BLOCK);
+                head += SCS_BLOCK;
             }
-            if (head > 0) {       // move the < 32 left-over candidates to the front
-                const int left = tail - head;
-                const unsigned short v = ring[min(head + lane, SCS_RING - 1)];
-                __syncwarp();
-                if (lane < left) ring[lane] = v;
-                tail = left;
-                __syncwarp();
-            }
+            // move the < SCS_BLOCK left-over candidates to the front (read all, then write: ranges may overlap)
+            const int left = tail - head;
+            unsigned short v[SCS_BLOCK / 32];
+#pragma unroll
+            for (int u = 0; u < SCS_BLOCK / 32; ++u) v[u] = ring[head + 32 * u + lane];
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < SCS_BLOCK / 32; ++u)
+                if (32 * u + lane < left) ring[32 * u + lane] = v[u];
+            tail = left;
+            __syncwarp();
         }
-        if (pend && tail > 0) {
-            for (int head = 0; head < tail && pend; head += 32) sweep((int)ring[min(head + lane, SCS_RING - 1)], head + lane < tail);
-        }
+        __syncwarp();
+        if (pend && tail > 0) sweep(0, tail);       // tail < SCS_BLOCK here
         __syncwarp();
     }
     return cnt;
@@ -371,16 +387,17 @@ __device__ __forceinline__ int search_scs(const StageArgs& p, int lane, const fl
 // step s/32.  The search (one of the two flavours above) leaves each lane's <= K neighbour indices, ascending,
 // in sel[lane*sel_stride(K) + k] (odd stride: the k-th hits of 32 samples and the consecutive hits of one sample
 // both fall in distinct banks); local geometry is then one per-lane pass over them in that order -- the
-// reference's summation order.  smem per warp: sel[32*sel_stride(K)] | scratch[search_smem_bytes(P)].
+// reference's summation order.  smem per warp: sel[32*sel_stride(K)] | scratch[search_smem_bytes(FL, P)].
+// FL: 0 = index-order stream, 1 = sorted-candidate sweep (separate kernel instances: the sweep alone fits 80
+// registers, i.e. three 8-warp blocks per SM).
 // ------------------------------------------------------------------------------------------------
-__host__ __device__ inline size_t search_smem_bytes(int P) {
-    const size_t a = BM_WORDS * sizeof(unsigned) + HITBUF * sizeof(int);
-    const size_t b = P <= SCS_MAX_POINTS ? scs_smem_bytes(P) : 0;
-    return a > b ? a : b;
+__host__ __device__ inline size_t search_smem_bytes(int flavour, int P) {
+    return flavour == 1 ? scs_smem_bytes(P) : BM_WORDS * sizeof(unsigned) + HITBUF * sizeof(int);
 }
 
 // The slot loop is deliberately NOT unrolled and keeps no per-slot register arrays: an unrolled copy per slot
 // made the kernel ~190 KB of SASS and 70 % of its stall samples instruction-cache misses.
+template <int FL>
 __device__ __forceinline__ void ray_query_group(const StageArgs& p, int lane, const float (&o)[3],
                                              const float (&d)[3], const float* zs /*smem: S sorted depths*/, int S,
                                              float* rec, int* rowid, int* row_counter, int* active_counter, int cap,
@@ -423,7 +440,7 @@ __device__ __forceinline__ void ray_query_group(const StageArgs& p, int lane, co
             continue;
         }
         int cnt;
-        if (p.search_mode == 1) cnt = search_scs(p, lane, o, d, zv, qx, qy, qz, search, gz0, gz1, qs, scratch, sel);
+        if constexpr (FL == 1) cnt = search_scs(p, lane, o, d, zv, qx, qy, qz, search, gz0, gz1, qs, scratch, sel);
         else cnt = search_stream(p, lane, qx, qy, qz, search, occ, qs, scratch, reinterpret_cast<int*>(scratch + BM_WORDS), sel);
         // ---- per-lane local geometry over the selected neighbours (ascending index, like the reference);
         //      one pass: var = (sum v^2 - 2 mean sum v + n mean^2) / n  ==  sum (v - mean)^2 / n
@@ -546,25 +563,25 @@ __device__ __forceinline__ void load_ray(const float* rays, int ray, float (&o)[
 // ------------------------------------------------------------------------------------------------
 // stage Q0
 // ------------------------------------------------------------------------------------------------
-__host__ __device__ inline size_t q0_smem_per_warp(int K, int P) {
-    return sel_bytes(K) + search_smem_bytes(P);
+__host__ __device__ inline size_t q0_smem_per_warp(int fl, int K, int P) {
+    return sel_bytes(K) + search_smem_bytes(fl, P);
 }
 
-template <int NS0>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_stage_q0(const StageArgs p) {
+template <int NS0, int FL>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, FL == 1 ? 3 : 2) k_stage_q0(const StageArgs p) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ float sm_z[NS0 * 32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int s = threadIdx.x; s < p.S0; s += blockDim.x) sm_z[s] = __ldg(p.z_coarse + s);
     __syncthreads();
-    int* sel = reinterpret_cast<int*>(dyn_smem + wib * q0_smem_per_warp(p.K, p.n_points));
+    int* sel = reinterpret_cast<int*>(dyn_smem + wib * q0_smem_per_warp(FL, p.K, p.n_points));
     unsigned* scratch = reinterpret_cast<unsigned*>(sel + 32 * sel_stride(p.K));
     QueryStats qs;
     for (int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ray < p.n_rays; ray += nwarps) {
         float o[3], d[3];
         load_ray(p.rays, ray, o, d);
-        ray_query_group(p, lane, o, d, sm_z, p.S0, p.rec0, p.rowid0, p.counters + 0, p.counters + 2, p.cap0, ray,
+        ray_query_group<FL>(p, lane, o, d, sm_z, p.S0, p.rec0, p.rowid0, p.counters + 0, p.counters + 2, p.cap0, ray,
                         p.num_nn0, p.act0, NS0, qs, sel, scratch, nullptr);
     }
     if (lane == 0) {
@@ -578,27 +595,30 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_stage_q0(const StageAr
 // ------------------------------------------------------------------------------------------------
 // stage MID
 // ------------------------------------------------------------------------------------------------
-__host__ __device__ inline size_t mid_smem_per_warp(int ns0, int ns1, int K, int P) {
-    return (size_t)(4 * ns0 * 32 + 2 * ns1 * 32) * sizeof(float) + (size_t)ns1 * 32 * sizeof(short) + sel_bytes(K) +
-           search_smem_bytes(P);
+// per warp: z1s[NS1*32] f32 | src1[NS1*32] i16 | sel | union { pdf scratch: z0s, ws, bins, cdf [NS0*32] f32, smp[NS1*32] f32 ;
+//                                                             search scratch }   (the pdf arrays are dead once the merged
+// depths exist, the search scratch is dead between rays)
+__host__ __device__ inline size_t mid_smem_per_warp(int fl, int ns0, int ns1, int K, int P) {
+    const size_t pdf = (size_t)(4 * ns0 * 32 + ns1 * 32) * sizeof(float);
+    const size_t srch = search_smem_bytes(fl, P);
+    return (size_t)ns1 * 32 * (sizeof(float) + sizeof(short)) + sel_bytes(K) + (pdf > srch ? pdf : srch);
 }
 
-template <int NS0, int NS1>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_stage_mid(const StageArgs p) {
+template <int NS0, int NS1, int FL>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, FL == 1 ? 3 : 2) k_stage_mid(const StageArgs p) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int S0 = p.S0, S1 = p.S1, NI = p.n_imp;
-    float* base = reinterpret_cast<float*>(dyn_smem + wib * mid_smem_per_warp(NS0, NS1, p.K, p.n_points));
-    float* z0s = base;                   // coarse depths
+    float* z1s = reinterpret_cast<float*>(dyn_smem + wib * mid_smem_per_warp(FL, NS0, NS1, p.K, p.n_points));   // merged depths
+    short* src1 = reinterpret_cast<short*>(z1s + NS1 * 32);      // merged sample -> coarse index or -1
+    int* sel = reinterpret_cast<int*>(src1 + NS1 * 32);
+    unsigned* scratch = reinterpret_cast<unsigned*>(sel + 32 * sel_stride(p.K));
+    float* z0s = reinterpret_cast<float*>(scratch);   // coarse depths            (pdf scratch overlays search scratch)
     float* ws = z0s + NS0 * 32;          // coarse weights
     float* bins = ws + NS0 * 32;
     float* cdf = bins + NS0 * 32;
     float* smp = cdf + NS0 * 32;         // importance samples
-    float* z1s = smp + NS1 * 32;         // merged depths
-    int* sel = reinterpret_cast<int*>(z1s + NS1 * 32);
-    unsigned* scratch = reinterpret_cast<unsigned*>(sel + 32 * sel_stride(p.K));
-    short* src1 = reinterpret_cast<short*>(reinterpret_cast<unsigned char*>(scratch) + search_smem_bytes(p.n_points));
     QueryStats qs;
     for (int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ray < p.n_rays; ray += nwarps) {
         float o[3], d[3], z0[NS0], w0[NS0];
@@ -711,7 +731,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_stage_mid(const StageA
         }
         __syncwarp();
         for (int s = lane; s < S1; s += 32) p.z1[(size_t)ray * S1 + s] = z1s[s];
-        ray_query_group(p, lane, o, d, z1s, S1, p.rec1, p.rowid1, p.counters + 1, p.counters + 3, p.cap1, ray,
+        ray_query_group<FL>(p, lane, o, d, z1s, S1, p.rec1, p.rowid1, p.counters + 1, p.counters + 3, p.cap1, ray,
                         p.num_nn1, p.act1, NS1, qs, sel, scratch, src1);
         __syncwarp();
     }
@@ -806,17 +826,18 @@ static WsLayout ws_layout(int R, int S0, int NI) {
     return L;
 }
 
-template <int NS0, int NS1>
-static int launch_mid2(int grid, const StageArgs& p, cudaStream_t st) {
-    const size_t smem = WARPS_PER_BLOCK * mid_smem_per_warp(NS0, NS1, p.K, p.n_points);
-    static size_t configured = 0;
-    if (smem > configured) {
-        NF_CUDA_OK(cudaFuncSetAttribute(k_stage_mid<NS0, NS1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
-    k_stage_mid<NS0, NS1><<<grid, WARPS_PER_BLOCK * 32, smem, st>>>(p);
+template <int NS0, int NS1, int FL>
+static int launch_mid3(int grid, const StageArgs& p, cudaStream_t st) {
+    const size_t smem = WARPS_PER_BLOCK * mid_smem_per_warp(FL, NS0, NS1, p.K, p.n_points);
+    NF_CUDA_OK(cudaFuncSetAttribute(k_stage_mid<NS0, NS1, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_stage_mid<NS0, NS1, FL><<<grid, WARPS_PER_BLOCK * 32, smem, st>>>(p);
     NF_LAUNCH_OK();
     return NF_OK;
+}
+
+template <int NS0, int NS1>
+static int launch_mid2(int grid, const StageArgs& p, cudaStream_t st) {
+    return p.search_mode == 1 ? launch_mid3<NS0, NS1, 1>(grid, p, st) : launch_mid3<NS0, NS1, 0>(grid, p, st);
 }
 
 template <int NS0>
@@ -827,6 +848,15 @@ static int launch_mid(int ns1, int grid, const StageArgs& p, cudaStream_t st) {
         case 8: return launch_mid2<NS0, 8>(grid, p, st);
         default: set_error("unsupported fine sample count"); return NF_E_UNSUPPORTED;
     }
+}
+
+template <int NS0, int FL>
+static int launch_q0(int grid, const StageArgs& p, cudaStream_t st) {
+    const size_t smem = WARPS_PER_BLOCK * q0_smem_per_warp(FL, p.K, p.n_points);
+    NF_CUDA_OK(cudaFuncSetAttribute(k_stage_q0<NS0, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_stage_q0<NS0, FL><<<grid, WARPS_PER_BLOCK * 32, smem, st>>>(p);
+    NF_LAUNCH_OK();
+    return NF_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -950,16 +980,9 @@ extern "C" int nf_render_forward(const nf_render_args* a, void* stream_) {
     StageTimer tm(st);
     // ---- stage Q0
     {
-        const size_t smem = WARPS_PER_BLOCK * q0_smem_per_warp(p.K, p.n_points);
-        static size_t configured = 0;
-        if (smem > configured) {
-            NF_CUDA_OK(cudaFuncSetAttribute(k_stage_q0<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            NF_CUDA_OK(cudaFuncSetAttribute(k_stage_q0<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
-        }
-        if (L.ns0 == 2) k_stage_q0<2><<<grid, threads, smem, st>>>(p);
-        else k_stage_q0<4><<<grid, threads, smem, st>>>(p);
-        NF_LAUNCH_OK();
+        const int rc0 = (L.ns0 == 2) ? (p.search_mode == 1 ? launch_q0<2, 1>(grid, p, st) : launch_q0<2, 0>(grid, p, st))
+                                     : (p.search_mode == 1 ? launch_q0<4, 1>(grid, p, st) : launch_q0<4, 0>(grid, p, st));
+        if (rc0 != NF_OK) return rc0;
     }
     tm.mark();
     // ---- coarse network
