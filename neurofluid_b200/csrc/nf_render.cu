@@ -43,7 +43,8 @@ struct StageArgs {
     int K;
     int use_mask, white_bg, mode;
     int search_mode;                           // 0 = index-order stream, 1 = sorted-candidate sweep
-    float sub_span;                            // sweep: max depth span of one sub-group
+    float sub_span;                            // sweep: max depth span of one gather
+    int sub_look;                              // sweep: ... and max samples ahead it reaches
     int solo_max_occ, peel_lanes, peel_from;   // stream: tuning, see search_stream
     const float* z_coarse;
     const float* u_imp;
@@ -230,6 +231,7 @@ __host__ __device__ inline size_t scs_smem_bytes(int P) {
 
 __device__ __forceinline__ int search_scs(const StageArgs& p, int lane, const float (&o)[3], const float (&d)[3],
                                           float zv, float qx, float qy, float qz, bool search, float& gz0, float& gz1,
+                                          const float* zs, int S, int s0 /*sample index of lane 0*/,
                                           QueryStats& qs, unsigned* ibm, int* sel) {
     const GridHeader* h = p.g.hdr;
     const int K = p.K;
@@ -254,12 +256,16 @@ __device__ __forceinline__ int search_scs(const StageArgs& p, int lane, const fl
         const int a = __ffs(todo) - 1;
         const float za = __shfl_sync(NF_FULL, zv, a);
         const bool fresh = !(za >= gz0 && za <= gz1);
-        if (fresh) { gz0 = za; gz1 = za + p.sub_span; }
+        if (fresh) {      // at most sub_span deep and at most sub_look samples ahead (importance samples cluster)
+            gz0 = za;
+            gz1 = fminf(za + p.sub_span, zs[min(s0 + a + p.sub_look, S - 1)]);
+        }
         const unsigned sub = __ballot_sync(NF_FULL, search && lane >= a && zv <= gz1) & todo;
         todo &= ~sub;
         if (fresh) {
         const float ax = __shfl_sync(NF_FULL, qx, a), ay = __shfl_sync(NF_FULL, qy, a), az = __shfl_sync(NF_FULL, qz, a);
-        const float ex = d[0] * p.sub_span, ey = d[1] * p.sub_span, ez = d[2] * p.sub_span;
+        const float span = gz1 - gz0;
+        const float ex = d[0] * span, ey = d[1] * span, ez = d[2] * span;
         const float len2 = ex * ex + ey * ey + ez * ez;
         const float inv_len2 = len2 > 0.f ? 1.0f / len2 : 0.f;
         const int lox = cell_coord(fminf(ax, ax + ex) - pad, ox, inv, nx), hix = cell_coord(fmaxf(ax, ax + ex) + pad, ox, inv, nx);
@@ -327,6 +333,7 @@ __device__ __forceinline__ int search_scs(const StageArgs& p, int lane, const fl
                 for (int u = 0; u < SCS_BLOCK / 32; ++u) hit[u] = dist2_exact(sx, sy, sz, c[u].x, c[u].y, c[u].z) < r2;
 #pragma unroll
                 for (int u = 0; u < SCS_BLOCK / 32; ++u) {
+                    if (u == 2 && n >= K) break;
                     const unsigned hm = __ballot_sync(NF_FULL, hit[u]);
                     const int slot = n + __popc(hm & lt);
                     if (hit[u] && slot < K) sel[s * KP + slot] = id[u];
@@ -440,7 +447,7 @@ __device__ __forceinline__ void ray_query_group(const StageArgs& p, int lane, co
             continue;
         }
         int cnt;
-        if constexpr (FL == 1) cnt = search_scs(p, lane, o, d, zv, qx, qy, qz, search, gz0, gz1, qs, scratch, sel);
+        if constexpr (FL == 1) cnt = search_scs(p, lane, o, d, zv, qx, qy, qz, search, gz0, gz1, zs, S, slot * 32, qs, scratch, sel);
         else cnt = search_stream(p, lane, qx, qy, qz, search, occ, qs, scratch, reinterpret_cast<int*>(scratch + BM_WORDS), sel);
         // ---- per-lane local geometry over the selected neighbours (ascending index, like the reference);
         //      one pass: var = (sum v^2 - 2 mean sum v + n mean^2) / n  ==  sum (v - mean)^2 / n
@@ -957,6 +964,7 @@ extern "C" int nf_render_forward(const nf_render_args* a, void* stream_) {
         p.search_mode = (a->search == NF_SEARCH_STREAM || a->n_particles > SCS_MAX_POINTS) ? 0 : 1;
         const char* span = getenv("NF_SUB_SPAN");
         p.sub_span = span ? (float)atof(span) : 1.75f * a->radius;
+        p.sub_look = env_int("NF_SUB_LOOK", 64);
     }
     p.z_coarse = a->z_coarse; p.u_imp = a->u_importance;
     p.S0 = a->n_coarse; p.n_imp = NI; p.S1 = a->n_coarse + NI;

@@ -17,7 +17,7 @@ for occ in sys.argv[1:]:        # "stream:solo_max_occ,peel_lanes,peel_from" or 
         a, b, c = arg.split(",")
         os.environ["NF_SOLO_MAX_OCC"], os.environ["NF_PEEL_LANES"], os.environ["NF_PEEL_FROM"] = a, b, c
     else:
-        os.environ["NF_SUB_SPAN"] = arg
+        os.environ["NF_SUB_SPAN"], os.environ["NF_SUB_LOOK"] = arg.split(",")
     for it in range(2):
         net(p_d, ro, rays_d, focal, cw)
     L.nf_profile_enable(1)
