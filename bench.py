@@ -58,6 +58,15 @@ def peaks():
     return dict(hbm=6650.0, tensor=1400.0, tensor_burst=1590.0, src="fallback")
 
 
+def ncu_traffic(name):
+    """DRAM bytes of one launch of `name` from the committed ncu --set full capture (profiles/traffic.json, written by
+    tools/ncu_summarise.py traffic); None when no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    return json.load(open(p)).get(name)
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -297,6 +306,7 @@ def main():
     S1 = 192
     mid_bytes = n_my * (24 + 8 + 24 + S1 * 12 + 24) + stats[2] * 16 + stats[1] * 68
     mid_gbs = mid_bytes / (st[2] * 1e-3) / 1e9 if st[2] > 0 else 0.0
+    tr_mlp, tr_mid = ncu_traffic("k_nerf_mlp_fine"), ncu_traffic("k_stage_mid")
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -313,10 +323,16 @@ def main():
         "clocks": clocks,
         "roofline": {"kernel": "k_nerf_mlp (fine network)", "bound": "tensor", "achieved": achieved_tflops,
                      "peak": pk["tensor"], "unit": "TFLOP/s", "frac": achieved_tflops / pk["tensor"],
-                     "peak_source": f"{pk['src']} bf16 dense, sustained", "traffic": None,
-                     "rows_evaluated": stats[3], "rows_launched": stats[1], "ms_per_launch_sum": mlp_fine_ms},
+                     "peak_source": f"{pk['src']} bf16 dense, sustained",
+                     "frac_of_burst_peak": achieved_tflops / pk["tensor_burst"],
+                     "traffic": tr_mlp["dram_bytes"] if tr_mlp else None,
+                     "traffic_note": (f"ncu dram bytes of one launch ({tr_mlp['rows']} rows, {tr_mlp['report']}); algorithmic "
+                                      f"{tr_mlp['rows'] * 84} B = 84 B/row (64 B record + 4 B row id in, 16 B out)") if tr_mlp else None,
+                     "rows_evaluated": stats[3], "rows_launched": stats[1], "launches_per_step": len(net.last_stats),
+                     "ms_per_launch_avg": mlp_fine_ms / max(len(net.last_stats), 1), "ms_per_step": mlp_fine_ms},
         "roofline_gather": {"kernel": "k_stage_mid (composite + resample + fine first-K ball query)", "bound": "hbm",
                             "achieved": mid_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": mid_gbs / pk["hbm"],
+                            "traffic": tr_mid["dram_bytes"] if tr_mid else None,
                             "note": "particles+grid (<1 MB) are L2-resident: this kernel is L2/latency-bound by construction "
                                     "(SURVEY 8d caveat)", "ms": st[2]},
         "stage_ms_rank0": {"ray_query_coarse": st[0], "mlp_coarse": st[1], "composite_resample_query_fine": st[2],

@@ -75,11 +75,13 @@ class ParticleNet(nn.Module):
 
     def _packed_weights(self):
         params = self.ordered_params()
-        for m in (self.conv0_fluid, self.conv0_obstacle, self.conv1, self.conv2, self.conv3):
-            if bool((m.offset != 0).any()):
-                raise NFError("non-zero ContinuousConv.offset is not supported (the reference never sets it)")
-        key = tuple((p.data_ptr(), p._version) for p in params) + (self.operand_dtype,)
+        convs = (self.conv0_fluid, self.conv0_obstacle, self.conv1, self.conv2, self.conv3)
+        key = tuple((p.data_ptr(), p._version) for p in params) + tuple(m.offset._version for m in convs) + \
+            (self.operand_dtype,)
         if self._packed is None or self._packed[0] != key:
+            for m in convs:      # checked when (re)packing only: a device sync per step would dominate small scenes
+                if bool((m.offset != 0).any()):
+                    raise NFError("non-zero ContinuousConv.offset is not supported (the reference never sets it)")
             ps = [p.detach().to(torch.float32).contiguous() for p in params]
             require_cuda(*ps)
             out = torch.empty(lib().nf_transition_packed_weights_bytes(), dtype=torch.uint8, device=ps[0].device)
