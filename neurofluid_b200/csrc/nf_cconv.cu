@@ -25,6 +25,7 @@
 //                      exists in HBM.
 //   k_update           pos/vel update
 #include <stdlib.h>
+#include <type_traits>
 
 #include "nf_common.cuh"
 
@@ -42,6 +43,13 @@ struct __align__(16) Pair {
     float w[8];           // trilinear weight * window
 };
 static_assert(sizeof(Pair) == 48, "Pair layout");
+
+// Slab lists: the fluid->fluid pairs regrouped by the (z,y) row of the 4x4x4 filter they touch.  A neighbour's 8
+// trilinear corners lie in <= 4 of the 16 rows; for row s the entry is {j, weight per x cell of that row}.  Per
+// particle: off[17] (prefix over rows, u16) and SLABCAP = 4*MAXNBR entries {j (int), wx (float4)}; entries keep the
+// pair order, so every sum runs in the same order as a walk over the pair list.
+constexpr int SLABCAP = 4 * MAXNBR;
+constexpr int SLABOFF = 32;           // u16 per particle (17 used; 64-byte rows)
 
 // ---------------------------------------------------------------- PTX wrappers (same as nf_mlp.cu)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -207,7 +215,9 @@ __global__ void k_update(const float* __restrict__ pos, const float* __restrict_
 __global__ void __launch_bounds__(256) k_nbr_build(GridView g, const float* __restrict__ out_pos, int begin, int end,
                                                    float radius, int ignore_same, int use_window,
                                                    Pair* __restrict__ pairs, int* __restrict__ counts,
-                                                   float* __restrict__ counts_f, int* __restrict__ overflow) {
+                                                   float* __restrict__ counts_f, int* __restrict__ overflow,
+                                                   int* __restrict__ slab_j, float4* __restrict__ slab_w,
+                                                   unsigned short* __restrict__ slab_off) {
     const int lane = threadIdx.x & 31;
     const int i = begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (i >= end) return;
@@ -265,6 +275,88 @@ __global__ void __launch_bounds__(256) k_nbr_build(GridView g, const float* __re
         if (n > MAXNBR) atomicAdd(overflow, 1);
         counts[i] = min(n, MAXNBR);
         if (counts_f) counts_f[i] = (float)n;
+    }
+    if (slab_j) {
+        // regroup this particle's pairs by filter row (stable: ballot ranks keep the pair order)
+        __syncwarp();
+        const int nn = min(n, MAXNBR);
+        const Pair* src = pairs + (size_t)i * MAXNBR;
+        int* dj = slab_j + (size_t)i * SLABCAP;
+        float4* dw = slab_w + (size_t)i * SLABCAP;
+        unsigned short* doff = slab_off + (size_t)i * SLABOFF;
+        const unsigned lt = (1u << lane) - 1u;
+        // which x cells of filter row `sidx` does a pair feed, and with what weight
+        auto row_part = [](const uint4& h0, const float (&w)[8], int sidx, float (&wx)[4]) {
+            bool rel = false;
+            wx[0] = wx[1] = wx[2] = wx[3] = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const unsigned cell = ((c < 4 ? h0.y : h0.z) >> (8 * (c & 3))) & 0xffu;
+                if ((int)(cell >> 2) == sidx) {
+                    rel = true;
+#pragma unroll
+                    for (int xx = 0; xx < 4; ++xx)
+                        if ((int)(cell & 3) == xx) wx[xx] += w[c];
+                }
+            }
+            return rel;
+        };
+        auto load_pair = [&](int t, uint4& h0, float (&w)[8]) {
+            h0 = make_uint4(0u, 0xffffffffu, 0xffffffffu, 0u);      // cells 255: touches no row
+#pragma unroll
+            for (int c = 0; c < 8; ++c) w[c] = 0.f;
+            if (t < nn) {
+                h0 = *reinterpret_cast<const uint4*>(src + t);
+                const float4 w0 = *(reinterpret_cast<const float4*>(src + t) + 1);
+                const float4 w1 = *(reinterpret_cast<const float4*>(src + t) + 2);
+                w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w; w[4] = w1.x; w[5] = w1.y; w[6] = w1.z; w[7] = w1.w;
+            }
+        };
+        int off = 0;
+        if (nn <= 64) {        // the usual case: both 32-pair chunks stay in registers for all 16 rows
+            uint4 ha, hb;
+            float wa[8], wb[8];
+            load_pair(lane, ha, wa);
+            load_pair(32 + lane, hb, wb);
+#pragma unroll 1
+            for (int sidx = 0; sidx < 16; ++sidx) {
+                float xa[4], xb[4];
+                const bool ra = row_part(ha, wa, sidx, xa), rb = row_part(hb, wb, sidx, xb);
+                const unsigned ma = __ballot_sync(NF_FULL, ra), mb = __ballot_sync(NF_FULL, rb);
+                if (lane == 0) doff[sidx] = (unsigned short)off;
+                if (ra) {
+                    const int e = off + __popc(ma & lt);
+                    dj[e] = (int)ha.x;
+                    dw[e] = make_float4(xa[0], xa[1], xa[2], xa[3]);
+                }
+                off += __popc(ma);
+                if (rb) {
+                    const int e = off + __popc(mb & lt);
+                    dj[e] = (int)hb.x;
+                    dw[e] = make_float4(xb[0], xb[1], xb[2], xb[3]);
+                }
+                off += __popc(mb);
+            }
+        } else {               // chunks re-read per row (L1-resident: <= 6 KB per particle)
+#pragma unroll 1
+            for (int sidx = 0; sidx < 16; ++sidx) {
+                if (lane == 0) doff[sidx] = (unsigned short)off;
+                for (int t0 = 0; t0 < nn; t0 += 32) {
+                    uint4 h0;
+                    float w[8], wx[4];
+                    load_pair(t0 + lane, h0, w);
+                    const bool rel = row_part(h0, w, sidx, wx);
+                    const unsigned m = __ballot_sync(NF_FULL, rel);
+                    if (rel) {
+                        const int e = off + __popc(m & lt);
+                        dj[e] = (int)h0.x;
+                        dw[e] = make_float4(wx[0], wx[1], wx[2], wx[3]);
+                    }
+                    off += __popc(m);
+                }
+            }
+        }
+        if (lane == 0) doff[16] = (unsigned short)off;
     }
 }
 
@@ -361,7 +453,7 @@ __global__ void __launch_bounds__(256) k_layer0(const Layer0Args a) {
 // layers 1..3 on tensor cores
 // ------------------------------------------------------------------------------------------------
 struct ConvArgs {
-    const Pair* pairs; const int* cnt;     // fluid->fluid lists
+    const int* slab_j; const float4* slab_w; const unsigned short* slab_off;   // fluid->fluid slab lists
     const void* x_in;                      // (N,CIN) fp16/bf16, already ReLU'd
     const uint8_t* w_packed;               // slabs (16 conv slabs + dense slab) + fp32 bias[COUT] at the end
     const float* residual;                 // (N, ld_res) fp32 or NULL
@@ -386,10 +478,9 @@ struct ConvCfg {
     static constexpr int PACKED_BYTES = W_BYTES + COUT_PAD * 4;
     static constexpr int SM_A = 0;                                   // 128 x KSLAB halves
     static constexpr int SM_W = SM_A + 128 * KSLAB * 2;
-    static constexpr int SM_MASK = SM_W + SLAB_BYTES;                // 128 x MAXNBR uint16
-    static constexpr int SM_BIAS = SM_MASK + 128 * MAXNBR * 2;
-    static constexpr int SM_LIST = SM_BIAS + COUT_PAD * 4;           // per worker warp: MAXNBR x {j, wx[4]}
-    static constexpr int SM_BAR = SM_LIST + 16 * MAXNBR * 20;
+    static constexpr int SM_BIAS = SM_W + SLAB_BYTES;
+    static constexpr int SM_OFFS = SM_BIAS + COUT_PAD * 4;           // 16 warps x 8 rows x 32 u16: slab list row starts
+    static constexpr int SM_BAR = SM_OFFS + 16 * 8 * 32 * 2;
     static constexpr int SM_TOTAL = SM_BAR + 64;
     static_assert(SM_TOTAL <= 232448, "smem budget");
 };
@@ -406,7 +497,6 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_cconv_tc(const ConvArgs a) 
     const int row0 = a.begin + blockIdx.x * 128;
     const uint32_t s_base = smem_u32(smem);
     const uint32_t s_a = s_base + C::SM_A, s_w = s_base + C::SM_W, s_bar = s_base + C::SM_BAR;
-    unsigned short* masks = reinterpret_cast<unsigned short*>(smem + C::SM_MASK);
     float* sbias = reinterpret_cast<float*>(smem + C::SM_BIAS);
     const uint32_t bar_a_ready = s_bar, bar_w_full = s_bar + 8, bar_mma_done = s_bar + 16;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::SM_BAR + 32);
@@ -450,124 +540,162 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_cconv_tc(const ConvArgs a) 
         }
     } else {
         // ============================================================ workers: slab construction
+        // warp = 8 particles (rows of the tile), lane = channels {lane, lane+32, ...}.  For filter row s and
+        // particle r the slab list gives the neighbours that touch the row, already reduced to {j, weight per
+        // x cell}: lanes fetch the entries in parallel (one coalesced load), broadcast them by shuffle and
+        // gather 8 neighbour feature rows at a time.  The entries of the NEXT (s, r) unit are fetched before
+        // the current unit's gathers are consumed, so two dependent L2 round trips per unit overlap.
         const int rbase = warp * ROWS_PER_WARP;
-        int* lst_j = reinterpret_cast<int*>(smem + C::SM_LIST + warp * MAXNBR * 20);
-        float* lst_w = reinterpret_cast<float*>(lst_j + MAXNBR);      // [MAXNBR][4]
-        const unsigned lt = (1u << lane) - 1u;
-        // which (z,y) filter rows does each neighbour touch?
+        // row starts of this warp's 8 slab lists: smem [r][32] u16 (17 used)
+        unsigned short* offs = reinterpret_cast<unsigned short*>(smem + C::SM_OFFS) + warp * ROWS_PER_WARP * 32;
         for (int r = 0; r < ROWS_PER_WARP; ++r) {
             const int row = row0 + rbase + r;
-            const int n = (row < a.end) ? a.cnt[row] : 0;
-            for (int t = lane; t < MAXNBR; t += 32) {
-                unsigned mk = 0;
-                if (t < n) {
-                    const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(a.pairs + (size_t)row * MAXNBR + t));
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const unsigned cell = ((c < 4 ? h0.y : h0.z) >> (8 * (c & 3))) & 0xffu;
-                        mk |= 1u << (cell >> 2);
-                    }
-                }
-                masks[(rbase + r) * MAXNBR + t] = (unsigned short)mk;
-            }
+            offs[r * 32 + lane] = (row < a.end && lane < 17) ? __ldg(a.slab_off + (size_t)row * SLABOFF + lane) : (unsigned short)0;
         }
         __syncwarp();
-        for (int s = 0; s <= 16; ++s) {
-            for (int r = 0; r < ROWS_PER_WARP; ++r) {
+        // unit u = s * 8 + r: filter row s of particle r.  Entry prefetch runs two units ahead of the gathers.
+        auto fetch_entries = [&](int unit, int& ne, int& ej, float4& ew) {
+            ne = 0; ej = 0;
+            ew = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (unit >= 16 * ROWS_PER_WARP) return;
+            const int r = unit & (ROWS_PER_WARP - 1), sr = unit >> 3;
+            const int beg = offs[r * 32 + sr];
+            ne = (int)offs[r * 32 + sr + 1] - beg;
+            if (lane < ne) {
+                const size_t base = (size_t)(row0 + rbase + r) * SLABCAP + beg + lane;
+                ej = __ldg(a.slab_j + base);
+                ew = __ldg(a.slab_w + base);
+            }
+        };
+        int ne_a, ej_a, ne_b, ej_b;
+        float4 ew_a, ew_b;
+        fetch_entries(0, ne_a, ej_a, ew_a);
+        fetch_entries(1, ne_b, ej_b, ew_b);
+        // channel ownership: lane l holds channels 2l, 2l+1 (one 32-bit load / store) and, for CIN = 96, 64 + l
+        constexpr bool THIRD = (CIN == 96);
+        static_assert(CIN == 64 || CIN == 96, "channel mapping");
+        const uint32_t* xin32 = reinterpret_cast<const uint32_t*>(a.x_in);
+        const unsigned short* xin16 = reinterpret_cast<const unsigned short*>(a.x_in);
+        auto cvt2 = [](uint32_t v, float& lo, float& hi) {
+            if (BF16) { lo = __uint_as_float(v << 16); hi = __uint_as_float(v & 0xffff0000u); }
+            else { const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&v)); lo = t.x; hi = t.y; }
+        };
+        auto cvt1 = [](unsigned short v) {
+            if (BF16) return __uint_as_float((uint32_t)v << 16);
+            return __half2float(*reinterpret_cast<const __half*>(&v));
+        };
+        // first PB entries of a unit: their feature rows are requested one whole unit before they are consumed
+        // (software pipeline over units, on top of the two-units-ahead entry prefetch); entries beyond PB (rare)
+        // are gathered in place.  Lanes >= ne hold j = 0, w = 0, so every batch runs unconditionally: gathers
+        // beyond the list read row 0 (an L1 hit) and add nothing.
+        constexpr int PB = THIRD ? 12 : 16;
+        auto load_feats = [&](auto nb, int ej, int u0, uint32_t* fp, unsigned short* fs) {
+#pragma unroll
+            for (int u = 0; u < decltype(nb)::value; ++u) {
+                const int j = __shfl_sync(NF_FULL, ej, (u0 + u) & 31);
+                fp[u] = __ldg(xin32 + (((size_t)j * CIN) >> 1) + lane);
+                if (THIRD) fs[u] = __ldg(xin16 + (size_t)j * CIN + 64 + lane);
+            }
+        };
+        auto fma_feats = [&](auto nb, const float4& ew, int u0, const uint32_t* fp, const unsigned short* fs, float (&acc)[4][3]) {
+#pragma unroll
+            for (int u = 0; u < decltype(nb)::value; ++u) {
+                const int src = (u0 + u) & 31;
+                const float wx = __shfl_sync(NF_FULL, ew.x, src), wy = __shfl_sync(NF_FULL, ew.y, src);
+                const float wz = __shfl_sync(NF_FULL, ew.z, src), ww = __shfl_sync(NF_FULL, ew.w, src);
+                float f0, f1;
+                cvt2(fp[u], f0, f1);
+                acc[0][0] += wx * f0; acc[1][0] += wy * f0; acc[2][0] += wz * f0; acc[3][0] += ww * f0;
+                acc[0][1] += wx * f1; acc[1][1] += wy * f1; acc[2][1] += wz * f1; acc[3][1] += ww * f1;
+                if (THIRD) {
+                    const float f2 = cvt1(fs[u]);
+                    acc[0][2] += wx * f2; acc[1][2] += wy * f2; acc[2][2] += wz * f2; acc[3][2] += ww * f2;
+                }
+            }
+        };
+        using PBc = std::integral_constant<int, PB>;
+        using B8 = std::integral_constant<int, 8>;
+        uint32_t fpc[PB], fpn[PB];
+        unsigned short fsc[PB], fsn[PB];
+        // prologue: unit 0's entries become "current", its features are requested now
+        int ne_c = ne_a, ej_c = ej_a;
+        float4 ew_c = ew_a;
+        ne_a = ne_b; ej_a = ej_b; ew_a = ew_b;
+        fetch_entries(2, ne_b, ej_b, ew_b);
+        load_feats(PBc{}, ej_c, 0, fpc, fsc);
+#pragma unroll 1
+        for (int unit = 0; unit < 17 * ROWS_PER_WARP; ++unit) {
+            {
+                const int s = unit >> 3, r = unit & (ROWS_PER_WARP - 1);
                 const int rl = rbase + r;
                 const int row = row0 + rl;
-                float acc[4][C::CPL];
+                float acc[4][3];
 #pragma unroll
-                for (int x = 0; x < 4; ++x)
-#pragma unroll
-                    for (int m = 0; m < C::CPL; ++m) acc[x][m] = 0.f;
+                for (int x = 0; x < 4; ++x) acc[x][0] = acc[x][1] = acc[x][2] = 0.f;
                 if (s < 16) {
-                    const int n = (row < a.end) ? a.cnt[row] : 0;
-                    const Pair* pr = a.pairs + (size_t)row * MAXNBR;
-                    // phase A: lanes fetch the records of the neighbours that touch filter row s in parallel and
-                    // reduce each to {j, weight per x cell}
-                    int ne = 0;
-                    __syncwarp();
-                    for (int t0 = 0; t0 < n; t0 += 32) {
-                        const int t = t0 + lane;
-                        const bool rel = (t < n) && ((masks[rl * MAXNBR + t] >> s) & 1u);
-                        const unsigned m = __ballot_sync(NF_FULL, rel);
-                        if (rel) {
-                            const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(pr + t));
-                            const float4 w0 = __ldg(reinterpret_cast<const float4*>(pr + t) + 1);
-                            const float4 w1 = __ldg(reinterpret_cast<const float4*>(pr + t) + 2);
-                            const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-                            float wx[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                            for (int c = 0; c < 8; ++c) {
-                                const unsigned cell = ((c < 4 ? h0.y : h0.z) >> (8 * (c & 3))) & 0xffu;
-                                if ((int)(cell >> 2) == s) {
-#pragma unroll
-                                    for (int xx = 0; xx < 4; ++xx)
-                                        if ((int)(cell & 3) == xx) wx[xx] += w[c];
+                    // request the next unit's first PB feature rows, then consume this unit's
+                    load_feats(PBc{}, ej_a, 0, fpn, fsn);
+                    fma_feats(PBc{}, ew_c, 0, fpc, fsc, acc);
+                    if (ne_c > PB) {                  // rare tail: gathered in place, 8 at a time
+                        int ej = ej_c;
+                        float4 ew = ew_c;
+                        for (int e0 = 0; e0 < ne_c; e0 += 32) {
+                            if (e0 > 0) {
+                                const size_t base = (size_t)row * SLABCAP + offs[r * 32 + s] + e0 + lane;
+                                ej = 0; ew = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (e0 + lane < ne_c) {
+                                    ej = __ldg(a.slab_j + base);
+                                    ew = __ldg(a.slab_w + base);
                                 }
                             }
-                            const int e = ne + __popc(m & lt);
-                            lst_j[e] = (int)h0.x;
-                            *reinterpret_cast<float4*>(lst_w + 4 * e) = make_float4(wx[0], wx[1], wx[2], wx[3]);
-                        }
-                        ne += __popc(m);
-                    }
-                    __syncwarp();
-                    // phase B: gather the neighbours' feature rows (4 in flight) and accumulate the slab row
-                    for (int e0 = 0; e0 < ne; e0 += 4) {
-                        float f[4][C::CPL];
-                        float4 wv[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int e = min(e0 + u, ne - 1);
-                            const int j = lst_j[e];
-                            wv[u] = *reinterpret_cast<const float4*>(lst_w + 4 * e);
-                            if (e0 + u >= ne) wv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                            for (int mm = 0; mm < C::CPL; ++mm) {
-                                if (BF16) f[u][mm] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.x_in)[(size_t)j * CIN + lane + 32 * mm]);
-                                else f[u][mm] = __half2float(reinterpret_cast<const __half*>(a.x_in)[(size_t)j * CIN + lane + 32 * mm]);
-                            }
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-#pragma unroll
-                            for (int mm = 0; mm < C::CPL; ++mm) {
-                                acc[0][mm] += wv[u].x * f[u][mm];
-                                acc[1][mm] += wv[u].y * f[u][mm];
-                                acc[2][mm] += wv[u].z * f[u][mm];
-                                acc[3][mm] += wv[u].w * f[u][mm];
+                            const int cnt = min(32, ne_c - e0);
+                            for (int u0 = (e0 == 0 ? PB : 0); u0 < cnt; u0 += 8) {
+                                uint32_t fp[8];
+                                unsigned short fs[8];
+                                load_feats(B8{}, ej, u0, fp, fs);
+                                fma_feats(B8{}, ew, u0, fp, fs, acc);
                             }
                         }
                     }
+                    // rotate the pipeline: next -> current, prefetch entries three units ahead
+                    ne_c = ne_a; ej_c = ej_a; ew_c = ew_a;
+                    ne_a = ne_b; ej_a = ej_b; ew_a = ew_b;
+                    fetch_entries(unit + 3, ne_b, ej_b, ew_b);
+#pragma unroll
+                    for (int u = 0; u < PB; ++u) { fpc[u] = fpn[u]; fsc[u] = fsn[u]; }
                 } else if (row < a.end) {
                     // dense branch: the particle's own (ReLU'd) features, K = CIN
-#pragma unroll
-                    for (int mm = 0; mm < C::CPL; ++mm) {
-                        if (BF16) acc[0][mm] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.x_in)[(size_t)row * CIN + lane + 32 * mm]);
-                        else acc[0][mm] = __half2float(reinterpret_cast<const __half*>(a.x_in)[(size_t)row * CIN + lane + 32 * mm]);
-                    }
+                    cvt2(__ldg(xin32 + (((size_t)row * CIN) >> 1) + lane), acc[0][0], acc[0][1]);
+                    if (THIRD) acc[0][2] = cvt1(__ldg(xin16 + (size_t)row * CIN + 64 + lane));
                 }
                 if (r == 0 && s > 0) mbar_wait(bar_mma_done, (s - 1) & 1);   // previous slab consumed
                 const int nx = (s < 16) ? 4 : 1;
 #pragma unroll
                 for (int x = 0; x < 4; ++x) {
                     if (x < nx) {
-#pragma unroll
-                        for (int mm = 0; mm < C::CPL; ++mm) {
-                            const int k = x * CIN + lane + 32 * mm;
+                        auto pack = [](float lo, float hi) -> uint32_t {
+                            if (BF16) { __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi); return *reinterpret_cast<uint32_t*>(&h); }
+                            __half2 h = __floats2half2_rn(lo, hi);
+                            return *reinterpret_cast<uint32_t*>(&h);
+                        };
+                        {
+                            const int k = x * CIN + 2 * lane;
                             const uint32_t addr = s_a + (uint32_t)(k >> 3) * 2048 + (uint32_t)rl * 16 + (uint32_t)(k & 7) * 2;
-                            unsigned short bits;
-                            if (BF16) { __nv_bfloat16 hv = __float2bfloat16(acc[x][mm]); bits = *reinterpret_cast<unsigned short*>(&hv); }
-                            else { __half hv = __float2half(acc[x][mm]); bits = *reinterpret_cast<unsigned short*>(&hv); }
-                            asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(bits) : "memory");
+                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(pack(acc[x][0], acc[x][1])) : "memory");
+                        }
+                        if (THIRD) {
+                            const int k = x * CIN + 64 + lane;
+                            const uint32_t addr = s_a + (uint32_t)(k >> 3) * 2048 + (uint32_t)rl * 16 + (uint32_t)(k & 7) * 2;
+                            const uint32_t bits = pack(acc[x][2], 0.f);
+                            asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)(bits & 0xffffu)) : "memory");
                         }
                     }
                 }
+                if (r == ROWS_PER_WARP - 1) {
+                    fence_proxy_async();
+                    mbar_arrive(bar_a_ready);
+                }
             }
-            fence_proxy_async();
-            mbar_arrive(bar_a_ready);
         }
         // ============================================================ epilogue (warps 0-3, thread = row)
         if (warp < 4) {
@@ -662,7 +790,7 @@ inline PackedLayout packed_layout() {
 }
 
 struct WsLayout {
-    size_t pos_new, vel_new, grid_f, grid_b, pairs_ff, cnt_ff, pairs_fb, cnt_fb, ans0, x0, ans1, x1, ans2, x2, ans3,
+    size_t pos_new, vel_new, grid_f, grid_b, pairs_ff, cnt_ff, pairs_fb, cnt_fb, slab_j, slab_w, slab_off, ans0, x0, ans1, x1, ans2, x2, ans3,
         flags, total;
 };
 inline WsLayout ws_layout(int n, int m) {
@@ -675,6 +803,7 @@ inline WsLayout ws_layout(int n, int m) {
     L.grid_b = take(grid_layout(m).total);
     L.pairs_ff = take(N * MAXNBR * sizeof(Pair)); L.cnt_ff = take(N * 4);
     L.pairs_fb = take(N * MAXNBR * sizeof(Pair)); L.cnt_fb = take(N * 4);
+    L.slab_j = take(N * SLABCAP * 4); L.slab_w = take(N * SLABCAP * 16); L.slab_off = take(N * SLABOFF * 2);
     L.ans0 = take(N * 96 * 4); L.x0 = take(N * 96 * 2);
     L.ans1 = take(N * 64 * 4); L.x1 = take(N * 64 * 2);
     L.ans2 = take(N * 64 * 4); L.x2 = take(N * 64 * 2);
@@ -789,6 +918,8 @@ extern "C" int nf_transition_step(const nf_transition_args* a, void* stream_) {
     float* vel_new = (float*)(b + L.vel_new);
     Pair* pairs_ff = (Pair*)(b + L.pairs_ff); int* cnt_ff = (int*)(b + L.cnt_ff);
     Pair* pairs_fb = (Pair*)(b + L.pairs_fb); int* cnt_fb = (int*)(b + L.cnt_fb);
+    int* slab_j = (int*)(b + L.slab_j); float4* slab_w = (float4*)(b + L.slab_w);
+    unsigned short* slab_off = (unsigned short*)(b + L.slab_off);
     float* ans0 = (float*)(b + L.ans0); void* x0 = b + L.x0;
     float* ans1 = (float*)(b + L.ans1); void* x1 = b + L.x1;
     float* ans2 = (float*)(b + L.ans2); void* x2 = b + L.x2;
@@ -810,10 +941,10 @@ extern "C" int nf_transition_step(const nf_transition_args* a, void* stream_) {
         if (nshard > 0) {
             const int blocks = (nshard + 7) / 8;
             k_nbr_build<<<blocks, 256, 0, st>>>(grid_view(b + L.grid_f, N), pos_new, begin, end, radius, 1, 1, pairs_ff,
-                                               cnt_ff, a->nnbr_out, flags);
+                                               cnt_ff, a->nnbr_out, flags, slab_j, slab_w, slab_off);
             NF_LAUNCH_OK();
             k_nbr_build<<<blocks, 256, 0, st>>>(grid_view(b + L.grid_b, M), pos_new, begin, end, radius, 1, 1, pairs_fb,
-                                               cnt_fb, nullptr, flags + 1);
+                                               cnt_fb, nullptr, flags + 1, nullptr, nullptr, nullptr);
             NF_LAUNCH_OK();
             Layer0Args l0;
             l0.pairs_ff = pairs_ff; l0.cnt_ff = cnt_ff; l0.pairs_fb = pairs_fb; l0.cnt_fb = cnt_fb;
@@ -830,7 +961,7 @@ extern "C" int nf_transition_step(const nf_transition_args* a, void* stream_) {
         }
     }
     ConvArgs c;
-    c.pairs = pairs_ff; c.cnt = cnt_ff; c.n = N; c.begin = begin; c.end = end;
+    c.slab_j = slab_j; c.slab_w = slab_w; c.slab_off = slab_off; c.n = N; c.begin = begin; c.end = end;
     if (all || a->phase == 1) {     // conv1 + dense1 : 96 -> 64 (no residual: widths differ, :127-130)
         c.x_in = x0; c.w_packed = w + PL.l1; c.residual = nullptr; c.ld_res = 0; c.ans = ans1; c.x_out = x1; c.cout = 64;
         int rc = launch_conv<96, 64>(c, a->dtype, st);

@@ -45,7 +45,7 @@ def launches(path):
     print(f"# {n} launches captured, {tot:.1f} ms total (cold-cache, serialised under the profiler: compare SHARES)")
     print("kernel,launches,total_ms,share")
     for k, (c, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        print(f"{k},{c},{ms:.3f},{ms / tot:.4f}")
+        print(f'"{k}",{c},{ms:.3f},{ms / tot:.4f}')
 
 
 def full(paths):
@@ -56,7 +56,7 @@ def full(paths):
         hdr, units = rows[0], rows[1]
         for v in rows[2:]:
             d = dict(zip(hdr, v)); u = dict(zip(hdr, units))
-            print(p.split("/")[-1] + "," + short(d["Kernel Name"]) + "," +
+            print(p.split("/")[-1] + ',"' + short(d["Kernel Name"]) + '",' +
                   ",".join(f"{d.get(m, '')} {u.get(m, '')}".strip().replace(",", "") for m in METRICS))
 
 
