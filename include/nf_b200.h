@@ -211,6 +211,22 @@ NF_API int nf_transition_step(const nf_transition_args* args, void* stream);
 NF_API int nf_transition_layer_buffer(int n_fluid, int n_box, int layer, size_t* offset_bytes_host,
                                       size_t* row_bytes_host);
 
+/* ---------------------------------------------------------------------------------------------
+ * Callers' side of the hot paths: camera rays and evaluation metrics on the device
+ * ------------------------------------------------------------------------------------------- */
+/* replaces: get_ray_directions + get_rays (utils/ray_utils.py:85-104, 107-130) for one view.
+ * c2w_dev: (3,4) row-major camera-to-world matrix in device memory; rays_out: (H*W,6) [origin, unit direction],
+ * pixel (row j, column i) at index j*W + i. */
+NF_API int nf_generate_rays(int H, int W, float focal, const float* c2w_dev, float* rays_out, void* stream);
+/* replaces: cKDTree(pred).query(gt) (utils/point_eval.py:11-14): for every query the Euclidean distance to (and
+ * optionally the index of) the nearest point of the grid-sorted set (nf_grid_build with any cell size). */
+NF_API int nf_nearest_distance(const void* grid_ws, int n_points, const float* queries, int n_queries, float* dist_out,
+                               int32_t* idx_out /* may be NULL */, void* stream);
+/* replaces: _distance (utils/point_eval.py:7-8): per-point distance of two equally ordered (n,3) sets. */
+NF_API int nf_pair_distance(const float* a, const float* b, int n, float* dist_out, void* stream);
+/* replaces: img2mse numerator (trainer/trainer_e2e.py:24): sum over n floats of (a-b)^2 into a device double. */
+NF_API int nf_sqdiff_sum(const float* a, const float* b, long long n, double* sum_out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

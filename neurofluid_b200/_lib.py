@@ -66,6 +66,10 @@ SIGNATURES = {
     "nf_transition_num_phases": (C.c_int, []),
     "nf_transition_step": (C.c_int, [C.POINTER(TransitionArgs), _vp]),
     "nf_transition_layer_buffer": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(_sz), C.POINTER(_sz)]),
+    "nf_generate_rays": (C.c_int, [C.c_int, C.c_int, _f32, _vp, _vp, _vp]),
+    "nf_nearest_distance": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp]),
+    "nf_pair_distance": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
+    "nf_sqdiff_sum": (C.c_int, [_vp, _vp, C.c_longlong, _vp, _vp]),
 }
 
 _lib = None

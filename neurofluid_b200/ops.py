@@ -7,7 +7,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import check, lib, ptr, require_cuda, stream_ptr
+from ._lib import check, lib, ptr, require_cuda, stream_ptr  # noqa: F401 (require_cuda re-exported)
 
 CELL_SCALE = 1.002   # grid cell edge = CELL_SCALE * search radius (include/nf_b200.h: nf_grid_build)
 
@@ -69,3 +69,54 @@ def nerf_mlp(packed: torch.Tensor, records: torch.Tensor, dtype=_lib.NF_DTYPE_F1
     check(lib().nf_nerf_mlp_forward(ptr(packed), int(dtype), ptr(rec), rec.shape[0], int(bool(sigma_only)), ptr(out),
                                     stream_ptr()), "nf_nerf_mlp_forward")
     return out
+
+
+def generate_rays(H: int, W: int, focal: float, c2w: torch.Tensor) -> torch.Tensor:
+    """get_ray_directions + get_rays (utils/ray_utils.py:85-130) for one view, on the device: (H*W, 6)."""
+    require_cuda(c2w)
+    m = c2w.detach().to(torch.float32).contiguous()
+    if m.shape != (3, 4):
+        raise _lib.NFError(f"c2w must be (3,4), got {tuple(m.shape)}")
+    rays = torch.empty((H * W, 6), dtype=torch.float32, device=m.device)
+    check(lib().nf_generate_rays(int(H), int(W), float(focal), ptr(m), ptr(rays), stream_ptr()), "nf_generate_rays")
+    return rays
+
+
+def nearest_distance(queries: torch.Tensor, points: torch.Tensor, cell: float = 0.1, grid: Grid | None = None,
+                     return_index: bool = False):
+    """cKDTree(points).query(queries) (utils/point_eval.py:11-14): distance to the nearest point, exact."""
+    require_cuda(queries, points)
+    q = queries.detach().to(torch.float32).contiguous().view(-1, 3)
+    grid = grid or Grid(points, cell)
+    dist = torch.empty((q.shape[0],), dtype=torch.float32, device=q.device)
+    idx = torch.empty((q.shape[0],), dtype=torch.int32, device=q.device) if return_index else None
+    check(lib().nf_nearest_distance(ptr(grid.ws), grid.n, ptr(q), q.shape[0], ptr(dist), ptr(idx), stream_ptr()),
+          "nf_nearest_distance")
+    return (dist, idx.to(torch.int64)) if return_index else dist
+
+
+def pair_distance(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """np.linalg.norm(a - b, axis=-1) (utils/point_eval.py:7-8)."""
+    require_cuda(a, b)
+    a, b = a.detach().to(torch.float32).contiguous().view(-1, 3), b.detach().to(torch.float32).contiguous().view(-1, 3)
+    if a.shape != b.shape:
+        raise _lib.NFError(f"pair_distance: shapes differ {tuple(a.shape)} vs {tuple(b.shape)}")
+    out = torch.empty((a.shape[0],), dtype=torch.float32, device=a.device)
+    check(lib().nf_pair_distance(ptr(a), ptr(b), a.shape[0], ptr(out), stream_ptr()), "nf_pair_distance")
+    return out
+
+
+def img2mse(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """torch.mean((x - y) ** 2) (trainer/trainer_e2e.py:24) as a 0-dim device tensor (float64 accumulation)."""
+    require_cuda(x, y)
+    x, y = x.detach().to(torch.float32).contiguous(), y.detach().to(torch.float32).contiguous()
+    if x.shape != y.shape:
+        raise _lib.NFError(f"img2mse: shapes differ {tuple(x.shape)} vs {tuple(y.shape)}")
+    acc = torch.empty((), dtype=torch.float64, device=x.device)
+    check(lib().nf_sqdiff_sum(ptr(x), ptr(y), x.numel(), ptr(acc), stream_ptr()), "nf_sqdiff_sum")
+    return (acc / max(x.numel(), 1)).to(torch.float32)
+
+
+def mse2psnr(mse: torch.Tensor) -> torch.Tensor:
+    """-10 log10(mse) (trainer/trainer_e2e.py:25); stays on the device."""
+    return -10.0 * torch.log10(mse)
