@@ -174,6 +174,32 @@ def bench_transition(dev, world, rank, args, timed, pk):
                          "note": "41 GFLOP per step: launch/latency-bound by construction (SURVEY 8d)"}}
 
 
+def bench_end2end(dev, world, rank, timed):
+    """BASELINE config[3]-shaped end-to-end rollout (eval_e2e.py:58-120): 60 frames of transition step + one
+    400x400 view, 23^3 = 12,167 particles, transition replicated, rays sharded by image row over the ranks."""
+    import neurofluid_b200 as nb
+    from neurofluid_b200 import pipeline, scenes
+    n, Hh, frames = 23, 400, 60
+    half = (n - 1) / 2 * 0.05
+    pos = torch.from_numpy(scenes.lattice_particles(n, 0, center=(0.0, 0.0, -1 + 0.03 + half))).to(dev)
+    vel = torch.zeros_like(pos)
+    bp, bn = scenes.box_points(0.032)
+    box, box_n = torch.from_numpy(bp).to(dev), torch.from_numpy(bn).to(dev)
+    tn = nb.ParticleNet(gravity=(0.0, 0.0, -9.81)); tn.load_state_dict(scenes.init_particle_state(0)); tn = tn.to(dev)
+    rn = nb.RenderNet(scenes.render_cfg(), scenes.NEAR, scenes.FAR); rn.load_state_dict(scenes.init_render_state(0, 5.0)); rn = rn.to(dev)
+    _, focal, cw = scenes.camera_rays(Hh, Hh)
+    # the camera of eval_renderer.py looks at the origin; the block rests on the box floor: aim it there
+    cw = cw.clone(); cw[2, 3] += -1 + 0.03 + half
+    cams = [(cw, focal)]
+    pipeline.rollout_and_render(tn, rn, pos, vel, box, box_n, cams, Hh, Hh, 3)          # warm-up
+    ms = timed(lambda: pipeline.rollout_and_render(tn, rn, pos, vel, box, box_n, cams, Hh, Hh, frames), 1)
+    return {"metric": "frames_per_sec_end2end_400x400", "value": frames / (ms * 1e-3), "unit": "frames/s", "frames": frames,
+            "ms_per_frame": ms / frames, "rays_per_sec": frames * Hh * Hh / (ms * 1e-3), "n_particles": n ** 3,
+            "n_box": int(box.shape[0]), "image": f"{Hh}x{Hh}", "views_per_frame": 1, "scaling": "strong",
+            "parallelism": f"transition replicated, rays sharded by image row over {world} GPU(s)",
+            "note": "BASELINE config[3] shape (honeycone stand-in): transition step + device ray generation + render per frame"}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path, all host threads."""
     if rank != 0:
@@ -341,6 +367,7 @@ def main():
     }
     # ---- second hot path (BASELINE config[2]): transition-model rollout, ~30k particles, reported as an extra block
     line["transition"] = bench_transition(dev, world, rank, args, timed, pk)
+    line["end2end"] = bench_end2end(dev, world, rank, timed)
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         v, cores, sample = cpu_reference_rays_per_sec(CPU_SAMPLE_RAYS)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
