@@ -516,6 +516,8 @@ __device__ __forceinline__ void ray_query_group(const StageArgs& p, int lane, co
         }
         if (coarse_pass && lane == 0) p.base0[(size_t)ray * act_stride + slot] = base;
     }
+    // mask words of unused 32-sample steps (S not a multiple that fills act_stride) must read as "none valid"
+    if (lane >= nslots && lane < act_stride) act[(size_t)ray * act_stride + lane] = 0u;
     if (lane == 0 && n_active) atomicAdd(active_counter, n_active);
 }
 

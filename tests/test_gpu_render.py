@@ -152,6 +152,48 @@ def test_render_search_flavours_agree_bitwise(dev, name):
     assert rel_l2(a["rgb1"].cpu(), c["g"]["forward.rgb1"]) < RGB_TOL
 
 
+@pytest.mark.parametrize("n_samples,n_importance,K", [(32, 64, 20), (64, 64, 8), (96, 160, 20), (128, 128, 32), (3, 1, 5)])
+def test_render_other_sample_counts_and_K_against_oracle(dev, n_samples, n_importance, K):
+    """Every (coarse, fine) step-count template and K bound, on rays through the fluid silhouette."""
+    H = 40
+    rays, focal, cw = scenes.camera_rays(H, H)
+    rays = scenes.center_crop_rays(rays, H, H, 12)
+    particles = torch.from_numpy(scenes.lattice_particles(10, 5))
+    cfg = scenes.render_cfg(n_samples=n_samples, n_importance=n_importance, n_neighbor=K)
+    sd = scenes.init_render_state(5, 5.0)
+    ref = orender.render_forward(sd, cfg, scenes.NEAR, scenes.FAR, particles, cw[:, 3], rays)
+    for search in ("sweep", "stream"):
+        out = make_net(cfg, sd, dev, search=search)(particles.to(dev), cw[:, 3].to(dev), rays.to(dev), focal, cw.to(dev))
+        assert torch.equal(out["num_nn_0"].cpu(), ref["num_nn_0"]), search
+        assert torch.equal(out["mask_0"].cpu().view(-1), ref["mask_0"].view(-1).float()), search
+        assert rel_l2(out["rgb0"].cpu(), ref["rgb0"]) < RGB_TOL and rel_l2(out["rgb1"].cpu(), ref["rgb1"]) < RGB_TOL
+        assert (out["num_nn_1"].cpu() != ref["num_nn_1"]).float().mean() < 5e-3
+
+
+def test_render_large_particle_set_takes_the_stream_search(dev):
+    """P > 65,536: the auto flavour is the index-order stream; sparse cloud so that most samples are partial."""
+    rng = np.random.RandomState(4)
+    particles = torch.from_numpy(rng.uniform(-0.9, 0.9, (70001, 3)).astype(np.float32))
+    H = 24
+    rays, focal, cw = scenes.camera_rays(H, H)
+    rays = scenes.center_crop_rays(rays, H, H, 6)
+    cfg = scenes.render_cfg(n_samples=64, n_importance=32)
+    cfg.NN_search.search_raduis_scale = 2.0            # r = 0.05: ~4 particles per ball -> never K = 20
+    sd = scenes.init_render_state(1, 5.0)
+    ref = orender.render_forward(sd, cfg, scenes.NEAR, scenes.FAR, particles, cw[:, 3], rays)
+    out = make_net(cfg, sd, dev)(particles.to(dev), cw[:, 3].to(dev), rays.to(dev), focal, cw.to(dev))
+    assert torch.equal(out["num_nn_0"].cpu(), ref["num_nn_0"]) and out["num_nn_0"].max() > 0
+    assert rel_l2(out["rgb1"].cpu(), ref["rgb1"]) < RGB_TOL
+    with pytest.raises(_lib.NFError):
+        make_net(cfg, sd, dev, search="sweep")(particles.to(dev), cw[:, 3].to(dev), rays.to(dev), focal, cw.to(dev))
+    cfg2 = scenes.render_cfg(n_samples=64, n_importance=32, use_mask=False)
+    cfg2.NN_search.search_raduis_scale = 4.0           # r = 0.1: ~36 per ball -> mostly full
+    ref2 = orender.render_forward(sd, cfg2, scenes.NEAR, scenes.FAR, particles, cw[:, 3], rays)
+    out2 = make_net(cfg2, sd, dev)(particles.to(dev), cw[:, 3].to(dev), rays.to(dev), focal, cw.to(dev))
+    assert torch.equal(out2["num_nn_0"].cpu(), ref2["num_nn_0"])
+    assert rel_l2(out2["rgb0"].cpu(), ref2["rgb0"]) < RGB_TOL and rel_l2(out2["rgb1"].cpu(), ref2["rgb1"]) < RGB_TOL
+
+
 def test_render_operand_dtype_switch_and_errors(dev):
     c = load_render_case("small_boost")
     net = make_net(c["cfg"], c["sd"], dev, operand_dtype="bf16")
