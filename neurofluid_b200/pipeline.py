@@ -143,19 +143,23 @@ class FluidErrors:
 # ------------------------------------------------------------------------------------------------ rollout
 @torch.no_grad()
 def rollout_and_render(transition_model, renderer, pos, vel, box, box_normals, cameras, H, W, n_frames,
-                       gt_positions=None, gt_images=None, group=None, keep_images=False):
+                       gt_positions=None, gt_images=None, group=None, keep_images=False, transition="replicated"):
     """The loop of eval_e2e.py:58-120 without the dataset: for every frame one transition step, the position
     metrics, and for every camera `(c2w (3,4), focal)` one rendered image (+ PSNR against `gt_images[f][v]`).
 
-    With torch.distributed initialised the transition model runs replicated and the rays of every image are sharded
-    block-cyclically by row over the ranks of `group` (the throughput-optimal layout); the
-    returned images are the local rows unless `keep_images`, which all-gathers them.  Nothing in the loop
-    synchronises with the host."""
+    With torch.distributed initialised the rays of every image are sharded block-cyclically by row over the ranks
+    of `group`; the transition model runs replicated (`transition="replicated"`, the throughput-optimal layout of
+    SURVEY.md section 8e) or particle-block sharded with an NCCL all-gather per layer and of the positions per step
+    (`transition="sharded"`, BASELINE.json's north_star layout; bit-identical results).  The returned images are
+    the local rows unless `keep_images`, which all-gathers them.  Nothing in the loop synchronises with the host."""
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     if len(cameras) == 0:
         raise NFError("rollout_and_render: no cameras")
+    if transition not in ("replicated", "sharded"):
+        raise NFError(f"rollout_and_render: transition={transition!r}")
+    from .distributed import transition_step_sharded
     fe = FluidErrors()
     cams = [(torch.as_tensor(c2w, dtype=torch.float32, device=pos.device), float(f)) for c2w, f in cameras]
     # rays of a fixed camera do not change between frames: generate once on the device, keep this rank's rows
@@ -163,7 +167,10 @@ def rollout_and_render(transition_model, renderer, pos, vel, box, box_normals, c
             for c2w, f in cams]
     frames, psnr, pos_hist = [], [], []
     for fidx in range(n_frames):
-        pos, vel, _ = transition_model(pos, vel, box, box_normals)
+        if transition == "sharded" and world > 1:
+            pos, vel, _ = transition_step_sharded(transition_model, pos, vel, box, box_normals, group)
+        else:
+            pos, vel, _ = transition_model(pos, vel, box, box_normals)
         pos, vel = pos.clone(), vel.clone()                      # eval_e2e.py:83
         if gt_positions is not None:
             fe.cal_errors(pos, gt_positions[fidx], fidx + 1)

@@ -42,9 +42,26 @@ p1, v1, n1 = tn(pos, vel, box, box_n)
 p1, v1, n1 = p1.clone(), v1.clone(), n1.clone()
 p2, v2, n2 = transition_step_sharded(tn, pos, vel, box, box_n)
 ok_t = torch.equal(p1, p2) and torch.equal(v1, v2) and torch.equal(n1, n2)
-res = torch.tensor([int(ok_r), int(ok_t)], device=dev)
+# eval_e2e-shaped rollout: sharded rays (+ sharded or replicated transition) == one process doing everything
+from neurofluid_b200 import ops, pipeline  # noqa: E402
+cams = [(cw, focal)]
+ok_e = True
+p0, v0 = pos, vel
+ref_img, ref_pos = [], []
+for f in range(2):
+    p0, v0, _ = tn(p0, v0, box, box_n)
+    p0, v0 = p0.clone(), v0.clone()
+    rr = ops.generate_rays(H, H, focal, cw.to(dev))
+    ref_img.append(net(p0, ro, rr, focal, cw)["rgb1"].view(H, H, 3).clone())
+    ref_pos.append(p0)
+for mode in ("replicated", "sharded"):
+    out = pipeline.rollout_and_render(tn, net, pos, vel, box, box_n, cams, H, H, 2, keep_images=True, transition=mode)
+    for f in range(2):
+        ok_e = ok_e and torch.equal(out["positions"][f], ref_pos[f]) and torch.equal(out["images"][f][0], ref_img[f])
+res = torch.tensor([int(ok_r), int(ok_t), int(ok_e)], device=dev)
 dist.all_reduce(res, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print(f"mgpu_check world={world}: renderer sharded==single {bool(res[0])}, transition sharded==single {bool(res[1])}")
+    print(f"mgpu_check world={world}: renderer sharded==single {bool(res[0])}, transition sharded==single {bool(res[1])}, "
+          f"rollout (sharded rays, replicated / sharded transition)==single {bool(res[2])}")
 dist.destroy_process_group()
 sys.exit(0 if bool(res.min()) else 1)
