@@ -194,6 +194,34 @@ def test_render_large_particle_set_takes_the_stream_search(dev):
     assert rel_l2(out2["rgb0"].cpu(), ref2["rgb0"]) < RGB_TOL and rel_l2(out2["rgb1"].cpu(), ref2["rgb1"]) < RGB_TOL
 
 
+@pytest.mark.parametrize("use_mask", [True, False])
+def test_render_degenerate_particle_sets(dev, use_mask):
+    """Empty set, a single particle, and K coincident particles (a neighbour at distance exactly 0 counts as
+    padding in the reference, models/renderer.py:137) -- against the oracle."""
+    H = 32
+    rays, focal, cw = scenes.camera_rays(H, H)
+    rays = scenes.center_crop_rays(rays, H, H, 8)
+    cfg = scenes.render_cfg(use_mask=use_mask, n_samples=64, n_importance=64, n_neighbor=4)
+    sd = scenes.init_render_state(2, 5.0)
+    z = orender.coarse_z_table(scenes.NEAR, scenes.FAR, 64)
+    on_ray = rays[27, :3] + rays[27, 3:] * z[40]                    # exactly a coarse sample position of ray 27
+    sets = [torch.zeros(0, 3), torch.tensor([[0.02, -0.01, 0.03]]), on_ray.repeat(5, 1),
+            torch.cat([on_ray[None], on_ray[None] + torch.tensor([[0.01, 0.0, 0.0]]), torch.zeros(3, 3)])]
+    for particles in sets:
+        net = make_net(cfg, sd, dev)
+        out = net(particles.to(dev), cw[:, 3].to(dev), rays.to(dev), focal, cw.to(dev))
+        if particles.shape[0] == 0:
+            assert (out["num_nn_0"] == 0).all() and (out["num_nn_1"] == 0).all() and (out["mask_1"] == 0).all()
+            if use_mask:
+                assert (out["rgb1"] == 1).all() and (out["opacity1"] == 0).all()
+            continue
+        ref = orender.render_forward(sd, cfg, scenes.NEAR, scenes.FAR, particles, cw[:, 3], rays)
+        assert torch.equal(out["num_nn_0"].cpu(), ref["num_nn_0"]), particles.shape
+        assert torch.equal(out["mask_0"].cpu().view(-1), ref["mask_0"].view(-1).float())
+        assert rel_l2(out["rgb0"].cpu(), ref["rgb0"]) < RGB_TOL and rel_l2(out["rgb1"].cpu(), ref["rgb1"]) < RGB_TOL
+        assert (out["num_nn_1"].cpu() != ref["num_nn_1"]).float().mean() < 5e-3
+
+
 def test_render_operand_dtype_switch_and_errors(dev):
     c = load_render_case("small_boost")
     net = make_net(c["cfg"], c["sd"], dev, operand_dtype="bf16")
