@@ -37,7 +37,7 @@ H = W = 800
 N_LATTICE = 27            # 27^3 = 19,683 particles
 MLP_FLOP_PER_ROW = 2 * 665984      # SURVEY.md 8d / BASELINE.md: 1,331,968 FLOP per evaluated sample
 CPU_SAMPLE_RAYS = 8192       # ~7-10 s of host work per timing at ~1.2k rays/s
-REF_STEP_RAYS = 2048          # --impl reference: rays per step (keeps K+W steps within a few minutes)
+REF_STEP_RAYS = int(os.environ.get("NF_REF_STEP_RAYS", "2048"))   # --impl reference: rays per step (K+W steps stay within minutes)
 
 
 def workload():
