@@ -198,6 +198,9 @@ typedef struct nf_transition_args {
        layer; rows outside the shard must be supplied by the caller between layers (see
        neurofluid_b200/distributed.py).  Single GPU: 0, n_fluid. */
     int32_t shard_begin, shard_end;
+    int32_t* overflow_out; /* optional device int32[2]: += number of particles of this call whose fluid / box neighbour
+                              list exceeded the 128 slots and was truncated (the reference has no cap): callers that
+                              care poll it -- results are only reference-exact while it stays 0 */
     int32_t phase; /* -1: whole step on all particles;  0..4: run only that phase on [shard_begin, shard_end):
                       0 integrate + grids + neighbour lists + layer 0,  1..3 conv layers,  4 position update.
                       Between phases the caller all-gathers the layer outputs (nf_transition_layer_buffer). */

@@ -183,6 +183,10 @@ __device__ __forceinline__ void filter_corners(float rx, float ry, float rz, flo
 }
 
 // ------------------------------------------------------------------------------------------------
+__global__ void k_add_overflow(const int* __restrict__ flags, int* __restrict__ out) {
+    if (threadIdx.x < 2 && flags[threadIdx.x]) atomicAdd(out + threadIdx.x, flags[threadIdx.x]);
+}
+
 __global__ void k_integrate(const float* __restrict__ pos, const float* __restrict__ vel, int n, float gx, float gy,
                             float gz, float dt, float* __restrict__ pos_new, float* __restrict__ vel_new) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -946,6 +950,10 @@ extern "C" int nf_transition_step(const nf_transition_args* a, void* stream_) {
             k_nbr_build<<<blocks, 256, 0, st>>>(grid_view(b + L.grid_b, M), pos_new, begin, end, radius, 1, 1, pairs_fb,
                                                cnt_fb, nullptr, flags + 1, nullptr, nullptr, nullptr);
             NF_LAUNCH_OK();
+            if (a->overflow_out) {
+                k_add_overflow<<<1, 32, 0, st>>>(flags, a->overflow_out);
+                NF_LAUNCH_OK();
+            }
             Layer0Args l0;
             l0.pairs_ff = pairs_ff; l0.cnt_ff = cnt_ff; l0.pairs_fb = pairs_fb; l0.cnt_fb = cnt_fb;
             l0.vel_new = vel_new; l0.box_normals = a->box_normals;

@@ -188,6 +188,8 @@ def rollout_and_render(transition_model, renderer, pos, vel, box, box_normals, c
             views.append(img)
         frames.append(views)
         pos_hist.append(pos)
+    if hasattr(transition_model, "check_neighbor_overflow"):
+        transition_model.check_neighbor_overflow()               # the one host sync of the rollout
     out = {"positions": pos_hist, "images": frames, "fluid_errors": fe}
     if gt_images is not None:
         mse = torch.stack(psnr).view(n_frames, len(cams))

@@ -62,6 +62,7 @@ class ParticleNet(nn.Module):
         self._ws = None
         self.num_fluid_neighbors = None
         self.pos_correction = None
+        self._overflow = None      # device int32[2]: particles whose fluid / box neighbour list was truncated
 
     # ------------------------------------------------------------------ internals
     def ordered_params(self):
@@ -110,7 +111,19 @@ class ParticleNet(nn.Module):
         a.delta_out = ptr(outs[3])
         a.workspace, a.workspace_bytes = ptr(ws), ws.numel()
         a.shard_begin, a.shard_end, a.phase = int(shard[0]), int(shard[1]), int(phase)
+        if self._overflow is None or self._overflow.device != pos.device:
+            self._overflow = torch.zeros(2, dtype=torch.int32, device=pos.device)
+        a.overflow_out = ptr(self._overflow)
         return a
+
+    def check_neighbor_overflow(self):
+        """The kernels keep at most 128 fluid and 128 box neighbours per particle (the reference has no cap).  Returns
+        silently while no list was ever truncated, raises otherwise.  Synchronises: call it once per rollout."""
+        if self._overflow is not None:
+            nf, nb = self._overflow.tolist()
+            if nf or nb:
+                raise NFError(f"neighbour lists truncated at 128 entries for {nf} (fluid) / {nb} (box) particle-steps: "
+                              "results differ from the reference; the scene is denser than the kernels support")
 
     def _prepare(self, pos, vel, box, box_feats, feats):
         if feats is not None:
@@ -160,6 +173,7 @@ def smoke_check(dev):
     box, box_n = torch.from_numpy(bp), torch.from_numpy(bn)
     p1, v1, nn1 = net(pos.to(dev), vel.to(dev), box.to(dev), box_n.to(dev))
     torch.cuda.synchronize()
+    net.check_neighbor_overflow()
     rp, rv, rn, dbg = otrans.particle_step(sd, pos, vel, box, box_n, debug=True)
     assert torch.equal(nn1.cpu(), rn), "fluid neighbour counts differ from the oracle"
     err = float(torch.norm(net.pos_correction.cpu() - dbg["feats"][-1] / 128) / torch.norm(dbg["feats"][-1] / 128))

@@ -6,7 +6,7 @@ import ctypes
 dev = torch.device("cuda:0")
 H = 800
 rays, focal, cw = scenes.camera_rays(H, H)
-particles = torch.from_numpy(scenes.lattice_particles(27, 0))
+particles = torch.from_numpy(scenes.lattice_particles(int(os.environ.get('NF_TUNE_N', '27')), 0))
 net = nb.RenderNet(scenes.render_cfg(), scenes.NEAR, scenes.FAR); net.load_state_dict(scenes.init_render_state(0, 5.0)); net = net.to(dev)
 rays_d, p_d, ro = rays.to(dev), particles.to(dev), cw[:, 3].to(dev)
 L = _lib.lib()

@@ -118,3 +118,21 @@ def test_full_size_rollout_properties(dev):
     rp, rv, rn = otrans.particle_step(sd, first[0], torch.zeros_like(first[0]), box.cpu(), box_n.cpu())
     assert torch.equal(first[3], rn)
     assert rel_l2(first[1], rp) < 1e-6 and rel_l2(first[2], rv) < 1e-3
+
+
+def test_neighbor_list_overflow_is_reported(dev):
+    """More than 128 neighbours inside the search radius: the lists are truncated and the module says so."""
+    net = nb.ParticleNet(gravity=(0.0, 0.0, -9.81))
+    net.load_state_dict(scenes.init_particle_state(0))
+    net = net.to(dev)
+    rng = np.random.RandomState(0)
+    bp, bn = scenes.box_points(0.1)
+    box, box_n = torch.from_numpy(bp).to(dev), torch.from_numpy(bn).to(dev)
+    sparse = torch.from_numpy(scenes.lattice_particles(6, 0)).to(dev)
+    net(sparse, torch.zeros_like(sparse), box, box_n)
+    net.check_neighbor_overflow()                                     # fine
+    dense = torch.from_numpy(rng.uniform(-0.05, 0.05, (400, 3)).astype(np.float32)).to(dev)   # 400 points in one ball
+    p, v, n = net(dense, torch.zeros_like(dense), box, box_n)
+    assert float(n.max()) > 128                                       # the reported count is the true one
+    with pytest.raises(_lib.NFError):
+        net.check_neighbor_overflow()
