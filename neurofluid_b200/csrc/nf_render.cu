@@ -282,9 +282,36 @@ __device__ __forceinline__ int search_scs(const StageArgs& p, int lane, const fl
             const int r = row0 + lane;
             int beg = 0, end = 0;
             if (r < nrows) {
-                const int rowbase = ((loz + r / wy) * ny + (loy + r % wy)) * nx;
-                beg = __ldg(p.g.cell_start + rowbase + lox);
-                end = __ldg(p.g.cell_start + rowbase + hix + 1);
+                // Row of cells (cy, cz): only the part of the segment whose y and z come within reach of the row's
+                // box can have neighbours there; that parameter interval also bounds the x cells worth reading.
+                // (A particle within `pad` of the segment at parameter t has y(t), z(t) within pad of its own y, z.)
+                // Grid boundary rows / cells also hold whatever was clamped into them: unbounded on that side.
+                const int cy = loy + r % wy, cz = loz + r / wy;
+                const float big = 3.0e30f;
+                const float y0 = cy == 0 ? -big : oy + (float)cy * h->cell - pad, y1 = cy == ny - 1 ? big : oy + (float)(cy + 1) * h->cell + pad;
+                const float z0 = cz == 0 ? -big : oz + (float)cz * h->cell - pad, z1 = cz == nz - 1 ? big : oz + (float)(cz + 1) * h->cell + pad;
+                float t0 = 0.f, t1 = 1.f;
+                bool any = true;
+                if (fabsf(ey) > 1e-12f) {
+                    const float ta = (y0 - ay) / ey, tb = (y1 - ay) / ey;
+                    t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb));
+                } else any = any && ay >= y0 && ay <= y1;
+                if (fabsf(ez) > 1e-12f) {
+                    const float ta = (z0 - az) / ez, tb = (z1 - az) / ez;
+                    t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb));
+                } else any = any && az >= z0 && az <= z1;
+                // the intervals were computed with rounding: widen a little, still inside [0, 1]
+                t0 = fmaxf(t0 - 1e-3f, 0.f); t1 = fminf(t1 + 1e-3f, 1.f);
+                if (any && t0 <= t1) {
+                    const float xa = ax + t0 * ex, xb = ax + t1 * ex;
+                    int rlo = cell_coord(fminf(xa, xb) - pad, ox, inv, nx), rhi = cell_coord(fmaxf(xa, xb) + pad, ox, inv, nx);
+                    rlo = max(rlo, lox); rhi = min(rhi, hix);
+                    if (rlo <= rhi) {
+                        const int rowbase = (cz * ny + cy) * nx;
+                        beg = __ldg(p.g.cell_start + rowbase + rlo);
+                        end = __ldg(p.g.cell_start + rowbase + rhi + 1);
+                    }
+                }
             }
             const int nr = min(32, nrows - row0);
             for (int t = 0; t < nr; ++t) {
@@ -965,8 +992,8 @@ extern "C" int nf_render_forward(const nf_render_args* a, void* stream_) {
                    "nf_render_forward: NF_SEARCH_SWEEP needs n_particles <= %d", SCS_MAX_POINTS);
         p.search_mode = (a->search == NF_SEARCH_STREAM || a->n_particles > SCS_MAX_POINTS) ? 0 : 1;
         const char* span = getenv("NF_SUB_SPAN");
-        p.sub_span = span ? (float)atof(span) : 1.75f * a->radius;
-        p.sub_look = env_int("NF_SUB_LOOK", 64);
+        p.sub_span = span ? (float)atof(span) : 3.5f * a->radius;
+        p.sub_look = env_int("NF_SUB_LOOK", 96);
     }
     p.z_coarse = a->z_coarse; p.u_imp = a->u_importance;
     p.S0 = a->n_coarse; p.n_imp = NI; p.S1 = a->n_coarse + NI;
