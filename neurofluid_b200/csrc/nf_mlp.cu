@@ -811,6 +811,7 @@ static int launch_t(const KernelArgs& a, cudaStream_t st) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     NF_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, a));
+    count_launch();
     return NF_OK;
 }
 
