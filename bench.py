@@ -243,6 +243,7 @@ def main():
     import torch.distributed as dist
     import neurofluid_b200 as nb
     from neurofluid_b200 import _lib, scenes
+    torch.set_grad_enabled(False)      # evaluation, like the reference's eval loops (eval_e2e.py:64): kernels are forward-only
     from neurofluid_b200.distributed import shard_rows
 
     torch.cuda.set_device(local_rank)

@@ -114,3 +114,42 @@ def require_cuda(*tensors):
         if t is not None and not t.is_cuda:
             raise NFError("neurofluid_b200 runs on CUDA tensors only (sm_100a kernels); got a CPU tensor and there "
                           "is no CPU fallback")
+
+
+_forward_only_fn = None
+
+
+def _forward_only_function():
+    global _forward_only_fn
+    if _forward_only_fn is None:
+        import torch
+
+        class ForwardOnly(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, anchor, *outs):
+                return tuple(o.view_as(o) for o in outs)
+
+            @staticmethod
+            def backward(ctx, *grads):
+                raise NFError("backward through the sm_100a kernels is not implemented yet (forward / evaluation only; "
+                              "DESIGN.md section 8): run under torch.no_grad() or detach the result")
+
+        _forward_only_fn = ForwardOnly
+    return _forward_only_fn
+
+
+def forward_only(anchors, outputs):
+    """The kernels are forward-only this round.  When autograd is recording and something that
+    feeds the call requires grad, the floating-point outputs are tied to it through a node whose backward raises --
+    so `loss.backward()` fails with that message instead of an unrelated autograd error or, worse, no gradient."""
+    import torch
+    live = [t for t in anchors if isinstance(t, torch.Tensor) and t.requires_grad]
+    if not (torch.is_grad_enabled() and live):
+        return outputs
+    if isinstance(outputs, dict):
+        keys = [k for k, v in outputs.items() if v.is_floating_point()]
+        tied = _forward_only_function().apply(live[0], *[outputs[k] for k in keys])
+        out = dict(outputs)
+        out.update(zip(keys, tied))
+        return out
+    return tuple(_forward_only_function().apply(live[0], *outputs))

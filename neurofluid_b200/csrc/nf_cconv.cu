@@ -821,15 +821,15 @@ template <int CIN, int COUT_PAD>
 static int launch_conv(const ConvArgs& a, int dtype, cudaStream_t st) {
     using C = ConvCfg<CIN, COUT_PAD>;
     if (a.end <= a.begin) return NF_OK;
-    static bool configured = false;
-    if (!configured) {
-        NF_CUDA_OK(cudaFuncSetAttribute(k_cconv_tc<CIN, COUT_PAD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SM_TOTAL));
-        NF_CUDA_OK(cudaFuncSetAttribute(k_cconv_tc<CIN, COUT_PAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SM_TOTAL));
-        configured = true;
-    }
     const int grid = (a.end - a.begin + 127) / 128;
-    if (dtype == NF_DTYPE_BF16) k_cconv_tc<CIN, COUT_PAD, true><<<grid, CONV_THREADS, C::SM_TOTAL, st>>>(a);
-    else k_cconv_tc<CIN, COUT_PAD, false><<<grid, CONV_THREADS, C::SM_TOTAL, st>>>(a);
+    // the attribute is per device, not per process: set it on every launch instead of caching a flag
+    if (dtype == NF_DTYPE_BF16) {
+        NF_CUDA_OK(cudaFuncSetAttribute(k_cconv_tc<CIN, COUT_PAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SM_TOTAL));
+        k_cconv_tc<CIN, COUT_PAD, true><<<grid, CONV_THREADS, C::SM_TOTAL, st>>>(a);
+    } else {
+        NF_CUDA_OK(cudaFuncSetAttribute(k_cconv_tc<CIN, COUT_PAD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SM_TOTAL));
+        k_cconv_tc<CIN, COUT_PAD, false><<<grid, CONV_THREADS, C::SM_TOTAL, st>>>(a);
+    }
     NF_LAUNCH_OK();
     return NF_OK;
 }

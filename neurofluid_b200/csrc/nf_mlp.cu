@@ -792,12 +792,9 @@ bool pair_mode() {
 
 template <bool BF16, bool PAIR>
 static int launch_t(const KernelArgs& a, cudaStream_t st) {
-    static bool attr_set = false;
     auto* kern = k_nerf_mlp<BF16, PAIR>;
-    if (!attr_set) {
-        NF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-        attr_set = true;
-    }
+    // per device, not per process: set it on every launch (a few hundred ns) instead of caching a flag
+    NF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(num_sms() & ~1), 1, 1);
     cfg.blockDim = dim3(NUM_THREADS, 1, 1);

@@ -985,15 +985,28 @@ extern "C" int nf_render_forward(const nf_render_args* a, void* stream_) {
     p.K = a->K;
     p.use_mask = a->use_mask; p.white_bg = a->white_background; p.mode = a->mode;
     {
-        const int tune[3] = {env_int("NF_SOLO_MAX_OCC", 600), env_int("NF_PEEL_LANES", 4), env_int("NF_PEEL_FROM", 1536)};
-        p.solo_max_occ = tune[0]; p.peel_lanes = tune[1]; p.peel_from = tune[2];
+        // search tuning: compile-time defaults; the NF_* environment overrides exist for tests/gpu_tune.py and are
+        // read once per process unless NF_TUNE_LIVE is set
+        struct Tune { int solo_max_occ, peel_lanes, peel_from, sub_look; float sub_span_r; };
+        auto read = [] {
+            Tune t;
+            t.solo_max_occ = env_int("NF_SOLO_MAX_OCC", 600);
+            t.peel_lanes = env_int("NF_PEEL_LANES", 4);
+            t.peel_from = env_int("NF_PEEL_FROM", 1536);
+            t.sub_look = env_int("NF_SUB_LOOK", 96);
+            const char* span = getenv("NF_SUB_SPAN");
+            t.sub_span_r = span ? -(float)atof(span) : 3.5f;      // negative: absolute length, positive: multiples of r
+            return t;
+        };
+        static const bool live = getenv("NF_TUNE_LIVE") != nullptr;
+        static const Tune cached = read();
+        const Tune t = live ? read() : cached;
+        p.solo_max_occ = t.solo_max_occ; p.peel_lanes = t.peel_lanes; p.peel_from = t.peel_from; p.sub_look = t.sub_look;
+        p.sub_span = t.sub_span_r < 0.f ? -t.sub_span_r : t.sub_span_r * a->radius;
         NF_REQUIRE(a->search >= NF_SEARCH_AUTO && a->search <= NF_SEARCH_SWEEP, NF_E_INVALID, "nf_render_forward: search %d", a->search);
         NF_REQUIRE(a->search != NF_SEARCH_SWEEP || a->n_particles <= SCS_MAX_POINTS, NF_E_UNSUPPORTED,
                    "nf_render_forward: NF_SEARCH_SWEEP needs n_particles <= %d", SCS_MAX_POINTS);
         p.search_mode = (a->search == NF_SEARCH_STREAM || a->n_particles > SCS_MAX_POINTS) ? 0 : 1;
-        const char* span = getenv("NF_SUB_SPAN");
-        p.sub_span = span ? (float)atof(span) : 3.5f * a->radius;
-        p.sub_look = env_int("NF_SUB_LOOK", 96);
     }
     p.z_coarse = a->z_coarse; p.u_imp = a->u_importance;
     p.S0 = a->n_coarse; p.n_imp = NI; p.S1 = a->n_coarse + NI;

@@ -151,7 +151,7 @@ class RenderNet(nn.Module):
             check(lib().nf_render_forward(C.byref(a), st), "nf_render_forward")
         self.last_stats = stats       # device tensor; .sum(0) = [rows0, rows1, active0, active1]
         self._keep = (grid, particles, rays)
-        return out
+        return _lib.forward_only([physical_particles, *self.parameters()], out)
 
     # ------------------------------------------------------------------ reference API
     def forward(self, physical_particles, ro, rays, focal=None, c2w=None, use_disp=False, perturb=0, noise_std=0.,

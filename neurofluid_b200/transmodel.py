@@ -143,6 +143,7 @@ class ParticleNet(nn.Module):
     # ------------------------------------------------------------------ reference API
     def forward(self, pos, vel, box, box_feats, feats=None, fixed_radius_search_hash_table=None, debug=None):
         """models/transmodel.py:151-163.  `fixed_radius_search_hash_table` is accepted and ignored, as upstream."""
+        pos_in, vel_in = pos, vel
         pos, vel, box, box_feats, outs, ws = self._prepare(pos, vel, box, box_feats, feats)
         if debug is not None:
             debug["feats0"] = torch.empty((pos.shape[0], 96), device=pos.device)
@@ -150,7 +151,7 @@ class ParticleNet(nn.Module):
         check(lib().nf_transition_step(C.byref(a), stream_ptr()), "nf_transition_step")
         self.num_fluid_neighbors, self.pos_correction = outs[2], outs[3]
         self._keep = (pos, vel, box, box_feats)
-        return outs[0], outs[1], outs[2]
+        return _lib.forward_only([pos_in, vel_in, *self.parameters()], (outs[0], outs[1], outs[2]))
 
     step = forward      # BASELINE.json's wording: TransModel.step
 

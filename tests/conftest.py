@@ -10,6 +10,15 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+@pytest.fixture(autouse=True)
+def _evaluation_mode():
+    """The kernels are forward-only; like the reference's eval loops (eval_e2e.py:64, `with torch.no_grad()`), the
+    tests run without autograd.  The one test of the backward error enables it locally."""
+    import torch
+    with torch.no_grad():
+        yield
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
 

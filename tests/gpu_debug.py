@@ -6,6 +6,7 @@ import time
 
 import numpy as np
 import torch
+torch.set_grad_enabled(False)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

@@ -2,6 +2,7 @@
 optionally, a few transition steps; prints per-chunk row counts so an ncu capture of launch i can be matched to
 its rows.   python tests/gpu_profile_render.py [n_forwards] [n_transition_steps]"""
 import json, os, sys, torch
+torch.set_grad_enabled(False)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import neurofluid_b200 as nb
 from neurofluid_b200 import scenes

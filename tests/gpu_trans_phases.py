@@ -1,4 +1,5 @@
 import os, sys, time, torch, ctypes as C
+torch.set_grad_enabled(False)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import neurofluid_b200 as nb
 from neurofluid_b200 import scenes, _lib

@@ -1,8 +1,10 @@
 import os, sys, time, torch
+torch.set_grad_enabled(False)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import neurofluid_b200 as nb
 from neurofluid_b200 import scenes, _lib
 import ctypes
+os.environ["NF_TUNE_LIVE"] = "1"
 dev = torch.device("cuda:0")
 H = 800
 rays, focal, cw = scenes.camera_rays(H, H)

@@ -7,6 +7,7 @@ import os
 import sys
 
 import torch
+torch.set_grad_enabled(False)
 import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
