@@ -16,7 +16,9 @@
 //                      The fluid->fluid list is reused by conv0_fluid, conv1, conv2, conv3; the
 //                      fluid->box list by conv0_obstacle.  48-byte records, fixed stride per particle.
 //   k_layer0           conv0_obstacle + conv0_fluid + dense0_fluid (14k MAC/particle): fp32 on CUDA cores
-//   k_cconv_tc<CIN,COUT>  conv_l + dense_l (+ residual) for l = 1..3: per 128-particle tile, for each of the
+//   k_conv3_project/gather  conv3 + dense3 (64 -> 3): features projected through the 64 filter cells once per
+//                      particle, then 8 x 3 floats gathered per neighbour pair (fp32)
+//   k_cconv_tc<CIN,COUT>  conv_l + dense_l (+ residual) for l = 1, 2: per 128-particle tile, for each of the
 //                      16 (z,y) filter rows the (128 x 4*CIN) slab of the patch matrix is accumulated in
 //                      registers straight from the neighbour gather, written to shared memory as the fp16
 //                      A operand (UMMA K-major core-matrix layout) and contracted with the matching filter
@@ -737,6 +739,97 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_cconv_tc(const ConvArgs a) 
 }
 
 // ------------------------------------------------------------------------------------------------
+// conv3 + dense3 (64 -> 3).  With 3 output channels the contraction is cheaper the other way round:
+//   out_i = sum_j sum_c w_ijc K_c^T f_j  =  sum_j sum_c w_ijc g_j[c],   g_j[c] = K_c^T f_j  (3 values per cell)
+// so every particle's features are projected through all 64 filter cells once (k_conv3_project: N x 64 x 192 MAC,
+// fp32, weights in shared memory) and the neighbour pass gathers 8 x 3 floats per pair instead of building a
+// 128 x 256 patch slab per filter row for 3 useful output columns (k_conv3_gather: one warp per particle, one
+// lane per pair, fixed reduction tree -> deterministic).  fp32 end to end.
+// ------------------------------------------------------------------------------------------------
+constexpr int C3_IN = 64, C3_OUT = 3, C3_G = NCELL * C3_OUT;      // 192 projected values per particle
+
+template <bool BF16>
+__global__ void __launch_bounds__(C3_G) k_conv3_project(const void* __restrict__ x_in, int n, const float* __restrict__ kern,
+                                                       float* __restrict__ g) {
+    // kern: (64 cells, 64 in, 3 out) fp32 = the reference's conv3.kernel (4,4,4,64,3) flattened
+    extern __shared__ float sk[];                     // [in][cell*3 + out]: thread q reads sk[ch*192 + q], conflict-free
+    __shared__ float4 sx[C3_IN];                      // [in] x 4 particles of this pass
+    for (int k = threadIdx.x; k < NCELL * C3_IN * C3_OUT; k += blockDim.x) {
+        const int o = k % C3_OUT, ch = (k / C3_OUT) % C3_IN, cell = k / (C3_OUT * C3_IN);
+        sk[ch * C3_G + cell * C3_OUT + o] = __ldg(kern + k);
+    }
+    const int q = threadIdx.x;
+    for (int i0 = blockIdx.x * 4; i0 < n; i0 += gridDim.x * 4) {      // 4 particles per pass share every weight read
+        __syncthreads();
+        for (int k = threadIdx.x; k < 4 * C3_IN; k += blockDim.x) {
+            const int ii = i0 + (k & 3), ch = k >> 2;
+            float v = 0.f;
+            if (ii < n) {
+                if (BF16) v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x_in)[(size_t)ii * C3_IN + ch]);
+                else v = __half2float(reinterpret_cast<const __half*>(x_in)[(size_t)ii * C3_IN + ch]);
+            }
+            reinterpret_cast<float*>(sx)[k] = v;
+        }
+        __syncthreads();
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+        for (int ch = 0; ch < C3_IN; ++ch) {
+            const float w = sk[ch * C3_G + q];
+            const float4 x = sx[ch];
+            a0 += w * x.x; a1 += w * x.y; a2 += w * x.z; a3 += w * x.w;
+        }
+        if (i0 < n) g[(size_t)i0 * C3_G + q] = a0;
+        if (i0 + 1 < n) g[(size_t)(i0 + 1) * C3_G + q] = a1;
+        if (i0 + 2 < n) g[(size_t)(i0 + 2) * C3_G + q] = a2;
+        if (i0 + 3 < n) g[(size_t)(i0 + 3) * C3_G + q] = a3;
+    }
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(256) k_conv3_gather(const Pair* __restrict__ pairs, const int* __restrict__ cnt,
+                                                      const float* __restrict__ g, const void* __restrict__ x_in,
+                                                      const float* __restrict__ b_conv, const float* __restrict__ w_dense,
+                                                      const float* __restrict__ b_dense, int begin, int end,
+                                                      float* __restrict__ ans3 /*(N,16)*/) {
+    const int lane = threadIdx.x & 31;
+    const int i = begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (i >= end) return;
+    float acc[C3_OUT] = {0.f, 0.f, 0.f};
+    const int n = cnt[i];
+    const Pair* pr = pairs + (size_t)i * MAXNBR;
+    for (int t = lane; t < n; t += 32) {
+        const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(pr + t));
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(pr + t) + 1);
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(pr + t) + 2);
+        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const float* gj = g + (size_t)h0.x * C3_G;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const unsigned cell = ((c < 4 ? h0.y : h0.z) >> (8 * (c & 3))) & 0xffu;
+            const float* gc = gj + cell * C3_OUT;
+            acc[0] += w[c] * __ldg(gc); acc[1] += w[c] * __ldg(gc + 1); acc[2] += w[c] * __ldg(gc + 2);
+        }
+    }
+    // dense3 on the particle's own features: lane owns channels lane and lane + 32
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        const int ch = lane + 32 * m;
+        float x;
+        if (BF16) x = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x_in)[(size_t)i * C3_IN + ch]);
+        else x = __half2float(reinterpret_cast<const __half*>(x_in)[(size_t)i * C3_IN + ch]);
+#pragma unroll
+        for (int o = 0; o < C3_OUT; ++o) acc[o] += x * __ldg(w_dense + o * C3_IN + ch);
+    }
+#pragma unroll
+    for (int o = 0; o < C3_OUT; ++o) acc[o] = warp_sum(acc[o]);
+    if (lane < 16) {
+        float v = 0.f;
+        if (lane < C3_OUT) v = (lane == 0 ? acc[0] : (lane == 1 ? acc[1] : acc[2])) + __ldg(b_conv + lane) + __ldg(b_dense + lane);
+        ans3[(size_t)i * 16 + lane] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // weight packing: conv kernel (4,4,4,CIN,COUT) + dense (COUT,CIN) -> K-step slabs in UMMA order
 //   conv slab s=(z*4+y): column k = x*CIN + ch   <-  kernel[z][y][x][ch][cout]
 //   dense slab         : column k = ch           <-  dense_w[cout][ch]
@@ -777,7 +870,7 @@ __global__ void k_pack_conv(const float* __restrict__ kern, const float* __restr
 
 // packed layout of the whole ParticleNet: fp32 layer-0 tensors, then the three tensor-core layers
 struct PackedLayout {
-    size_t k_fluid, b_fluid, k_obst, b_obst, w_dense0, b_dense0, l1, l2, l3, total;
+    size_t k_fluid, b_fluid, k_obst, b_obst, w_dense0, b_dense0, l1, l2, k3, b3, w_dense3, b_dense3, total;
 };
 inline PackedLayout packed_layout() {
     PackedLayout L;
@@ -788,14 +881,15 @@ inline PackedLayout packed_layout() {
     L.w_dense0 = take(32 * 4 * 4); L.b_dense0 = take(32 * 4);
     L.l1 = take(ConvCfg<96, 64>::PACKED_BYTES);
     L.l2 = take(ConvCfg<64, 64>::PACKED_BYTES);
-    L.l3 = take(ConvCfg<64, 16>::PACKED_BYTES);
+    L.k3 = take(NCELL * 64 * 3 * 4); L.b3 = take(3 * 4);          // conv3 / dense3 stay fp32 (k_conv3_*)
+    L.w_dense3 = take(3 * 64 * 4); L.b_dense3 = take(3 * 4);
     L.total = o;
     return L;
 }
 
 struct WsLayout {
     size_t pos_new, vel_new, grid_f, grid_b, pairs_ff, cnt_ff, pairs_fb, cnt_fb, slab_j, slab_w, slab_off, ans0, x0, ans1, x1, ans2, x2, ans3,
-        flags, total;
+        g3, flags, total;
 };
 inline WsLayout ws_layout(int n, int m) {
     WsLayout L;
@@ -812,6 +906,7 @@ inline WsLayout ws_layout(int n, int m) {
     L.ans1 = take(N * 64 * 4); L.x1 = take(N * 64 * 2);
     L.ans2 = take(N * 64 * 4); L.x2 = take(N * 64 * 2);
     L.ans3 = take(N * 16 * 4);
+    L.g3 = take(N * C3_G * 4);
     L.flags = take(256);
     L.total = o;
     return L;
@@ -872,13 +967,10 @@ extern "C" int nf_transition_pack_weights(const float* const* p, int dtype, void
         else k_pack_conv<64, 64, false><<<(tot + 255) / 256, 256, 0, st>>>(p[10], p[11], p[12], p[13], 64, b + L.l2);
         NF_LAUNCH_OK();
     }
-    {
-        using C = ConvCfg<64, 16>;
-        const int tot = (16 * C::KSTEPS + C::KSTEPS_DENSE) * 2 * 16;
-        if (bf) k_pack_conv<64, 16, true><<<(tot + 255) / 256, 256, 0, st>>>(p[14], p[15], p[16], p[17], 3, b + L.l3);
-        else k_pack_conv<64, 16, false><<<(tot + 255) / 256, 256, 0, st>>>(p[14], p[15], p[16], p[17], 3, b + L.l3);
-        NF_LAUNCH_OK();
-    }
+    NF_CUDA_OK(cudaMemcpyAsync(b + L.k3, p[14], NCELL * 64 * 3 * 4, cudaMemcpyDeviceToDevice, st));
+    NF_CUDA_OK(cudaMemcpyAsync(b + L.b3, p[15], 3 * 4, cudaMemcpyDeviceToDevice, st));
+    NF_CUDA_OK(cudaMemcpyAsync(b + L.w_dense3, p[16], 3 * 64 * 4, cudaMemcpyDeviceToDevice, st));
+    NF_CUDA_OK(cudaMemcpyAsync(b + L.b_dense3, p[17], 3 * 4, cudaMemcpyDeviceToDevice, st));
     return NF_OK;
 }
 
@@ -980,10 +1072,27 @@ extern "C" int nf_transition_step(const nf_transition_args* a, void* stream_) {
         int rc = launch_conv<64, 64>(c, a->dtype, st);
         if (rc != NF_OK) return rc;
     }
-    if (all || a->phase == 3) {     // conv3 + dense3 : 64 -> 3
-        c.x_in = x2; c.w_packed = w + PL.l3; c.residual = nullptr; c.ld_res = 0; c.ans = ans3; c.x_out = nullptr; c.cout = 3;
-        int rc = launch_conv<64, 16>(c, a->dtype, st);
-        if (rc != NF_OK) return rc;
+    if (all || a->phase == 3) {     // conv3 + dense3 : 64 -> 3  (project every particle, then gather per neighbour)
+        float* g3 = (float*)(b + L.g3);
+        const bool bf = a->dtype == NF_DTYPE_BF16;
+        const size_t smem = (size_t)NCELL * 64 * 3 * sizeof(float);
+        const int pgrid = min((N + 3) / 4, 2 * num_sms());
+        if (bf) {
+            NF_CUDA_OK(cudaFuncSetAttribute(k_conv3_project<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_conv3_project<true><<<pgrid, C3_G, smem, st>>>(x2, N, (const float*)(w + PL.k3), g3);
+        } else {
+            NF_CUDA_OK(cudaFuncSetAttribute(k_conv3_project<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_conv3_project<false><<<pgrid, C3_G, smem, st>>>(x2, N, (const float*)(w + PL.k3), g3);
+        }
+        NF_LAUNCH_OK();
+        if (nshard > 0) {
+            const int blocks = (nshard + 7) / 8;
+            if (bf) k_conv3_gather<true><<<blocks, 256, 0, st>>>(pairs_ff, cnt_ff, g3, x2, (const float*)(w + PL.b3), (const float*)(w + PL.w_dense3),
+                                                                (const float*)(w + PL.b_dense3), begin, end, ans3);
+            else k_conv3_gather<false><<<blocks, 256, 0, st>>>(pairs_ff, cnt_ff, g3, x2, (const float*)(w + PL.b3), (const float*)(w + PL.w_dense3),
+                                                               (const float*)(w + PL.b_dense3), begin, end, ans3);
+            NF_LAUNCH_OK();
+        }
     }
     if ((all || a->phase == 4) && nshard > 0) {
         k_update<<<(3 * nshard + 255) / 256, 256, 0, st>>>(a->pos, pos_new, ans3, 16, begin, end, a->dt, a->pos_out,
