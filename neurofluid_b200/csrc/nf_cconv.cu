@@ -320,25 +320,56 @@ __global__ void __launch_bounds__(256) k_nbr_build(GridView g, const float* __re
         };
         int off = 0;
         if (nn <= 64) {        // the usual case: both 32-pair chunks stay in registers for all 16 rows
-            uint4 ha, hb;
-            float wa[8], wb[8];
-            load_pair(lane, ha, wa);
-            load_pair(32 + lane, hb, wb);
+            // A pair's 8 corners are 4 (z,y) combinations x 2 x-neighbours: reduce them once to
+            // {filter row, weight per x cell} x 4, so that the 16-row loop only compares and adds.
+            auto combos = [&](int t, int& j, unsigned& rows, float (&cx)[4][4]) {
+                uint4 h0;
+                float w[8];
+                load_pair(t, h0, w);
+                j = (int)h0.x;
+                rows = 0u;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const unsigned c0 = ((q < 2 ? h0.y : h0.z) >> (16 * (q & 1))) & 0xffu;          // corner 2q
+                    const unsigned c1 = ((q < 2 ? h0.y : h0.z) >> (16 * (q & 1) + 8)) & 0xffu;      // corner 2q + 1
+                    rows |= (t < nn ? (c0 >> 2) : 31u) << (8 * q);                                  // 31: no row
+#pragma unroll
+                    for (int xx = 0; xx < 4; ++xx)
+                        cx[q][xx] = ((int)(c0 & 3) == xx ? w[2 * q] : 0.f) + ((int)(c1 & 3) == xx ? w[2 * q + 1] : 0.f);
+                }
+            };
+            int ja, jb;
+            unsigned ra4, rb4;
+            float ca[4][4], cb[4][4];
+            combos(lane, ja, ra4, ca);
+            combos(32 + lane, jb, rb4, cb);
+            auto row_sum = [](unsigned rows, const float (&cx)[4][4], int sidx, float (&wx)[4]) {
+                bool rel = false;
+                wx[0] = wx[1] = wx[2] = wx[3] = 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if ((int)((rows >> (8 * q)) & 0xffu) == sidx) {
+                        rel = true;
+                        wx[0] += cx[q][0]; wx[1] += cx[q][1]; wx[2] += cx[q][2]; wx[3] += cx[q][3];
+                    }
+                }
+                return rel;
+            };
 #pragma unroll 1
             for (int sidx = 0; sidx < 16; ++sidx) {
                 float xa[4], xb[4];
-                const bool ra = row_part(ha, wa, sidx, xa), rb = row_part(hb, wb, sidx, xb);
+                const bool ra = row_sum(ra4, ca, sidx, xa), rb = row_sum(rb4, cb, sidx, xb);
                 const unsigned ma = __ballot_sync(NF_FULL, ra), mb = __ballot_sync(NF_FULL, rb);
                 if (lane == 0) doff[sidx] = (unsigned short)off;
                 if (ra) {
                     const int e = off + __popc(ma & lt);
-                    dj[e] = (int)ha.x;
+                    dj[e] = ja;
                     dw[e] = make_float4(xa[0], xa[1], xa[2], xa[3]);
                 }
                 off += __popc(ma);
                 if (rb) {
                     const int e = off + __popc(mb & lt);
-                    dj[e] = (int)hb.x;
+                    dj[e] = jb;
                     dw[e] = make_float4(xb[0], xb[1], xb[2], xb[3]);
                 }
                 off += __popc(mb);
