@@ -419,7 +419,7 @@ struct Layer0Args {
 };
 
 __global__ void __launch_bounds__(256) k_layer0(const Layer0Args a) {
-    __shared__ float sm_patch[8][NCELL * 4 + NCELL * 3];
+    __shared__ __align__(16) float sm_patch[8][NCELL * 4 + NCELL * 3];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int i = a.begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (i >= a.end) return;
@@ -466,9 +466,30 @@ __global__ void __launch_bounds__(256) k_layer0(const Layer0Args a) {
     }
     __syncwarp();
     // lane = output channel
-    float of = __ldg(a.b_fluid + lane), oo = __ldg(a.b_obst + lane);
-    for (int k = 0; k < NCELL * 4; ++k) of += pf[k] * __ldg(a.k_fluid + k * 32 + lane);
-    for (int k = 0; k < NCELL * 3; ++k) oo += po[k] * __ldg(a.k_obst + k * 32 + lane);
+    // four independent partial sums per output (a single chain of 256 dependent FMAs was latency-bound)
+    float of, oo;
+    {
+        float s0 = __ldg(a.b_fluid + lane), s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 4
+        for (int k = 0; k < NCELL * 4; k += 4) {
+            const float4 p4 = *reinterpret_cast<const float4*>(pf + k);
+            s0 += p4.x * __ldg(a.k_fluid + k * 32 + lane);
+            s1 += p4.y * __ldg(a.k_fluid + (k + 1) * 32 + lane);
+            s2 += p4.z * __ldg(a.k_fluid + (k + 2) * 32 + lane);
+            s3 += p4.w * __ldg(a.k_fluid + (k + 3) * 32 + lane);
+        }
+        of = (s0 + s1) + (s2 + s3);
+        s0 = __ldg(a.b_obst + lane); s1 = 0.f; s2 = 0.f; s3 = 0.f;
+#pragma unroll 4
+        for (int k = 0; k < NCELL * 3; k += 4) {
+            const float4 p4 = *reinterpret_cast<const float4*>(po + k);
+            s0 += p4.x * __ldg(a.k_obst + k * 32 + lane);
+            s1 += p4.y * __ldg(a.k_obst + (k + 1) * 32 + lane);
+            s2 += p4.z * __ldg(a.k_obst + (k + 2) * 32 + lane);
+            s3 += p4.w * __ldg(a.k_obst + (k + 3) * 32 + lane);
+        }
+        oo = (s0 + s1) + (s2 + s3);
+    }
     float od = __ldg(a.b_dense + lane) + __ldg(a.w_dense + lane * 4);
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) od += __ldg(a.vel_new + 3 * i + ch) * __ldg(a.w_dense + lane * 4 + 1 + ch);
