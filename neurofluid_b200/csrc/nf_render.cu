@@ -61,6 +61,7 @@ struct StageArgs {
     unsigned* act0;      // (R, NS0)
     int* base0;          // (R, NS0) first row of each 32-sample coarse step in rec0
     unsigned char* cnt0; // (R, S0) neighbour count of every coarse sample
+    unsigned char* miss; // (R) 1: the ray never comes within reach of the particle set (use_mask only)
     unsigned* act1;      // (R, NS1)
     float* z1;           // (R, S1)
     float* rec0; int* rowid0; float4* out0; int cap0;
@@ -597,6 +598,33 @@ __device__ __forceinline__ void load_ray(const float* rays, int ray, float (&o)[
 }
 
 // ------------------------------------------------------------------------------------------------
+// Rays that never come within reach of the particle set's bounding box (most of an image: the fluid covers a
+// fraction of it) need no search, no pdf and no merge: every sample has zero neighbours, so with use_mask every
+// output is known -- white / zero, counts zero -- and identical to what the general path computes (all weights
+// are exactly 0).  Stage Q0 decides it once per ray (slab test of the sampled depth range against the box grown
+// by the search reach, with margin) and the later stages follow the flag.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool ray_misses_points(const StageArgs& p, const float (&o)[3], const float (&d)[3], float z_lo,
+                                                  float z_hi) {
+    const GridHeader* h = p.g.hdr;
+    if (h->n == 0) return true;
+    const float pad = p.radius * 1.002f + 1e-3f;
+    float t0 = z_lo - 1e-3f, t1 = z_hi + 1e-3f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float lo = h->bmin[a] - pad, hi = h->bmax[a] + pad;
+        if (fabsf(d[a]) > 1e-9f) {
+            const float ta = (lo - o[a]) / d[a], tb = (hi - o[a]) / d[a];
+            t0 = fmaxf(t0, fminf(ta, tb) - 1e-3f);
+            t1 = fminf(t1, fmaxf(ta, tb) + 1e-3f);
+        } else if (o[a] < lo || o[a] > hi) {
+            return true;
+        }
+    }
+    return t0 > t1;
+}
+
+// ------------------------------------------------------------------------------------------------
 // stage Q0
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t q0_smem_per_warp(int fl, int K, int P) {
@@ -617,6 +645,16 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, FL == 1 ? 3 : 2) k_stage
     for (int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ray < p.n_rays; ray += nwarps) {
         float o[3], d[3];
         load_ray(p.rays, ray, o, d);
+        const bool miss = p.use_mask && ray_misses_points(p, o, d, sm_z[0], sm_z[p.S0 - 1]);
+        if (lane == 0) p.miss[ray] = miss ? 1 : 0;
+        if (miss) {
+            for (int s = lane; s < p.S0; s += 32) {
+                if (p.num_nn0) p.num_nn0[(size_t)ray * p.S0 + s] = 0;
+                p.cnt0[(size_t)ray * p.S0 + s] = 0;
+            }
+            if (lane < NS0) { p.act0[(size_t)ray * NS0 + lane] = 0u; p.base0[(size_t)ray * NS0 + lane] = 0; }
+            continue;
+        }
         ray_query_group<FL>(p, lane, o, d, sm_z, p.S0, p.rec0, p.rowid0, p.counters + 0, p.counters + 2, p.cap0, ray,
                         p.num_nn0, p.act0, NS0, qs, sel, scratch, nullptr);
     }
@@ -657,6 +695,19 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, FL == 1 ? 3 : 2) k_stage
     float* smp = cdf + NS0 * 32;         // importance samples
     QueryStats qs;
     for (int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ray < p.n_rays; ray += nwarps) {
+        if (p.miss[ray]) {          // nothing within reach anywhere along the ray: every output is known
+            if (lane == 0) {
+                const float bg = p.white_bg ? 1.f : 0.f;
+                if (p.rgb0) { p.rgb0[3 * (size_t)ray] = bg; p.rgb0[3 * (size_t)ray + 1] = bg; p.rgb0[3 * (size_t)ray + 2] = bg; }
+                if (p.depth0) p.depth0[ray] = 0.f;
+                if (p.opac0) p.opac0[ray] = 0.f;
+                if (p.mask0) p.mask0[ray] = 0.f;
+            }
+            if (p.num_nn1)
+                for (int s = lane; s < S1; s += 32) p.num_nn1[(size_t)ray * S1 + s] = 0;
+            if (lane < NS1) p.act1[(size_t)ray * NS1 + lane] = 0u;
+            continue;
+        }
         float o[3], d[3], z0[NS0], w0[NS0];
         float4 c0[NS0];
         load_ray(p.rays, ray, o, d);
@@ -794,6 +845,16 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_stage_fin(const StageA
     float* o_opac = FIRST ? p.opac0 : p.opac1;
     float* o_mask = FIRST ? p.mask0 : p.mask1;
     for (int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ray < p.n_rays; ray += nwarps) {
+        if (p.miss[ray]) {          // see ray_misses_points: merged depths were never written for this ray
+            if (lane == 0) {
+                const float bg = p.white_bg ? 1.f : 0.f;
+                if (o_rgb) { o_rgb[3 * (size_t)ray] = bg; o_rgb[3 * (size_t)ray + 1] = bg; o_rgb[3 * (size_t)ray + 2] = bg; }
+                if (o_depth) o_depth[ray] = 0.f;
+                if (o_opac) o_opac[ray] = 0.f;
+                if (o_mask) o_mask[ray] = 0.f;
+            }
+            continue;
+        }
         float o[3], d[3], z[NS], w[NS];
         float4 c[NS];
         load_ray(p.rays, ray, o, d);
@@ -825,7 +886,7 @@ static int env_int(const char* name, int dflt) {
 }
 
 struct WsLayout {
-    size_t counters, act0, act1, base0, cnt0, z1, rec0, rowid0, out0, rec1, rowid1, out1, total;
+    size_t counters, act0, act1, base0, cnt0, miss, z1, rec0, rowid0, out0, rec1, rowid1, out1, total;
     int cap0, cap1, ns0, ns1;
 };
 
@@ -851,6 +912,7 @@ static WsLayout ws_layout(int R, int S0, int NI) {
     L.act1 = take(sizeof(unsigned) * (size_t)R * 8);
     L.base0 = take(sizeof(int) * (size_t)R * 4);
     L.cnt0 = take((size_t)R * S0);
+    L.miss = take((size_t)R);
     L.z1 = take(sizeof(float) * (size_t)R * S1);
     L.rec0 = take(sizeof(float) * 16 * (size_t)L.cap0);
     L.rowid0 = take(sizeof(int) * (size_t)L.cap0);
@@ -1018,7 +1080,7 @@ extern "C" int nf_render_forward(const nf_render_args* a, void* stream_) {
     p.num_nn1 = (long long*)a->num_nn1;
     p.counters = (int*)(b + L.counters);
     p.act0 = (unsigned*)(b + L.act0); p.act1 = (unsigned*)(b + L.act1);
-    p.base0 = (int*)(b + L.base0); p.cnt0 = (unsigned char*)(b + L.cnt0);
+    p.base0 = (int*)(b + L.base0); p.cnt0 = (unsigned char*)(b + L.cnt0); p.miss = (unsigned char*)(b + L.miss);
     p.z1 = (float*)(b + L.z1);
     p.rec0 = (float*)(b + L.rec0); p.rowid0 = (int*)(b + L.rowid0); p.out0 = (float4*)(b + L.out0); p.cap0 = L.cap0;
     p.rec1 = (float*)(b + L.rec1); p.rowid1 = (int*)(b + L.rowid1); p.out1 = (float4*)(b + L.out1); p.cap1 = L.cap1;
