@@ -198,6 +198,9 @@ typedef struct nf_transition_args {
        layer; rows outside the shard must be supplied by the caller between layers (see
        neurofluid_b200/distributed.py).  Single GPU: 0, n_fluid. */
     int32_t shard_begin, shard_end;
+    const void* box_grid_ws; /* optional: nf_grid_build(box, n_box, 1.002 * filter_extent / 2) done once by the caller
+                                for a static container (the role of the reference's fixed_radius_search_hash_table
+                                argument); NULL: built inside every step */
     int32_t* overflow_out; /* optional device int32[2]: += number of particles of this call whose fluid / box neighbour
                               list exceeded the 128 slots and was truncated (the reference has no cap): callers that
                               care poll it -- results are only reference-exact while it stays 0 */

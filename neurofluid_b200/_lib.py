@@ -41,7 +41,7 @@ class TransitionArgs(C.Structure):
         ("pos_out", _vp), ("vel_out", _vp), ("nnbr_out", _vp),
         ("feats0_out", _vp), ("delta_out", _vp),
         ("workspace", _vp), ("workspace_bytes", _sz),
-        ("shard_begin", _i32), ("shard_end", _i32), ("overflow_out", _vp), ("phase", _i32),
+        ("shard_begin", _i32), ("shard_end", _i32), ("box_grid_ws", _vp), ("overflow_out", _vp), ("phase", _i32),
     ]
 
 

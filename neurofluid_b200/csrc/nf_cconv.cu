@@ -1084,14 +1084,16 @@ extern "C" int nf_transition_step(const nf_transition_args* a, void* stream_) {
         NF_LAUNCH_OK();
         int rc = nf_grid_build(pos_new, N, 1.002f * radius, b + L.grid_f, grid_layout(N).total, stream_);
         if (rc != NF_OK) return rc;
-        rc = nf_grid_build(a->box, M, 1.002f * radius, b + L.grid_b, grid_layout(M).total, stream_);
-        if (rc != NF_OK) return rc;
+        if (!a->box_grid_ws) {
+            rc = nf_grid_build(a->box, M, 1.002f * radius, b + L.grid_b, grid_layout(M).total, stream_);
+            if (rc != NF_OK) return rc;
+        }
         if (nshard > 0) {
             const int blocks = (nshard + 7) / 8;
             k_nbr_build<<<blocks, 256, 0, st>>>(grid_view(b + L.grid_f, N), pos_new, begin, end, radius, 1, 1, pairs_ff,
                                                cnt_ff, a->nnbr_out, flags, slab_j, slab_w, slab_off);
             NF_LAUNCH_OK();
-            k_nbr_build<<<blocks, 256, 0, st>>>(grid_view(b + L.grid_b, M), pos_new, begin, end, radius, 1, 1, pairs_fb,
+            k_nbr_build<<<blocks, 256, 0, st>>>(grid_view(a->box_grid_ws ? a->box_grid_ws : b + L.grid_b, M), pos_new, begin, end, radius, 1, 1, pairs_fb,
                                                cnt_fb, nullptr, flags + 1, nullptr, nullptr, nullptr);
             NF_LAUNCH_OK();
             if (a->overflow_out) {

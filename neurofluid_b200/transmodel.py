@@ -111,10 +111,23 @@ class ParticleNet(nn.Module):
         a.delta_out = ptr(outs[3])
         a.workspace, a.workspace_bytes = ptr(ws), ws.numel()
         a.shard_begin, a.shard_end, a.phase = int(shard[0]), int(shard[1]), int(phase)
+        a.box_grid_ws = ptr(self._box_grid(box).ws)
         if self._overflow is None or self._overflow.device != pos.device:
             self._overflow = torch.zeros(2, dtype=torch.int32, device=pos.device)
         a.overflow_out = ptr(self._overflow)
         return a
+
+    def _box_grid(self, box):
+        """Cell-sorted grid of the container points, rebuilt only when the tensor changes (the container is static in
+        every reference scene; Open3D offers the same reuse through `fixed_radius_search_hash_table`)."""
+        from .ops import CELL_SCALE, Grid
+        key = (box.data_ptr(), box._version, tuple(box.shape), str(box.device), float(self.filter_extent))
+        hit = getattr(self, "_box_grid_cache", None)
+        if hit is None or hit[0] != key:
+            import numpy as np
+            cell = float(np.float32(CELL_SCALE) * (np.float32(0.5) * np.float32(self.filter_extent)))   # as nf_transition_step
+            self._box_grid_cache = (key, Grid(box, cell), box)
+        return self._box_grid_cache[1]
 
     def check_neighbor_overflow(self):
         """The kernels keep at most 128 fluid and 128 box neighbours per particle (the reference has no cap).  Returns
