@@ -12,13 +12,15 @@
 //
 // One warp owns one ray; inside a ray, sample s lives in lane s%32 of 32-sample step s/32.
 //
-// stage Q0 : coarse depths -> sample positions -> first-K ball query (group scan, see ray_query_group) ->
-//            num_nn, "all K slots valid" bitmask, and one 64-byte geometry record per evaluated sample
-//            appended to a compact list (rows are handed out per 32-sample step: one atomic, no holes).
+// stage Q0 : coarse depths -> sample positions -> first-K ball query (search_scs / search_stream, see
+//            ray_query_group) -> num_nn, "all K slots valid" bitmask, and one 64-byte geometry record per evaluated
+//            sample appended to a compact list (rows are handed out per 32-sample step: one atomic, no holes).
+//            Rays that never come within reach of the particle set are flagged here and only written later on.
 // [MLP]    : nf_mlp.cu over the compact list -> (r,g,b,sigma) scattered to a dense per-sample array.
 // stage MID: alpha-composite the coarse samples (warp scans), emit rgb0/depth0/opacity0/mask_0, build
 //            the piecewise-constant pdf, draw the importance samples by inverse CDF, merge with the
-//            coarse depths (rank merge in shared memory), then run the ball query for the merged samples.
+//            coarse depths (rank merge in shared memory), then run the ball query for the merged samples (the
+//            coarse ones among them reuse stage Q0's records and counts).
 // [MLP]    : fine network.
 // stage FIN: alpha-composite the fine samples -> rgb1/depth1/opacity1/mask_1.
 #include <stdlib.h>
