@@ -600,9 +600,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_cconv_tc(const ConvArgs a) 
         // ============================================================ workers: slab construction
         // warp = 8 particles (rows of the tile), lane = channels {lane, lane+32, ...}.  For filter row s and
         // particle r the slab list gives the neighbours that touch the row, already reduced to {j, weight per
-        // x cell}: lanes fetch the entries in parallel (one coalesced load), broadcast them by shuffle and
-        // gather 8 neighbour feature rows at a time.  The entries of the NEXT (s, r) unit are fetched before
-        // the current unit's gathers are consumed, so two dependent L2 round trips per unit overlap.
+        // x cell}: lanes fetch the entries in parallel (one coalesced load, issued two units ahead), broadcast them
+        // by shuffle and gather 8 neighbour feature rows at a time.
         const int rbase = warp * ROWS_PER_WARP;
         // row starts of this warp's 8 slab lists: smem [r][32] u16 (17 used)
         unsigned short* offs = reinterpret_cast<unsigned short*>(smem + C::SM_OFFS) + warp * ROWS_PER_WARP * 32;
@@ -642,11 +641,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_cconv_tc(const ConvArgs a) 
             if (BF16) return __uint_as_float((uint32_t)v << 16);
             return __half2float(*reinterpret_cast<const __half*>(&v));
         };
-        // first PB entries of a unit: their feature rows are requested one whole unit before they are consumed
-        // (software pipeline over units, on top of the two-units-ahead entry prefetch); entries beyond PB (rare)
-        // are gathered in place.  Lanes >= ne hold j = 0, w = 0, so every batch runs unconditionally: gathers
-        // beyond the list read row 0 (an L1 hit) and add nothing.
-        constexpr int PB = THIRD ? 12 : 16;
+        constexpr int GB = 8;                    // neighbour rows gathered per round trip (4 .. 16 measured alike)
+        // Lanes >= ne hold j = 0, w = 0, so every batch of GB gathers runs unconditionally: gathers beyond the list
+        // read row 0 (an L1 hit) and add nothing.  The batch loop is deliberately rolled: with the 16-deep, software-
+        // pipelined variant the hot loop outgrew the instruction cache (13 % no-instruction stalls) and was slower.
         auto load_feats = [&](auto nb, int ej, int u0, uint32_t* fp, unsigned short* fs) {
 #pragma unroll
             for (int u = 0; u < decltype(nb)::value; ++u) {
@@ -671,16 +669,11 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_cconv_tc(const ConvArgs a) 
                 }
             }
         };
-        using PBc = std::integral_constant<int, PB>;
-        using B8 = std::integral_constant<int, 8>;
-        uint32_t fpc[PB], fpn[PB];
-        unsigned short fsc[PB], fsn[PB];
-        // prologue: unit 0's entries become "current", its features are requested now
+        // prologue: unit 0's entries become "current"
         int ne_c = ne_a, ej_c = ej_a;
         float4 ew_c = ew_a;
         ne_a = ne_b; ej_a = ej_b; ew_a = ew_b;
         fetch_entries(2, ne_b, ej_b, ew_b);
-        load_feats(PBc{}, ej_c, 0, fpc, fsc);
 #pragma unroll 1
         for (int unit = 0; unit < 17 * ROWS_PER_WARP; ++unit) {
             {
@@ -691,12 +684,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_cconv_tc(const ConvArgs a) 
 #pragma unroll
                 for (int x = 0; x < 4; ++x) acc[x][0] = acc[x][1] = acc[x][2] = 0.f;
                 if (s < 16) {
-                    // request the next unit's first PB feature rows, then consume this unit's
-                    load_feats(PBc{}, ej_a, 0, fpn, fsn);
-                    fma_feats(PBc{}, ew_c, 0, fpc, fsc, acc);
-                    if (ne_c > PB) {                  // rare tail: gathered in place, 8 at a time
+                    // this unit's entries were fetched two units ago; gather and accumulate 8 neighbour rows per round
+                    // (rolled: the hot loop stays small enough for the instruction cache)
+                    {
                         int ej = ej_c;
                         float4 ew = ew_c;
+#pragma unroll 1
                         for (int e0 = 0; e0 < ne_c; e0 += 32) {
                             if (e0 > 0) {
                                 const size_t base = (size_t)row * SLABCAP + offs[r * 32 + s] + e0 + lane;
@@ -707,20 +700,19 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_cconv_tc(const ConvArgs a) 
                                 }
                             }
                             const int cnt = min(32, ne_c - e0);
-                            for (int u0 = (e0 == 0 ? PB : 0); u0 < cnt; u0 += 8) {
-                                uint32_t fp[8];
-                                unsigned short fs[8];
-                                load_feats(B8{}, ej, u0, fp, fs);
-                                fma_feats(B8{}, ew, u0, fp, fs, acc);
+#pragma unroll 1
+                            for (int u0 = 0; u0 < cnt; u0 += GB) {
+                                uint32_t fp[GB];
+                                unsigned short fs[GB];
+                                load_feats(std::integral_constant<int, GB>{}, ej, u0, fp, fs);
+                                fma_feats(std::integral_constant<int, GB>{}, ew, u0, fp, fs, acc);
                             }
                         }
                     }
-                    // rotate the pipeline: next -> current, prefetch entries three units ahead
+                    // rotate: next -> current, prefetch entries three units ahead
                     ne_c = ne_a; ej_c = ej_a; ew_c = ew_a;
                     ne_a = ne_b; ej_a = ej_b; ew_a = ew_b;
                     fetch_entries(unit + 3, ne_b, ej_b, ew_b);
-#pragma unroll
-                    for (int u = 0; u < PB; ++u) { fpc[u] = fpn[u]; fsc[u] = fsn[u]; }
                 } else if (row < a.end) {
                     // dense branch: the particle's own (ReLU'd) features, K = CIN
                     cvt2(__ldg(xin32 + (((size_t)row * CIN) >> 1) + lane), acc[0][0], acc[0][1]);
