@@ -226,7 +226,7 @@ __device__ __forceinline__ int search_stream(const StageArgs& p, int lane, float
 // ------------------------------------------------------------------------------------------------
 constexpr int SCS_MAX_POINTS = 65536;
 constexpr int SCS_BLOCK = 128;                  // candidates per sweep (4 per lane)
-constexpr int SCS_RING = 1024 + 2 * SCS_BLOCK;  // left-over (< block) + one 1024-index batch + read slack
+constexpr int SCS_RING = 1024 + 2 * SCS_BLOCK;  // sorted candidate list: un-swept rest (< block) + one 1024-index batch + read slack
 
 __host__ __device__ inline size_t scs_smem_bytes(int P) {
     return (size_t)((P + 1023) / 1024) * 128 + SCS_RING * sizeof(unsigned short);
@@ -234,7 +234,7 @@ __host__ __device__ inline size_t scs_smem_bytes(int P) {
 
 __device__ __forceinline__ int search_scs(const StageArgs& p, int lane, const float (&o)[3], const float (&d)[3],
                                           float zv, float qx, float qy, float qz, bool search, float& gz0, float& gz1,
-                                          const float* zs, int S, int s0 /*sample index of lane 0*/,
+                                          int& lst_len, int& lst_word, const float* zs, int S, int s0 /*sample index of lane 0*/,
                                           QueryStats& qs, unsigned* ibm, int* sel) {
     const GridHeader* h = p.g.hdr;
     const int K = p.K;
@@ -342,7 +342,6 @@ __device__ __forceinline__ int search_scs(const StageArgs& p, int lane, const fl
         // ---- 2 + 3. walk the bitmap in index order; sweep the unfinished samples over blocks of <= 128
         //      candidates (4 per lane, positions in registers): per sample one broadcast, four distance tests
         unsigned pend = sub;
-        int tail = 0;
         auto sweep = [&](int head, int navail) {
             float4 c[SCS_BLOCK / 32];
             int id[SCS_BLOCK / 32];
@@ -375,8 +374,24 @@ __device__ __forceinline__ int search_scs(const StageArgs& p, int lane, const fl
                 if (n >= K) pend &= ~(1u << s);
             }
         };
-        for (int w0 = 0; w0 < nwords && pend; w0 += 32) {
-            unsigned w = ibm[w0 + lane];
+        // The sorted candidate list is kept in `ring` from candidate 0 on and survives to the next sub-group that
+        // uses the same gather (lst_len candidates, bitmap walked up to word lst_word): a cluster of importance
+        // samples spread over several 32-sample steps walks the bitmap once.  When the list would outgrow the ring
+        // its already-swept prefix is dropped (lst_word < 0 from then on: the next sub-group starts over).
+        if (fresh || lst_word < 0) { lst_len = 0; lst_word = 0; }
+        int pos = 0;                      // sweep cursor of this sub-group
+        int wnext = lst_word;
+        bool dropped = false;
+        while (pend) {
+            const int avail = lst_len - pos;
+            if (avail >= SCS_BLOCK || (avail > 0 && wnext >= nwords)) {
+                const int nb = min(avail, SCS_BLOCK);
+                sweep(pos, nb);
+                pos += nb;
+                continue;
+            }
+            if (wnext >= nwords) break;
+            unsigned w = ibm[wnext + lane];
             const int c = __popc(w);
             int incl = c;
 #pragma unroll
@@ -385,35 +400,32 @@ __device__ __forceinline__ int search_scs(const StageArgs& p, int lane, const fl
                 if (lane >= off) incl += t;
             }
             const int tot = __shfl_sync(NF_FULL, incl, 31);
+            const int base = (wnext + lane) << 5;
+            wnext += 32;
             if (!tot) continue;
-            int pos = tail + incl - c;
-            const int base = (w0 + lane) << 5;
+            if (lst_len + tot > SCS_RING - SCS_BLOCK) {
+                // no room: keep only the < SCS_BLOCK candidates not swept yet (read all, then write: ranges may overlap)
+                unsigned short v[SCS_BLOCK / 32];
+#pragma unroll
+                for (int u = 0; u < SCS_BLOCK / 32; ++u) v[u] = ring[pos + 32 * u + lane];
+                __syncwarp();
+#pragma unroll
+                for (int u = 0; u < SCS_BLOCK / 32; ++u)
+                    if (32 * u + lane < avail) ring[32 * u + lane] = v[u];
+                lst_len = avail;
+                pos = 0;
+                dropped = true;
+                __syncwarp();
+            }
+            int wpos = lst_len + incl - c;
             while (w) {
-                ring[pos++] = (unsigned short)(base + __ffs(w) - 1);
+                ring[wpos++] = (unsigned short)(base + __ffs(w) - 1);
                 w &= w - 1;
             }
-            tail += tot;
-            if (tail < SCS_BLOCK) continue;
-            __syncwarp();
-            int head = 0;
-            while (tail - head >= SCS_BLOCK && pend) {
-                sweep(head, SCS_BLOCK);
-                head += SCS_BLOCK;
-            }
-            // move the < SCS_BLOCK left-over candidates to the front (read all, then write: ranges may overlap)
-            const int left = tail - head;
-            unsigned short v[SCS_BLOCK / 32];
-#pragma unroll
-            for (int u = 0; u < SCS_BLOCK / 32; ++u) v[u] = ring[head + 32 * u + lane];
-            __syncwarp();
-#pragma unroll
-            for (int u = 0; u < SCS_BLOCK / 32; ++u)
-                if (32 * u + lane < left) ring[32 * u + lane] = v[u];
-            tail = left;
+            lst_len += tot;
             __syncwarp();
         }
-        __syncwarp();
-        if (pend && tail > 0) sweep(0, tail);       // tail < SCS_BLOCK here
+        lst_word = dropped ? -1 : wnext;
         __syncwarp();
     }
     return cnt;
@@ -451,6 +463,7 @@ __device__ __forceinline__ void ray_query_group(const StageArgs& p, int lane, co
     const int KP = sel_stride(K);
     const float radius = p.radius;
     float gz0 = 1.f, gz1 = 0.f;      // sweep: depth interval whose candidates the index bitmap currently holds
+    int lst_len = 0, lst_word = -1;  // sweep: sorted candidate list kept across sub-groups of one gather
     const unsigned lt = (1u << lane) - 1u;
     int n_active = 0;
     const int sample_base = ray * S;
@@ -477,7 +490,7 @@ __device__ __forceinline__ void ray_query_group(const StageArgs& p, int lane, co
             continue;
         }
         int cnt;
-        if constexpr (FL == 1) cnt = search_scs(p, lane, o, d, zv, qx, qy, qz, search, gz0, gz1, zs, S, slot * 32, qs, scratch, sel);
+        if constexpr (FL == 1) cnt = search_scs(p, lane, o, d, zv, qx, qy, qz, search, gz0, gz1, lst_len, lst_word, zs, S, slot * 32, qs, scratch, sel);
         else cnt = search_stream(p, lane, qx, qy, qz, search, occ, qs, scratch, reinterpret_cast<int*>(scratch + BM_WORDS), sel);
         // ---- per-lane local geometry over the selected neighbours (ascending index, like the reference);
         //      one pass: var = (sum v^2 - 2 mean sum v + n mean^2) / n  ==  sum (v - mean)^2 / n
