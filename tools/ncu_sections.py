@@ -22,7 +22,7 @@ src = open(os.path.join(ROOT, "neurofluid_b200/csrc/nf_render.cu")).read().split
 def find(t):
     return next(i + 1 for i, l in enumerate(src) if t in l)
 marks = sorted([("search_stream", find("int search_stream(")), ("scs_head", find("int search_scs(")), ("scs_gather", find("// ---- 1. gather")),
-         ("scs_sweep", find("// ---- 2 + 3. walk")), ("scs_enumerate", find("for (int w0 = 0; w0 < nwords && pend")),
+         ("scs_sweep", find("// ---- 2 + 3. walk")), ("scs_enumerate", find("if (fresh || lst_word < 0) { lst_len = 0; lst_word = 0; }")),
          ("group_head", find("void ray_query_group(")), ("geometry", find("// ---- per-lane local geometry")),
          ("record", find("const bool full = in &&")), ("composite", find("void ray_composite(")), ("q0", find("// stage Q0")),
          ("mid_head", find("// stage MID")), ("pdf", find("// ---------------- sample_pdf")), ("invcdf", find("// inverse CDF")),
