@@ -104,12 +104,23 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU legs set their thread counts explicitly (torch's
+    intra-op pool and the OpenMP team of the compiled oracle operators) to every core of the box."""
+    from oracle import third_party_ops as tpo
+    n = os.cpu_count() or 1
+    torch.set_num_threads(n)
+    tpo.set_default_threads(n)
+    return n
+
+
 def cpu_reference_rays_per_sec(n_rays, repeats=1):
     """The reference's CPU path (oracle port of models/renderer.py on the third-party-op restatements)
     on the host cores, on a strided sample of the same workload.  Checker/baseline only."""
     from oracle import renderer as orender
     from oracle import third_party_ops as tpo
     from neurofluid_b200 import scenes
+    use_all_host_threads()
     rays, focal, cw, particles, cfg, sd = workload()
     sel = torch.arange(0, H * W, (H * W) // n_rays)[:n_rays]
     r = rays[sel].contiguous()
@@ -118,7 +129,7 @@ def cpu_reference_rays_per_sec(n_rays, repeats=1):
         t0 = time.perf_counter()
         orender.render_forward(sd, cfg, scenes.NEAR, scenes.FAR, particles, cw[:, 3], r)
         best = min(best, time.perf_counter() - t0)
-    cores = max(torch.get_num_threads(), tpo.max_threads())
+    cores = min(torch.get_num_threads(), tpo.max_threads())     # both pools are set to the host's core count
     return n_rays / best, cores, f"{n_rays} rays strided over the {H}x{W} image (same scene, weights and sample counts)"
 
 
@@ -134,12 +145,41 @@ def transition_workload():
 def cpu_reference_particle_steps_per_sec():
     from oracle import transition as otrans
     from oracle import third_party_ops as tpo
+    use_all_host_threads()
     pos, vel, box, box_n, sd = transition_workload()
     t0 = time.perf_counter()
     otrans.particle_step(sd, pos, vel, box, box_n)
     dt = time.perf_counter() - t0
-    return {"value": pos.shape[0] / dt, "unit": "particle-steps/s", "cores": max(torch.get_num_threads(), tpo.max_threads()),
+    return {"value": pos.shape[0] / dt, "unit": "particle-steps/s", "cores": min(torch.get_num_threads(), tpo.max_threads()),
             "kind": "port", "sample": f"1 full step, {pos.shape[0]} particles + {box.shape[0]} box points"}
+
+
+def transition_drift(dev, steps=50):
+    """Teacher-forced and free-running error of the rollout against the CPU oracle, BASELINE
+    config[2] size: every step the GPU runs once from the oracle's state (teacher-forced: correction error of one
+    step) and once from its own (free-running: accumulated position error)."""
+    import neurofluid_b200 as nb
+    from oracle import transition as otrans
+    use_all_host_threads()
+    pos, vel, box, box_n, sd = transition_workload()
+    net = nb.ParticleNet(gravity=(0.0, 0.0, -9.81)); net.load_state_dict(sd); net = net.to(dev)
+    rel = lambda a, b: float(torch.norm(a.double() - b.double()) / torch.norm(b.double()).clamp_min(1e-30))
+    box_d, boxn_d = box.to(dev), box_n.to(dev)
+    gp, gv, op, ov = pos.to(dev), vel.to(dev), pos, vel
+    tf_corr, tf_pos, fr = [], [], []
+    for _ in range(steps):
+        tp, _, _ = net(op.to(dev), ov.to(dev), box_d, boxn_d)
+        tcorr = net.pos_correction.cpu()
+        op2, ov2, _, dbg = otrans.particle_step(sd, op, ov, box, box_n, debug=True)
+        tf_corr.append(rel(tcorr, dbg["feats"][-1] / 128)); tf_pos.append(rel(tp.cpu(), op2))
+        gp, gv, _ = net(gp, gv, box_d, boxn_d)
+        op, ov = op2, ov2
+        fr.append(rel(gp.cpu(), op))
+    dev_abs = float((gp.cpu() - op).norm(dim=1).mean())
+    return {"steps": steps, "teacher_forced_correction_rel_l2_max": max(tf_corr), "teacher_forced_position_rel_l2_max": max(tf_pos),
+            "free_running_position_rel_l2": {"step1": fr[0], "step10": fr[min(9, steps - 1)], f"step{steps}": fr[-1]},
+            "free_running_mean_abs_deviation_final": dev_abs,
+            "note": "positions in a 2 x 2 x 3.5 box; particle spacing 0.05"}
 
 
 def bench_transition(dev, world, rank, args, timed, pk):
@@ -174,9 +214,10 @@ def bench_transition(dev, world, rank, args, timed, pk):
                          "note": "41 GFLOP per step: launch/latency-bound by construction (SURVEY 8d)"}}
 
 
-def bench_end2end(dev, world, rank, timed):
+def bench_end2end(dev, world, rank, timed, transition="replicated"):
     """BASELINE config[3]-shaped end-to-end rollout (eval_e2e.py:58-120): 60 frames of transition step + one
-    400x400 view, 23^3 = 12,167 particles, transition replicated, rays sharded by image row over the ranks."""
+    400x400 view, 23^3 = 12,167 particles, rays sharded by image row over the ranks; the transition step replicated on
+    every rank or particle-block sharded with NCCL all-gathers (north_star's layout).  Median of 3 repetitions."""
     import neurofluid_b200 as nb
     from neurofluid_b200 import pipeline, scenes
     n, Hh, frames = 23, 400, 60
@@ -191,19 +232,76 @@ def bench_end2end(dev, world, rank, timed):
     # the camera of eval_renderer.py looks at the origin; the block rests on the box floor: aim it there
     cw = cw.clone(); cw[2, 3] += -1 + 0.03 + half
     cams = [(cw, focal)]
-    pipeline.rollout_and_render(tn, rn, pos, vel, box, box_n, cams, Hh, Hh, 3)          # warm-up
-    ms = timed(lambda: pipeline.rollout_and_render(tn, rn, pos, vel, box, box_n, cams, Hh, Hh, frames), 1)
+    run = lambda k: pipeline.rollout_and_render(tn, rn, pos, vel, box, box_n, cams, Hh, Hh, k, transition=transition)
+    run(3)                                                                              # warm-up
+    reps = sorted(timed(lambda: run(frames), 1) for _ in range(3))
+    ms = reps[1]
     return {"metric": "frames_per_sec_end2end_400x400", "value": frames / (ms * 1e-3), "unit": "frames/s", "frames": frames,
+            "repetitions_ms": reps, "transition": transition,
             "ms_per_frame": ms / frames, "rays_per_sec": frames * Hh * Hh / (ms * 1e-3), "n_particles": n ** 3,
             "n_box": int(box.shape[0]), "image": f"{Hh}x{Hh}", "views_per_frame": 1, "scaling": "strong",
-            "parallelism": f"transition replicated, rays sharded by image row over {world} GPU(s)",
+            "parallelism": f"transition {transition}, rays sharded by image row over {world} GPU(s)",
             "note": "BASELINE config[3] shape (honeycone stand-in): transition step + device ray generation + render per frame"}
+
+
+def bench_config4(dev, world, rank, timed):
+    """BASELINE config[4] size: 37^3 = 50,653 particles, 800x800, rays sharded by image row over the ranks."""
+    import neurofluid_b200 as nb
+    from neurofluid_b200 import scenes
+    from neurofluid_b200.distributed import shard_rows
+    rays, focal, cw = scenes.camera_rays(H, W)
+    particles = torch.from_numpy(scenes.lattice_particles(37, 0)).to(dev)
+    net = nb.RenderNet(scenes.render_cfg(), scenes.NEAR, scenes.FAR); net.load_state_dict(scenes.init_render_state(0, 5.0)); net = net.to(dev)
+    mine = shard_rows(rays.view(H, W, 6), rank, world).reshape(-1, 6).contiguous().to(dev)
+    ro = cw[:, 3].to(dev)
+    L = __import__("neurofluid_b200")._lib.lib()
+    for _ in range(2):
+        net(particles, ro, mine, focal, cw)
+    L.nf_profile_enable(1)
+    ms = timed(lambda: net(particles, ro, mine, focal, cw), 3)
+    stage_ms = (ctypes.c_double * 5)(); ncalls = ctypes.c_int(0)
+    L.nf_profile_read(stage_ms, ctypes.byref(ncalls)); L.nf_profile_enable(0)
+    st = [float(x) / 3 for x in stage_ms]
+    stats = net.last_stats.sum(0).cpu().tolist()
+    return {"metric": "rays_per_sec_render_800x800_64+128_50k_particles", "value": H * W * 3 / (ms * 1e-3), "unit": "rays/s",
+            "ms_per_step": ms / 3, "n_particles": 37 ** 3, "scaling": "strong",
+            "stage_ms_rank0": {"ray_query_coarse": st[0], "mlp_coarse": st[1], "composite_resample_query_fine": st[2],
+                               "mlp_fine": st[3], "composite_fine": st[4]},
+            "samples": {"active_coarse": stats[2], "active_fine": stats[3]}}
+
+
+def mgpu_parity(dev, world, rank):
+    """Under torchrun: on a small case the sharded renderer and the sharded transition step must reproduce what this
+    rank computes alone, bit for bit (all ranks agree -> True)."""
+    import torch.distributed as dist
+    import neurofluid_b200 as nb
+    from neurofluid_b200 import scenes
+    from neurofluid_b200.distributed import render_image_sharded, transition_step_sharded
+    Hs = 64
+    rays, focal, cw = scenes.camera_rays(Hs, Hs)
+    particles = torch.from_numpy(scenes.lattice_particles(12, 0)).to(dev)
+    net = nb.RenderNet(scenes.render_cfg(), scenes.NEAR, scenes.FAR); net.load_state_dict(scenes.init_render_state(0, 5.0)); net = net.to(dev)
+    ro = cw[:, 3].to(dev)
+    single = net(particles, ro, rays.to(dev), focal, cw)["rgb1"].view(Hs, Hs, 3).clone()
+    sharded = render_image_sharded(net, particles, ro, rays.view(Hs, Hs, 6).to(dev), focal, cw)
+    ok = torch.equal(single, sharded)
+    tn = nb.ParticleNet(gravity=(0.0, 0.0, -9.81)); tn.load_state_dict(scenes.init_particle_state(0)); tn = tn.to(dev)
+    pos = torch.from_numpy(scenes.lattice_particles(13, 1, center=(0.0, 0.0, -0.65))).to(dev)
+    bp, bn = scenes.box_points(0.06)
+    box, box_n = torch.from_numpy(bp).to(dev), torch.from_numpy(bn).to(dev)
+    p1, v1, n1 = (t.clone() for t in tn(pos, torch.zeros_like(pos), box, box_n))
+    p2, v2, n2 = transition_step_sharded(tn, pos, torch.zeros_like(pos), box, box_n)
+    ok = ok and torch.equal(p1, p2) and torch.equal(v1, v2) and torch.equal(n1, n2)
+    t = torch.tensor([int(ok)], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(t.item())
 
 
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path, all host threads."""
     if rank != 0:
         return
+    use_all_host_threads()
     per_step = []
     for i in range(args.warmup + args.steps):
         v, cores, sample = cpu_reference_rays_per_sec(REF_STEP_RAYS)
@@ -230,6 +328,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-drift", action="store_true", help="skip the 50-step oracle drift report of the transition block")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -349,9 +448,9 @@ def main():
         "gpu_launches": int(launches_t.item()),
         "clocks": clocks,
         "roofline": {"kernel": "k_nerf_mlp (fine network)", "bound": "tensor", "achieved": achieved_tflops,
-                     "peak": pk["tensor"], "unit": "TFLOP/s", "frac": achieved_tflops / pk["tensor"],
-                     "peak_source": f"{pk['src']} bf16 dense, sustained",
-                     "frac_of_burst_peak": achieved_tflops / pk["tensor_burst"],
+                     "peak": pk["tensor_burst"], "unit": "TFLOP/s", "frac": achieved_tflops / pk["tensor_burst"],
+                     "peak_source": f"{pk['src']} bf16 dense, burst (the kernel runs in ~6 ms bursts at full clock inside the step)",
+                     "frac_of_sustained_peak": achieved_tflops / pk["tensor"],
                      "traffic": tr_mlp["dram_bytes"] if tr_mlp else None,
                      "traffic_note": (f"ncu dram bytes of one launch ({tr_mlp['rows']} rows, {tr_mlp['report']}); algorithmic "
                                       f"{tr_mlp['rows'] * 84} B = 84 B/row (64 B record + 4 B row id in, 16 B out)") if tr_mlp else None,
@@ -369,10 +468,16 @@ def main():
     # ---- second hot path (BASELINE config[2]): transition-model rollout, ~30k particles, reported as an extra block
     line["transition"] = bench_transition(dev, world, rank, args, timed, pk)
     line["end2end"] = bench_end2end(dev, world, rank, timed)
-    if rank == 0 and not args.no_cpu_baseline and world == 1:
+    line["config4"] = bench_config4(dev, world, rank, timed)
+    if world > 1:
+        line["end2end_sharded_transition"] = bench_end2end(dev, world, rank, timed, transition="sharded")
+        line["mgpu_parity"] = mgpu_parity(dev, world, rank)
+    if rank == 0 and not args.no_cpu_baseline:
         v, cores, sample = cpu_reference_rays_per_sec(CPU_SAMPLE_RAYS)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
         line["transition"]["cpu_baseline"] = cpu_reference_particle_steps_per_sec()
+        if world == 1 and not args.no_drift:
+            line["transition"]["parity"] = transition_drift(dev)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -119,6 +119,7 @@ typedef struct nf_render_args {
     const float* rays; /* (n_rays,6) [origin(3), direction(3)]                                  */
     int32_t n_rays;
     float ro[3]; /* camera position used for the smoothed-direction feature (set_ro)          */
+    const float* ro_dev; /* optional device float[3]: read instead of ro (no host copy of a device tensor) */
     /* sampling */
     const float* z_coarse; /* (n_coarse) depths shared by all rays: near*(1-t)+far*t            */
     const float* u_importance; /* (n_importance) inverse-CDF arguments: linspace(0,1,n)         */
@@ -153,9 +154,23 @@ typedef struct nf_render_args {
         fine pass: group scans, solo row-scan queries, scan steps / 64, candidates tested / 64,
         coarse pass: the same four, 4 reserved} */
     int32_t* stats;
+    int32_t flags; /* NF_RENDER_SAVE_NEIGHBORS: keep every record row's neighbour list in the workspace (parity tests,
+                      backward pass); size the workspace with nf_render_workspace_bytes_ex(..., K, flags) */
 } nf_render_args;
 
+#define NF_RENDER_SAVE_NEIGHBORS 1
+
+/* Byte offsets of the regions of a render workspace that outlive nf_render_forward (tests compare them with the oracle,
+ * nf_render_backward reads them).  Row r of rec/rowid/nbr (r < counters[0] coarse, counters[1] fine) is one evaluated
+ * sample: rec (16 floats, layout of nf_nerf_mlp_forward), rowid = ray * S + sample, nbr = K neighbour indices (-1 padded). */
+typedef struct nf_render_ws_view {
+    size_t counters, act0, act1, z1, rec0, rowid0, out0, rec1, rowid1, out1, nbr0, nbr1, total;
+    int32_t act_stride0, act_stride1, cap0, cap1;
+} nf_render_ws_view;
+
 NF_API size_t nf_render_workspace_bytes(int n_rays, int n_coarse, int n_importance);
+NF_API size_t nf_render_workspace_bytes_ex(int n_rays, int n_coarse, int n_importance, int K, int flags);
+NF_API int nf_render_workspace_view(int n_rays, int n_coarse, int n_importance, int K, int flags, nf_render_ws_view* view_host);
 NF_API int nf_render_forward(const nf_render_args* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -216,6 +231,40 @@ NF_API int nf_transition_step(const nf_transition_args* args, void* stream);
  * layer 0: 96 channels, 1 and 2: 64 channels.  Used by the sharded execution to all-gather rows. */
 NF_API int nf_transition_layer_buffer(int n_fluid, int n_box, int layer, size_t* offset_bytes_host,
                                       size_t* row_bytes_host);
+
+/* ---------------------------------------------------------------------------------------------
+ * One ContinuousConv (operator-level drop-in for a maintainer who keeps models/transmodel.py and swaps only the layer)
+ * replaces: open3d.ml.torch.layers.ContinuousConv.forward as constructed at models/transmodel.py:79-98 (kernel_size
+ *           [4,4,4], linear interpolation, ball_to_cube_volume_preserving, normalize=False, window = poly6 or none,
+ *           radius_search_ignore_query_points) and called at :116, :118, :125; count_out is what
+ *           ml3d.ops.reduce_subarrays_sum(ones, conv.nns.neighbors_row_splits) returns at :135-138.
+ * Supported channel shapes: cin * cout <= 768 (fp32 on CUDA cores: the model's 4->32, 3->32, 64->3 layers) and
+ * 64 -> 64 / 96 -> 64 (tcgen05, fp16/bf16 operands, fp32 accumulate); anything else: NF_E_UNSUPPORTED.
+ * ------------------------------------------------------------------------------------------- */
+NF_API size_t nf_cconv_packed_weights_bytes(int cin, int cout);
+NF_API int nf_cconv_pack_weights(const float* kernel /*(4,4,4,cin,cout)*/, const float* bias /*(cout) or NULL*/, int cin,
+                                 int cout, int dtype, void* packed_out, void* stream);
+NF_API size_t nf_cconv_workspace_bytes(int n_in, int n_out, int cin, int cout);
+
+typedef struct nf_cconv_args {
+    const void* grid_in;   /* nf_grid_build(in_positions, n_in, cell >= 1.002 * extent / 2) */
+    const float* in_feat;  /* (n_in, cin)  */
+    int32_t n_in, cin;
+    const float* out_pos;  /* (n_out, 3)   */
+    int32_t n_out, cout;
+    float extent;          /* filter diameter; search radius = extent / 2 (d^2 <= r^2) */
+    int32_t use_window;    /* poly6 window clamp((1 - d^2/r^2)^3, 0, 1) (models/transmodel.py:73-77) */
+    int32_t ignore_same;   /* radius_search_ignore_query_points: skip in-points whose coordinates equal the out-point's */
+    int32_t dtype;         /* NF_DTYPE_*: operand type of the tensor-core shapes */
+    const void* weights;   /* nf_cconv_pack_weights */
+    float* out;            /* (n_out, cout) = conv + bias */
+    float* count_out;      /* optional (n_out): number of neighbours of every out point (uncapped) */
+    int32_t* nbr_index_out; /* optional (n_out, 128): neighbour indices in search order, -1 padded (conv.nns.neighbors_index) */
+    int32_t* overflow_out; /* optional device int32[2]: [0] += out points with more than 128 neighbours (list truncated) */
+    void* workspace;
+    size_t workspace_bytes;
+} nf_cconv_args;
+NF_API int nf_cconv_forward(const nf_cconv_args* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Callers' side of the hot paths: camera rays and evaluation metrics on the device

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnf_b200.so")
+LIB_PATH = os.environ.get("NF_B200_LIB") or os.path.join(_HERE, "libnf_b200.so")     # NF_B200_LIB: the -DNF_TUNING build
 
 NF_DTYPE_F16, NF_DTYPE_BF16 = 0, 1
 NF_RENDER_FORWARD, NF_RENDER_COARSE, NF_RENDER_FINE = 0, 1, 2
@@ -21,15 +21,24 @@ _vp, _i32, _f32, _sz, _i64 = C.c_void_p, C.c_int32, C.c_float, C.c_size_t, C.c_i
 class RenderArgs(C.Structure):
     _fields_ = [
         ("grid_ws", _vp), ("particles", _vp), ("n_particles", _i32),
-        ("rays", _vp), ("n_rays", _i32), ("ro", _f32 * 3),
+        ("rays", _vp), ("n_rays", _i32), ("ro", _f32 * 3), ("ro_dev", _vp),
         ("z_coarse", _vp), ("u_importance", _vp), ("n_coarse", _i32), ("n_importance", _i32),
         ("radius", _f32), ("K", _i32), ("search", _i32),
         ("mode", _i32), ("use_mask", _i32), ("white_background", _i32), ("dtype", _i32),
         ("weights_coarse", _vp), ("weights_fine", _vp),
         ("rgb0", _vp), ("depth0", _vp), ("opacity0", _vp), ("num_nn0", _vp), ("mask0", _vp),
         ("rgb1", _vp), ("depth1", _vp), ("opacity1", _vp), ("num_nn1", _vp), ("mask1", _vp),
-        ("workspace", _vp), ("workspace_bytes", _sz), ("stats", _vp),
+        ("workspace", _vp), ("workspace_bytes", _sz), ("stats", _vp), ("flags", _i32),
     ]
+
+
+NF_RENDER_SAVE_NEIGHBORS = 1
+
+
+class RenderWsView(C.Structure):
+    _fields_ = [(n, _sz) for n in ("counters", "act0", "act1", "z1", "rec0", "rowid0", "out0", "rec1", "rowid1", "out1",
+                                   "nbr0", "nbr1", "total")] + \
+               [(n, _i32) for n in ("act_stride0", "act_stride1", "cap0", "cap1")]
 
 
 class TransitionArgs(C.Structure):
@@ -42,6 +51,16 @@ class TransitionArgs(C.Structure):
         ("feats0_out", _vp), ("delta_out", _vp),
         ("workspace", _vp), ("workspace_bytes", _sz),
         ("shard_begin", _i32), ("shard_end", _i32), ("box_grid_ws", _vp), ("overflow_out", _vp), ("phase", _i32),
+    ]
+
+
+class CConvArgs(C.Structure):
+    _fields_ = [
+        ("grid_in", _vp), ("in_feat", _vp), ("n_in", _i32), ("cin", _i32),
+        ("out_pos", _vp), ("n_out", _i32), ("cout", _i32),
+        ("extent", _f32), ("use_window", _i32), ("ignore_same", _i32), ("dtype", _i32),
+        ("weights", _vp), ("out", _vp), ("count_out", _vp), ("nbr_index_out", _vp), ("overflow_out", _vp),
+        ("workspace", _vp), ("workspace_bytes", _sz),
     ]
 
 
@@ -59,6 +78,8 @@ SIGNATURES = {
     "nf_render_pack_weights": (C.c_int, [C.POINTER(_vp), C.c_int, _vp, _vp]),
     "nf_nerf_mlp_forward": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, _vp, _vp]),
     "nf_render_workspace_bytes": (_sz, [C.c_int, C.c_int, C.c_int]),
+    "nf_render_workspace_bytes_ex": (_sz, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "nf_render_workspace_view": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(RenderWsView)]),
     "nf_render_forward": (C.c_int, [C.POINTER(RenderArgs), _vp]),
     "nf_transition_packed_weights_bytes": (_sz, []),
     "nf_transition_pack_weights": (C.c_int, [C.POINTER(_vp), C.c_int, _vp, _vp]),
@@ -66,6 +87,10 @@ SIGNATURES = {
     "nf_transition_num_phases": (C.c_int, []),
     "nf_transition_step": (C.c_int, [C.POINTER(TransitionArgs), _vp]),
     "nf_transition_layer_buffer": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(_sz), C.POINTER(_sz)]),
+    "nf_cconv_packed_weights_bytes": (_sz, [C.c_int, C.c_int]),
+    "nf_cconv_pack_weights": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "nf_cconv_workspace_bytes": (_sz, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "nf_cconv_forward": (C.c_int, [C.POINTER(CConvArgs), _vp]),
     "nf_generate_rays": (C.c_int, [C.c_int, C.c_int, _f32, _vp, _vp, _vp]),
     "nf_nearest_distance": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp]),
     "nf_pair_distance": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),

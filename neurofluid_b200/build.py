@@ -1,6 +1,10 @@
 """In-tree build of libnf_b200.so (hand-written sm_100a kernels + C ABI, include/nf_b200.h).
 
-    python -m neurofluid_b200.build [--force] [--verbose]
+    python -m neurofluid_b200.build [--force] [--verbose] [--tuning]
+
+`--tuning` builds libnf_b200_tune.so with -DNF_TUNING: the same kernels plus the NF_* environment overrides the
+profiling / tuning scripts use (tests/gpu_tune.py, tests/gpu_mlp_trace.py; load it with NF_B200_LIB=<path>).  The
+release library never reads the environment.
 
 nvcc cross-compiles for sm_100a without a GPU; the resulting .so is git-ignored but travels to the
 GPU box with the gpurun snapshot.
@@ -27,16 +31,19 @@ def _deps():
         [os.path.join(os.path.dirname(HERE), "include", "nf_b200.h")]
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, tuning: bool = False) -> str:
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
     newest = max(os.path.getmtime(p) for p in _deps())
-    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= newest:
-        return OUT
-    os.makedirs(OBJ, exist_ok=True)
+    out = OUT[:-3] + "_tune.so" if tuning else OUT
+    objdir = OBJ + ("_tune" if tuning else "")
+    flags = FLAGS + (["-DNF_TUNING"] if tuning else [])
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= newest:
+        return out
+    os.makedirs(objdir, exist_ok=True)
 
     def compile_one(src):
-        obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
-        r = subprocess.run([NVCC, *FLAGS, "-c", src, "-o", obj], capture_output=True, text=True)
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        r = subprocess.run([NVCC, *flags, "-c", src, "-o", obj], capture_output=True, text=True)
         return src, obj, r
 
     objs = []
@@ -49,9 +56,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
             with open(obj + ".ptxas.log", "w") as f:
                 f.write(r.stderr)
             objs.append(obj)
-    subprocess.check_call([NVCC, "-shared", "-o", OUT, *objs, "-lcudart"])
-    return OUT
+    subprocess.check_call([NVCC, "-shared", "-o", out, *objs, "-lcudart"])
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, tuning="--tuning" in sys.argv))

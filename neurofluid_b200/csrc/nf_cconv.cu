@@ -521,6 +521,8 @@ struct ConvArgs {
     int n;                                 // total particles (rows of x_in)
     int begin, end;                        // rows computed by this launch
     int cout;                              // real output channels (<= COUT_PAD)
+    int dense;                             // 1: the 17th slab is the dense (nn.Linear) branch on the particle's own row;
+                                           // 0: plain ContinuousConv (operator-level entry point; in / out sets may differ)
 };
 
 template <int CIN, int COUT_PAD>
@@ -713,7 +715,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_cconv_tc(const ConvArgs a) 
                     ne_c = ne_a; ej_c = ej_a; ew_c = ew_a;
                     ne_a = ne_b; ej_a = ej_b; ew_a = ew_b;
                     fetch_entries(unit + 3, ne_b, ej_b, ew_b);
-                } else if (row < a.end) {
+                } else if (row < a.end && a.dense) {
                     // dense branch: the particle's own (ReLU'd) features, K = CIN
                     cvt2(__ldg(xin32 + (((size_t)row * CIN) >> 1) + lane), acc[0][0], acc[0][1]);
                     if (THIRD) acc[0][2] = cvt1(__ldg(xin16 + (size_t)row * CIN + 64 + lane));
@@ -898,7 +900,7 @@ __global__ void k_pack_conv(const float* __restrict__ kern, const float* __restr
                     v = kern[((size_t)(s * 4 + x) * CIN + ch) * cout + n];
                 } else {
                     const int k = (step - 16 * C::KSTEPS) * 16 + kc * 8 + i;
-                    v = wd[(size_t)n * CIN + k];
+                    v = wd ? wd[(size_t)n * CIN + k] : 0.f;
                 }
             }
             if (BF16) { __nv_bfloat16 h = __float2bfloat16(v); e[i] = *reinterpret_cast<unsigned short*>(&h); }
@@ -909,7 +911,7 @@ __global__ void k_pack_conv(const float* __restrict__ kern, const float* __restr
         pk.z = e[4] | ((unsigned)e[5] << 16); pk.w = e[6] | ((unsigned)e[7] << 16);
         *reinterpret_cast<uint4*>(out + (size_t)step * C::STEP_BYTES + ((size_t)kc * COUT_PAD + n) * 16) = pk;
     }
-    if (t < COUT_PAD) reinterpret_cast<float*>(out + C::W_BYTES)[t] = t < cout ? bconv[t] + bd[t] : 0.f;
+    if (t < COUT_PAD) reinterpret_cast<float*>(out + C::W_BYTES)[t] = t < cout ? (bconv ? bconv[t] : 0.f) + (bd ? bd[t] : 0.f) : 0.f;
 }
 
 // packed layout of the whole ParticleNet: fp32 layer-0 tensors, then the three tensor-core layers
@@ -973,6 +975,106 @@ static int launch_conv(const ConvArgs& a, int dtype, cudaStream_t st) {
     return NF_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Operator-level ContinuousConv (nf_cconv_forward): one conv on arbitrary in / out point sets.
+//   small shapes (cin * cout <= SMALL_MAX: the 4->32, 3->32, 64->3 layers): fp32 on CUDA cores, the whole filter in
+//   shared memory, one warp per out point: patch (64 cells x cin) accumulated from the pair list, then contracted.
+//   64/96 -> 64: the slab-list tensor-core kernel above with the dense slab switched off.
+// ------------------------------------------------------------------------------------------------
+constexpr int SMALL_MAX = 768;
+
+__global__ void __launch_bounds__(256) k_cconv_small(const Pair* __restrict__ pairs, const int* __restrict__ cnt,
+                                                     const float* __restrict__ in_feat, int cin, int cout,
+                                                     const float* __restrict__ kern /*(64, cin, cout)*/,
+                                                     const float* __restrict__ bias /*(cout)*/, int n_out,
+                                                     float* __restrict__ out /*(n_out, cout)*/) {
+    extern __shared__ __align__(16) float sm[];
+    float* sk = sm;                                   // 64 * cin * cout
+    const int kn = NCELL * cin * cout, pn = NCELL * cin;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    float* patch = sm + kn + wib * pn;
+    for (int k = threadIdx.x; k < kn; k += blockDim.x) sk[k] = __ldg(kern + k);
+    __syncthreads();
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_out; i += nwarps) {
+        for (int k = lane; k < pn; k += 32) patch[k] = 0.f;
+        __syncwarp();
+        const int n = cnt[i];
+        const Pair* pr = pairs + (size_t)i * MAXNBR;
+        for (int t0 = 0; t0 < n; t0 += 32) {
+            uint4 h0 = make_uint4(0u, 0u, 0u, 0u);
+            float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
+            if (t0 + lane < n) {
+                h0 = __ldg(reinterpret_cast<const uint4*>(pr + t0 + lane));
+                w0 = __ldg(reinterpret_cast<const float4*>(pr + t0 + lane) + 1);
+                w1 = __ldg(reinterpret_cast<const float4*>(pr + t0 + lane) + 2);
+            }
+            const int m = min(32, n - t0);
+            for (int u = 0; u < m; ++u) {            // pairs in list order: the patch sums run like a walk over the list
+                const int j = __shfl_sync(NF_FULL, (int)h0.x, u);
+                const unsigned c03 = __shfl_sync(NF_FULL, h0.y, u), c47 = __shfl_sync(NF_FULL, h0.z, u);
+                float w[8];
+                w[0] = __shfl_sync(NF_FULL, w0.x, u); w[1] = __shfl_sync(NF_FULL, w0.y, u);
+                w[2] = __shfl_sync(NF_FULL, w0.z, u); w[3] = __shfl_sync(NF_FULL, w0.w, u);
+                w[4] = __shfl_sync(NF_FULL, w1.x, u); w[5] = __shfl_sync(NF_FULL, w1.y, u);
+                w[6] = __shfl_sync(NF_FULL, w1.z, u); w[7] = __shfl_sync(NF_FULL, w1.w, u);
+                for (int ch = lane; ch < cin; ch += 32) {
+                    const float f = __ldg(in_feat + (size_t)j * cin + ch);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const unsigned cell = ((c < 4 ? c03 : c47) >> (8 * (c & 3))) & 0xffu;
+                        patch[cell * cin + ch] += w[c] * f;       // a lane owns its channels: no conflicts between lanes
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        for (int co = 0; co < cout; ++co) {
+            float acc = 0.f;
+            for (int k = lane; k < pn; k += 32) acc += patch[k] * sk[k * cout + co];
+            acc = warp_sum(acc);
+            if (lane == 0) out[(size_t)i * cout + co] = acc + (bias ? __ldg(bias + co) : 0.f);
+        }
+        __syncwarp();
+    }
+}
+
+template <bool BF16>
+__global__ void k_to_half(const float* __restrict__ in, size_t n, void* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (BF16) reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16(in[i]);
+    else reinterpret_cast<__half*>(out)[i] = __float2half(in[i]);
+}
+
+__global__ void k_pairs_index(const Pair* __restrict__ pairs, const int* __restrict__ cnt, int n_out, int32_t* __restrict__ idx) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_out * MAXNBR) return;
+    const int i = t / MAXNBR, k = t % MAXNBR;
+    idx[t] = k < cnt[i] ? pairs[(size_t)i * MAXNBR + k].j : -1;
+}
+
+struct OpWs {
+    size_t pairs, cnt, slab_j, slab_w, slab_off, x16, flags, total;
+};
+inline bool op_is_tc(int cin, int cout) { return (cin == 64 || cin == 96) && cout == 64; }
+inline OpWs op_ws(int n_in, int n_out, int cin, int cout) {
+    OpWs L;
+    size_t o = 0;
+    auto take = [&](size_t b) { size_t r = o; o += align_up(b, 256); return r; };
+    const size_t N = (size_t)(n_out > 0 ? n_out : 1), NI = (size_t)(n_in > 0 ? n_in : 1);
+    L.pairs = take(N * MAXNBR * sizeof(Pair)); L.cnt = take(N * 4);
+    L.slab_j = L.slab_w = L.slab_off = L.x16 = 0;
+    if (op_is_tc(cin, cout)) {
+        L.slab_j = take(N * SLABCAP * 4); L.slab_w = take(N * SLABCAP * 16); L.slab_off = take(N * SLABOFF * 2);
+        L.x16 = take(NI * cin * 2);
+    }
+    L.flags = take(256);
+    L.total = o;
+    return L;
+}
+
 }  // namespace cconv
 }  // namespace nf
 
@@ -1021,6 +1123,110 @@ extern "C" int nf_transition_pack_weights(const float* const* p, int dtype, void
 extern "C" size_t nf_transition_workspace_bytes(int n_fluid, int n_box) {
     if (n_fluid < 0 || n_box < 0) return 0;
     return ws_layout(n_fluid, n_box).total;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// operator-level entry points
+// ------------------------------------------------------------------------------------------------
+extern "C" size_t nf_cconv_packed_weights_bytes(int cin, int cout) {
+    if (cin <= 0 || cout <= 0) return 0;
+    if (op_is_tc(cin, cout)) return cin == 96 ? ConvCfg<96, 64>::PACKED_BYTES : ConvCfg<64, 64>::PACKED_BYTES;
+    if (cin * cout > SMALL_MAX) return 0;
+    return align_up((size_t)NCELL * cin * cout * 4, 256) + align_up((size_t)cout * 4, 256);
+}
+
+extern "C" int nf_cconv_pack_weights(const float* kernel, const float* bias, int cin, int cout, int dtype, void* packed_out,
+                                     void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    NF_REQUIRE(kernel && packed_out, NF_E_INVALID, "nf_cconv_pack_weights: null argument");
+    NF_REQUIRE(dtype == NF_DTYPE_F16 || dtype == NF_DTYPE_BF16, NF_E_UNSUPPORTED, "nf_cconv_pack_weights: dtype %d", dtype);
+    NF_REQUIRE(nf_cconv_packed_weights_bytes(cin, cout) > 0, NF_E_UNSUPPORTED,
+               "nf_cconv_pack_weights: %d -> %d channels (supported: cin*cout <= %d in fp32, 64/96 -> 64 on tensor cores)", cin, cout, SMALL_MAX);
+    uint8_t* b = (uint8_t*)packed_out;
+    const bool bf = dtype == NF_DTYPE_BF16;
+    if (op_is_tc(cin, cout)) {
+        if (cin == 96) {
+            using C = ConvCfg<96, 64>;
+            const int tot = (16 * C::KSTEPS + C::KSTEPS_DENSE) * 2 * 64;
+            if (bf) k_pack_conv<96, 64, true><<<(tot + 255) / 256, 256, 0, st>>>(kernel, bias, nullptr, nullptr, 64, b);
+            else k_pack_conv<96, 64, false><<<(tot + 255) / 256, 256, 0, st>>>(kernel, bias, nullptr, nullptr, 64, b);
+        } else {
+            using C = ConvCfg<64, 64>;
+            const int tot = (16 * C::KSTEPS + C::KSTEPS_DENSE) * 2 * 64;
+            if (bf) k_pack_conv<64, 64, true><<<(tot + 255) / 256, 256, 0, st>>>(kernel, bias, nullptr, nullptr, 64, b);
+            else k_pack_conv<64, 64, false><<<(tot + 255) / 256, 256, 0, st>>>(kernel, bias, nullptr, nullptr, 64, b);
+        }
+        NF_LAUNCH_OK();
+        return NF_OK;
+    }
+    const size_t kb = (size_t)NCELL * cin * cout * 4;
+    NF_CUDA_OK(cudaMemcpyAsync(b, kernel, kb, cudaMemcpyDeviceToDevice, st));
+    if (bias) NF_CUDA_OK(cudaMemcpyAsync(b + align_up(kb, 256), bias, (size_t)cout * 4, cudaMemcpyDeviceToDevice, st));
+    else NF_CUDA_OK(cudaMemsetAsync(b + align_up(kb, 256), 0, (size_t)cout * 4, st));
+    return NF_OK;
+}
+
+extern "C" size_t nf_cconv_workspace_bytes(int n_in, int n_out, int cin, int cout) {
+    if (n_in < 0 || n_out < 0 || cin <= 0 || cout <= 0) return 0;
+    return op_ws(n_in, n_out, cin, cout).total;
+}
+
+extern "C" int nf_cconv_forward(const nf_cconv_args* a, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    NF_REQUIRE(a != nullptr, NF_E_INVALID, "nf_cconv_forward: null args");
+    NF_REQUIRE(a->n_in >= 0 && a->n_out >= 0 && a->cin > 0 && a->cout > 0, NF_E_INVALID, "nf_cconv_forward: bad sizes");
+    NF_REQUIRE(nf_cconv_packed_weights_bytes(a->cin, a->cout) > 0, NF_E_UNSUPPORTED, "nf_cconv_forward: %d -> %d channels unsupported",
+               a->cin, a->cout);
+    if (a->n_out == 0) return NF_OK;
+    NF_REQUIRE(a->grid_in && a->out_pos && a->weights && a->out && a->workspace, NF_E_INVALID, "nf_cconv_forward: null pointer");
+    NF_REQUIRE(a->n_in == 0 || a->in_feat, NF_E_INVALID, "nf_cconv_forward: null features");
+    NF_REQUIRE(a->extent > 2e-3f, NF_E_INVALID, "nf_cconv_forward: bad extent");
+    const OpWs L = op_ws(a->n_in, a->n_out, a->cin, a->cout);
+    NF_REQUIRE(a->workspace_bytes >= L.total, NF_E_WORKSPACE, "nf_cconv_forward: workspace %zu < %zu", a->workspace_bytes, L.total);
+    char* b = (char*)a->workspace;
+    Pair* pairs = (Pair*)(b + L.pairs);
+    int* cnt = (int*)(b + L.cnt);
+    int* flags = (int*)(b + L.flags);
+    const bool tc = op_is_tc(a->cin, a->cout);
+    const float radius = 0.5f * a->extent;
+    NF_CUDA_OK(cudaMemsetAsync(flags, 0, 256, st));
+    const int blocks = (a->n_out + 7) / 8;
+    k_nbr_build<<<blocks, 256, 0, st>>>(grid_view(a->grid_in, a->n_in), a->out_pos, 0, a->n_out, radius, a->ignore_same != 0,
+                                       a->use_window != 0, pairs, cnt, a->count_out, flags,
+                                       tc ? (int*)(b + L.slab_j) : nullptr, tc ? (float4*)(b + L.slab_w) : nullptr,
+                                       tc ? (unsigned short*)(b + L.slab_off) : nullptr);
+    NF_LAUNCH_OK();
+    if (a->overflow_out) {
+        k_add_overflow<<<1, 32, 0, st>>>(flags, a->overflow_out);
+        NF_LAUNCH_OK();
+    }
+    if (a->nbr_index_out) {
+        k_pairs_index<<<(a->n_out * MAXNBR + 255) / 256, 256, 0, st>>>(pairs, cnt, a->n_out, a->nbr_index_out);
+        NF_LAUNCH_OK();
+    }
+    if (tc) {
+        const size_t nx = (size_t)a->n_in * a->cin;
+        if (nx) {
+            if (a->dtype == NF_DTYPE_BF16) k_to_half<true><<<(unsigned)((nx + 255) / 256), 256, 0, st>>>(a->in_feat, nx, b + L.x16);
+            else k_to_half<false><<<(unsigned)((nx + 255) / 256), 256, 0, st>>>(a->in_feat, nx, b + L.x16);
+            NF_LAUNCH_OK();
+        }
+        ConvArgs c;
+        c.slab_j = (const int*)(b + L.slab_j); c.slab_w = (const float4*)(b + L.slab_w);
+        c.slab_off = (const unsigned short*)(b + L.slab_off);
+        c.x_in = b + L.x16; c.w_packed = (const uint8_t*)a->weights; c.residual = nullptr; c.ld_res = 0;
+        c.ans = a->out; c.x_out = nullptr; c.n = a->n_in; c.begin = 0; c.end = a->n_out; c.cout = 64; c.dense = 0;
+        return a->cin == 96 ? launch_conv<96, 64>(c, a->dtype, st) : launch_conv<64, 64>(c, a->dtype, st);
+    }
+    const size_t kb = (size_t)NCELL * a->cin * a->cout * 4;
+    const size_t smem = kb + (size_t)8 * NCELL * a->cin * 4;
+    NF_CUDA_OK(cudaFuncSetAttribute(k_cconv_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = min(blocks, 2 * num_sms());
+    k_cconv_small<<<grid, 256, smem, st>>>(pairs, cnt, a->in_feat, a->cin, a->cout, (const float*)a->weights,
+                                          (const float*)((const char*)a->weights + align_up(kb, 256)), a->n_out, a->out);
+    NF_LAUNCH_OK();
+    return NF_OK;
 }
 
 // phases: 0 integrate + grids + neighbour lists + layer 0;  1,2,3 conv layers;  4 position/velocity update
@@ -1107,7 +1313,7 @@ extern "C" int nf_transition_step(const nf_transition_args* a, void* stream_) {
         }
     }
     ConvArgs c;
-    c.slab_j = slab_j; c.slab_w = slab_w; c.slab_off = slab_off; c.n = N; c.begin = begin; c.end = end;
+    c.slab_j = slab_j; c.slab_w = slab_w; c.slab_off = slab_off; c.n = N; c.begin = begin; c.end = end; c.dense = 1;
     if (all || a->phase == 1) {     // conv1 + dense1 : 96 -> 64 (no residual: widths differ, :127-130)
         c.x_in = x0; c.w_packed = w + PL.l1; c.residual = nullptr; c.ld_res = 0; c.ans = ans1; c.x_out = x1; c.cout = 64;
         int rc = launch_conv<96, 64>(c, a->dtype, st);

@@ -363,7 +363,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp(const KernelArgs a)
     const int npass = (ntiles + TPU - 1) / TPU;
     if (unit >= npass) return;          // both CTAs of a pair leave together
     const int nl = a.n_layers;
-    const bool no_weights = (a.desc_swap & 16) != 0;   // debug: do not stream / wait for weights (timing only)
+#ifdef NF_TUNING
+    const bool no_weights = (a.desc_swap & 16) != 0;   // tuning builds only: do not stream / wait for weights (timing only)
+#else
+    constexpr bool no_weights = false;
+#endif
 
     const uint32_t s_base = smem_u32(smem);
     const uint32_t s_hidden = s_base + SM_HIDDEN, s_pexyz = s_base + SM_PEXYZ, s_pedir = s_base + SM_PEDIR;
@@ -781,13 +785,18 @@ __global__ void k_pack_weights(PackArgs p, uint8_t* out, int pair) {
     }
 }
 
+// CTA pairs (cta_group::2) always; a build with -DNF_TUNING can fall back to single CTAs through NF_MLP_PAIR=0
 bool pair_mode() {
+#ifdef NF_TUNING
     static int mode = -1;
     if (mode < 0) {
         const char* v = getenv("NF_MLP_PAIR");
         mode = v ? (atoi(v) != 0) : 1;
     }
     return mode != 0;
+#else
+    return true;
+#endif
 }
 
 template <bool BF16, bool PAIR>
@@ -844,10 +853,12 @@ extern "C" int nf_render_pack_weights(const float* const* params, int dtype, voi
     return NF_OK;
 }
 
+#ifdef NF_TUNING
 static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return v ? atoi(v) : dflt;
 }
+#endif
 
 extern "C" int nf_nerf_mlp_forward(const void* packed, int dtype, const float* records, int n_rows, int sigma_only,
                                    float* out, void* stream_) {
@@ -864,8 +875,13 @@ extern "C" int nf_nerf_mlp_forward(const void* packed, int dtype, const float* r
     a.n_rows_host = n_rows;
     a.n_rows_cap = n_rows;
     a.n_layers = sigma_only ? 8 : 10;
-    a.desc_swap = env_int("NF_MLP_DESC_SWAP", 0);
     a.out4 = (float4*)out;
+#ifdef NF_TUNING      // tests/gpu_mlp_trace.py (clock64 timeline of one tile) runs against the tuning build only
+    a.desc_swap = env_int("NF_MLP_DESC_SWAP", 0);
     a.trace = (long long*)(uintptr_t)strtoull(getenv("NF_MLP_TRACE_PTR") ? getenv("NF_MLP_TRACE_PTR") : "0", nullptr, 0);
+#else
+    a.desc_swap = 0;
+    a.trace = nullptr;
+#endif
     return mlp::launch(a, dtype, st);
 }

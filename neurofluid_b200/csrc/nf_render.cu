@@ -41,6 +41,7 @@ struct StageArgs {
     const float* rays;
     int n_rays;
     float ro[3];
+    const float* ro_dev;                       // optional: camera position read from device memory (overrides ro)
     float radius;
     int K;
     int use_mask, white_bg, mode;
@@ -68,6 +69,7 @@ struct StageArgs {
     float* z1;           // (R, S1)
     float* rec0; int* rowid0; float4* out0; int cap0;
     float* rec1; int* rowid1; float4* out1; int cap1;
+    int* nbr0; int* nbr1;   // optional (NF_RENDER_SAVE_NEIGHBORS): (rows, K) neighbour indices of every record row, -1 padded
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -452,7 +454,8 @@ __device__ __forceinline__ void ray_query_group(const StageArgs& p, int lane, co
                                              float* rec, int* rowid, int* row_counter, int* active_counter, int cap,
                                              int ray, long long* num_nn, unsigned* act, int act_stride,
                                              QueryStats& qs, int* sel, unsigned* scratch,
-                                             const short* src /*smem or null: coarse index of each merged sample*/) {
+                                             const short* src /*smem or null: coarse index of each merged sample*/,
+                                             int* nbr /*null or (rows, K): neighbour list of every record row*/) {
     // Fine pass: a merged sample that IS one of the coarse samples (same depth, same position, bit for bit) was
     // already searched by stage Q0 -- its neighbour count comes from cnt0 and its geometry record is copied from
     // rec0 instead of being searched and built again (the coarse samples are the ones spread through the whole
@@ -468,6 +471,8 @@ __device__ __forceinline__ void ray_query_group(const StageArgs& p, int lane, co
     int n_active = 0;
     const int sample_base = ray * S;
     const int nslots = (S + 31) >> 5;
+    const float rox = p.ro_dev ? __ldg(p.ro_dev) : p.ro[0], roy = p.ro_dev ? __ldg(p.ro_dev + 1) : p.ro[1],
+                roz = p.ro_dev ? __ldg(p.ro_dev + 2) : p.ro[2];
 #pragma unroll 1
     for (int slot = 0; slot < nslots; ++slot) {
         const int s = slot * 32 + lane;
@@ -544,15 +549,19 @@ __device__ __forceinline__ void ray_query_group(const StageArgs& p, int lane, co
                     const int row0 = p.base0[(size_t)ray * act_stride0 + slot0] + __popc(ev0 & ((1u << (from & 31)) - 1u));
                     const float4* sp = reinterpret_cast<const float4*>(p.rec0 + (size_t)row0 * 16);
                     dst[0] = sp[0]; dst[1] = sp[1]; dst[2] = sp[2]; dst[3] = sp[3];
+                    if (nbr)
+                        for (int k = 0; k < K; ++k) nbr[(size_t)row * K + k] = p.nbr0[(size_t)row0 * K + k];
                 } else {
                     const float den = wsum + 1e-12f;
                     const float sx = wx / den, sy = wy / den, sz = wz / den;
-                    const float tx = sx - p.ro[0], ty = sy - p.ro[1], tz = sz - p.ro[2];
+                    const float tx = sx - rox, ty = sy - roy, tz = sz - roz;
                     const float tn = sqrtf(tx * tx + ty * ty + tz * tz);
                     dst[0] = make_float4(qx, qy, qz, wsum);
                     dst[1] = make_float4(sx, sy, sz, ax / nvf);
                     dst[2] = make_float4(ay / nvf, az / nvf, d[0], d[1]);
                     dst[3] = make_float4(d[2], tx / tn, ty / tn, tz / tn);
+                    if (nbr)
+                        for (int k = 0; k < K; ++k) nbr[(size_t)row * K + k] = k < cnt ? sel[lane * KP + k] : -1;
                 }
                 rowid[row] = sample_base + s;
             }
@@ -671,7 +680,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, FL == 1 ? 3 : 2) k_stage
             continue;
         }
         ray_query_group<FL>(p, lane, o, d, sm_z, p.S0, p.rec0, p.rowid0, p.counters + 0, p.counters + 2, p.cap0, ray,
-                        p.num_nn0, p.act0, NS0, qs, sel, scratch, nullptr);
+                        p.num_nn0, p.act0, NS0, qs, sel, scratch, nullptr, p.nbr0);
     }
     if (lane == 0) {
         atomicAdd(p.counters + 8, qs.n_lock);
@@ -834,7 +843,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, FL == 1 ? 3 : 2) k_stage
         __syncwarp();
         for (int s = lane; s < S1; s += 32) p.z1[(size_t)ray * S1 + s] = z1s[s];
         ray_query_group<FL>(p, lane, o, d, z1s, S1, p.rec1, p.rowid1, p.counters + 1, p.counters + 3, p.cap1, ray,
-                        p.num_nn1, p.act1, NS1, qs, sel, scratch, src1);
+                        p.num_nn1, p.act1, NS1, qs, sel, scratch, src1, p.nbr1);
         __syncwarp();
     }
     if (lane == 0) {
@@ -895,13 +904,15 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_stage_fin(const StageA
     }
 }
 
+#ifdef NF_TUNING
 static int env_int(const char* name, int dflt) {
     const char* e = getenv(name);
     return e ? atoi(e) : dflt;
 }
+#endif
 
 struct WsLayout {
-    size_t counters, act0, act1, base0, cnt0, miss, z1, rec0, rowid0, out0, rec1, rowid1, out1, total;
+    size_t counters, act0, act1, base0, cnt0, miss, z1, rec0, rowid0, out0, rec1, rowid1, out1, nbr0, nbr1, total;
     int cap0, cap1, ns0, ns1;
 };
 
@@ -911,7 +922,7 @@ static int pick_ns(int s, const int* opts, int n) {
     return -1;
 }
 
-static WsLayout ws_layout(int R, int S0, int NI) {
+static WsLayout ws_layout(int R, int S0, int NI, int K = 0 /* > 0: room for the saved neighbour lists */) {
     WsLayout L;
     const int S1 = S0 + NI;
     static const int o0[] = {2, 4};
@@ -935,6 +946,11 @@ static WsLayout ws_layout(int R, int S0, int NI) {
     L.rec1 = take(sizeof(float) * 16 * (size_t)L.cap1);
     L.rowid1 = take(sizeof(int) * (size_t)L.cap1);
     L.out1 = take(sizeof(float4) * (size_t)R * S1);
+    L.nbr0 = L.nbr1 = 0;
+    if (K > 0) {
+        L.nbr0 = take(sizeof(int) * (size_t)L.cap0 * K);
+        L.nbr1 = take(sizeof(int) * (size_t)L.cap1 * K);
+    }
     L.total = o;
     return L;
 }
@@ -1029,6 +1045,23 @@ extern "C" size_t nf_render_workspace_bytes(int n_rays, int n_coarse, int n_impo
     return ws_layout(n_rays, n_coarse, n_importance).total;
 }
 
+extern "C" size_t nf_render_workspace_bytes_ex(int n_rays, int n_coarse, int n_importance, int K, int flags) {
+    if (n_rays <= 0 || n_coarse <= 0 || n_importance < 0) return 0;
+    return ws_layout(n_rays, n_coarse, n_importance, (flags & NF_RENDER_SAVE_NEIGHBORS) ? K : 0).total;
+}
+
+extern "C" int nf_render_workspace_view(int n_rays, int n_coarse, int n_importance, int K, int flags, nf_render_ws_view* v) {
+    NF_REQUIRE(v && n_rays > 0 && n_coarse > 0 && n_importance >= 0, NF_E_INVALID, "nf_render_workspace_view: bad arguments");
+    const WsLayout L = ws_layout(n_rays, n_coarse, n_importance, (flags & NF_RENDER_SAVE_NEIGHBORS) ? K : 0);
+    v->counters = L.counters; v->act0 = L.act0; v->act1 = L.act1; v->z1 = L.z1;
+    v->rec0 = L.rec0; v->rowid0 = L.rowid0; v->out0 = L.out0;
+    v->rec1 = L.rec1; v->rowid1 = L.rowid1; v->out1 = L.out1;
+    v->nbr0 = L.nbr0; v->nbr1 = L.nbr1;
+    v->act_stride0 = L.ns0; v->act_stride1 = L.ns1; v->cap0 = L.cap0; v->cap1 = L.cap1;
+    v->total = L.total;
+    return NF_OK;
+}
+
 extern "C" int nf_render_forward(const nf_render_args* a, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     NF_REQUIRE(a != nullptr, NF_E_INVALID, "nf_render_forward: null args");
@@ -1047,7 +1080,8 @@ extern "C" int nf_render_forward(const nf_render_args* a, void* stream_) {
     if (a->n_rays == 0) return NF_OK;
     NF_REQUIRE(a->n_rays > 0 && (size_t)a->n_rays * (a->n_coarse + NI) < (size_t)1 << 30, NF_E_UNSUPPORTED,
                "nf_render_forward: too many samples in one call (chunk the rays)");
-    const WsLayout L = ws_layout(a->n_rays, a->n_coarse, NI);
+    const bool save_nbr = (a->flags & NF_RENDER_SAVE_NEIGHBORS) != 0;
+    const WsLayout L = ws_layout(a->n_rays, a->n_coarse, NI, save_nbr ? a->K : 0);
     NF_REQUIRE(a->workspace_bytes >= L.total, NF_E_WORKSPACE, "nf_render_forward: workspace %zu < %zu",
                a->workspace_bytes, L.total);
     char* b = (char*)a->workspace;
@@ -1058,13 +1092,15 @@ extern "C" int nf_render_forward(const nf_render_args* a, void* stream_) {
     p.rays = a->rays;
     p.n_rays = a->n_rays;
     p.ro[0] = a->ro[0]; p.ro[1] = a->ro[1]; p.ro[2] = a->ro[2];
+    p.ro_dev = a->ro_dev;
     p.radius = a->radius;
     p.K = a->K;
     p.use_mask = a->use_mask; p.white_bg = a->white_background; p.mode = a->mode;
     {
-        // search tuning: compile-time defaults; the NF_* environment overrides exist for tests/gpu_tune.py and are
-        // read once per process unless NF_TUNE_LIVE is set
+        // search tuning: compile-time constants.  A build with -DNF_TUNING (tests/gpu_tune.py) reads NF_* environment
+        // overrides instead; the release library never looks at the environment.
         struct Tune { int solo_max_occ, peel_lanes, peel_from, sub_look; float sub_span_r; };
+#ifdef NF_TUNING
         auto read = [] {
             Tune t;
             t.solo_max_occ = env_int("NF_SOLO_MAX_OCC", 600);
@@ -1075,9 +1111,10 @@ extern "C" int nf_render_forward(const nf_render_args* a, void* stream_) {
             t.sub_span_r = span ? -(float)atof(span) : 3.5f;      // negative: absolute length, positive: multiples of r
             return t;
         };
-        static const bool live = getenv("NF_TUNE_LIVE") != nullptr;
-        static const Tune cached = read();
-        const Tune t = live ? read() : cached;
+        const Tune t = read();
+#else
+        const Tune t = {600, 4, 1536, 96, 3.5f};
+#endif
         p.solo_max_occ = t.solo_max_occ; p.peel_lanes = t.peel_lanes; p.peel_from = t.peel_from; p.sub_look = t.sub_look;
         p.sub_span = t.sub_span_r < 0.f ? -t.sub_span_r : t.sub_span_r * a->radius;
         NF_REQUIRE(a->search >= NF_SEARCH_AUTO && a->search <= NF_SEARCH_SWEEP, NF_E_INVALID, "nf_render_forward: search %d", a->search);
@@ -1099,6 +1136,8 @@ extern "C" int nf_render_forward(const nf_render_args* a, void* stream_) {
     p.z1 = (float*)(b + L.z1);
     p.rec0 = (float*)(b + L.rec0); p.rowid0 = (int*)(b + L.rowid0); p.out0 = (float4*)(b + L.out0); p.cap0 = L.cap0;
     p.rec1 = (float*)(b + L.rec1); p.rowid1 = (int*)(b + L.rowid1); p.out1 = (float4*)(b + L.out1); p.cap1 = L.cap1;
+    p.nbr0 = save_nbr ? (int*)(b + L.nbr0) : nullptr;
+    p.nbr1 = save_nbr ? (int*)(b + L.nbr1) : nullptr;
 
     NF_CUDA_OK(cudaMemsetAsync(p.counters, 0, 64, st));
     const int threads = WARPS_PER_BLOCK * 32;

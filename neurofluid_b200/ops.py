@@ -120,3 +120,101 @@ def img2mse(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
 def mse2psnr(mse: torch.Tensor) -> torch.Tensor:
     """-10 log10(mse) (trainer/trainer_e2e.py:25); stays on the device."""
     return -10.0 * torch.log10(mse)
+
+
+# ------------------------------------------------------------------------------------------------
+# open3d.ml.torch operator mirrors (SURVEY.md section 8b-2): swap only the layer, keep models/transmodel.py
+# ------------------------------------------------------------------------------------------------
+def reduce_subarrays_sum(values: torch.Tensor, row_splits: torch.Tensor) -> torch.Tensor:
+    """ml3d.ops.reduce_subarrays_sum (models/transmodel.py:135): segmented sum of `values` over CSR rows."""
+    cs = torch.cat([values.new_zeros(1, dtype=torch.float64), torch.cumsum(values.to(torch.float64), 0)])
+    return (cs[row_splits[1:]] - cs[row_splits[:-1]]).to(values.dtype)
+
+
+class ContinuousConv(torch.nn.Module):
+    """`open3d.ml.torch.layers.ContinuousConv` with the constructor arguments the reference passes
+    (models/transmodel.py:86-95) and its call signature `conv(inp_features, inp_positions, out_positions, extents)`
+    (:116,:118,:125); after a call `conv.nns.neighbors_index` (int32) / `.neighbors_row_splits` (int64) hold the
+    neighbour lists the reference reads at :135-138.  Runs nf_cconv_forward (one launch group per call); forward only.
+    Parameters / buffers as upstream: `kernel` (*kernel_size, in_channels, filters) ~ U(-0.05, 0.05), `bias`, `offset`."""
+
+    def __init__(self, in_channels, filters, kernel_size, activation=None, use_bias=True, align_corners=True,
+                 coordinate_mapping="ball_to_cube_radial", interpolation="linear", normalize=True,
+                 radius_search_ignore_query_points=False, radius_search_metric="L2", offset=None, window_function=None,
+                 use_dense_layer_for_center=False, operand_dtype="fp16", **kwargs):
+        super().__init__()
+        if list(kernel_size) != [4, 4, 4] or coordinate_mapping != "ball_to_cube_volume_preserving" \
+                or interpolation != "linear" or normalize or not align_corners or use_dense_layer_for_center \
+                or radius_search_metric != "L2":
+            raise _lib.NFError("ContinuousConv: only the configuration of models/transmodel.py:79-98 is implemented "
+                               "(4x4x4, linear, ball_to_cube_volume_preserving, normalize=False, L2)")
+        if lib().nf_cconv_packed_weights_bytes(int(in_channels), int(filters)) == 0:
+            raise _lib.NFError(f"ContinuousConv: {in_channels} -> {filters} channels is not a supported shape")
+        self.in_channels, self.filters, self.kernel_size = int(in_channels), int(filters), list(kernel_size)
+        self.activation = activation
+        self.window_function = window_function       # None or the reference's poly6 (the kernel evaluates poly6 itself)
+        self.radius_search_ignore_query_points = bool(radius_search_ignore_query_points)
+        self.kernel = torch.nn.Parameter(torch.empty(*kernel_size, in_channels, filters).uniform_(-0.05, 0.05))
+        self.bias = torch.nn.Parameter(torch.zeros(filters)) if use_bias else None
+        self.register_buffer("offset", torch.zeros(3) if offset is None else torch.as_tensor(offset).float())
+        self.operand_dtype = {"fp16": _lib.NF_DTYPE_F16, "bf16": _lib.NF_DTYPE_BF16}[operand_dtype]
+        self.nns = None
+        self._packed = None
+        self._ws = None
+        self._overflow = None
+
+    def _weights(self):
+        key = (self.kernel.data_ptr(), self.kernel._version, None if self.bias is None else self.bias._version,
+               self.offset._version)
+        if self._packed is None or self._packed[0] != key:
+            if bool((self.offset != 0).any()):
+                raise _lib.NFError("non-zero ContinuousConv.offset is not supported (the reference never sets it)")
+            k = self.kernel.detach().to(torch.float32).contiguous()
+            b = None if self.bias is None else self.bias.detach().to(torch.float32).contiguous()
+            require_cuda(k)
+            out = torch.empty(lib().nf_cconv_packed_weights_bytes(self.in_channels, self.filters), dtype=torch.uint8,
+                              device=k.device)
+            check(lib().nf_cconv_pack_weights(ptr(k), ptr(b), self.in_channels, self.filters, self.operand_dtype, ptr(out),
+                                              stream_ptr()), "nf_cconv_pack_weights")
+            out._keepalive = (k, b)
+            self._packed = (key, out)
+        return self._packed[1]
+
+    def forward(self, inp_features, inp_positions, out_positions, extents, inp_importance=None,
+                fixed_radius_search_hash_table=None, **unused):
+        from types import SimpleNamespace
+        require_cuda(inp_features, inp_positions, out_positions)
+        if inp_importance is not None:
+            raise _lib.NFError("ContinuousConv: inp_importance is not used by the reference and not implemented")
+        f = lambda t: t.detach().to(torch.float32).contiguous()
+        feat, ipos, opos = f(inp_features), f(inp_positions), f(out_positions)
+        extent = float(extents)
+        n_in, n_out = ipos.shape[0], opos.shape[0]
+        dev = opos.device
+        grid = fixed_radius_search_hash_table if isinstance(fixed_radius_search_hash_table, Grid) else \
+            Grid(ipos, float(CELL_SCALE * 0.5 * extent))
+        need = lib().nf_cconv_workspace_bytes(n_in, n_out, self.in_channels, self.filters)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        if self._overflow is None or self._overflow.device != dev:
+            self._overflow = torch.zeros(2, dtype=torch.int32, device=dev)
+        out = torch.empty((n_out, self.filters), dtype=torch.float32, device=dev)
+        counts = torch.empty((n_out,), dtype=torch.float32, device=dev)
+        nbr = torch.empty((n_out, 128), dtype=torch.int32, device=dev)
+        a = _lib.CConvArgs()
+        a.grid_in, a.in_feat, a.n_in, a.cin = ptr(grid.ws), ptr(feat), n_in, self.in_channels
+        a.out_pos, a.n_out, a.cout = ptr(opos), n_out, self.filters
+        a.extent, a.use_window = extent, int(self.window_function is not None)
+        a.ignore_same, a.dtype = int(self.radius_search_ignore_query_points), self.operand_dtype
+        a.weights, a.out, a.count_out, a.nbr_index_out = ptr(self._weights()), ptr(out), ptr(counts), ptr(nbr)
+        a.overflow_out = ptr(self._overflow)
+        a.workspace, a.workspace_bytes = ptr(self._ws), self._ws.numel()
+        check(lib().nf_cconv_forward(C.byref(a), stream_ptr()), "nf_cconv_forward")
+        self._keep = (grid, feat, ipos, opos)
+        valid = nbr >= 0
+        row_splits = torch.zeros(n_out + 1, dtype=torch.int64, device=dev)
+        row_splits[1:] = torch.cumsum(valid.sum(1), 0)
+        self.nns = SimpleNamespace(neighbors_index=nbr[valid], neighbors_row_splits=row_splits, neighbor_counts=counts)
+        if self.activation is not None:
+            out = self.activation(out)
+        return _lib.forward_only([inp_features, self.kernel], (out,))[0]

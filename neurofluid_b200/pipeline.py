@@ -30,20 +30,25 @@ def render_image(renderer, particle_pos, N_ray, ro, rays, focal_length, cw, ray_
     for ray_idx in range(0, N_ray, chunk):
         r = renderer(particle_pos, ro, rays[ray_idx:ray_idx + chunk], focal_length, cw)
         acc["pred_rgbs_0"].append(r["rgb0"])
-        acc["num_nn_0"].append(r["num_nn_0"].view(-1))
+        if "num_nn_0" in r:                      # absent when the renderer was told to skip them (return_num_nn=False)
+            acc["num_nn_0"].append(r["num_nn_0"].view(-1))
         if iseval:
             acc["mask_0"].append(r["mask_0"])
         if fine:
             acc["pred_rgbs_1"].append(r["rgb1"])
-            acc["num_nn_1"].append(r["num_nn_1"].view(-1))
+            if "num_nn_1" in r:
+                acc["num_nn_1"].append(r["num_nn_1"].view(-1))
             if iseval:
                 acc["mask_1"].append(r["mask_1"])
-    ret = {"pred_rgbs_0": torch.cat(acc["pred_rgbs_0"], 0), "num_nn_0": torch.cat(acc["num_nn_0"], 0)}
+    ret = {"pred_rgbs_0": torch.cat(acc["pred_rgbs_0"], 0)}
+    if acc["num_nn_0"]:
+        ret["num_nn_0"] = torch.cat(acc["num_nn_0"], 0)
     if iseval:
         ret["mask_0"] = torch.cat(acc["mask_0"], 0)
     if fine:
         ret["pred_rgbs_1"] = torch.cat(acc["pred_rgbs_1"], 0)
-        ret["num_nn_1"] = torch.cat(acc["num_nn_1"], 0)
+        if acc["num_nn_1"]:
+            ret["num_nn_1"] = torch.cat(acc["num_nn_1"], 0)
         if iseval:
             ret["mask_1"] = torch.cat(acc["mask_1"], 0)
     return ret
@@ -151,7 +156,10 @@ def rollout_and_render(transition_model, renderer, pos, vel, box, box_normals, c
     of `group`; the transition model runs replicated (`transition="replicated"`, the throughput-optimal layout of
     SURVEY.md section 8e) or particle-block sharded with an NCCL all-gather per layer and of the positions per step
     (`transition="sharded"`, BASELINE.json's north_star layout; bit-identical results).  The returned images are
-    the local rows unless `keep_images`, which all-gathers them.  Nothing in the loop synchronises with the host."""
+    the local rows unless `keep_images`, which all-gathers them.  The loop issues no host synchronisation (the camera
+    position is read from device memory, the particle grid and workspaces are cached); the neighbour-overflow check
+    after the last frame is the one sync of the rollout.  The per-sample neighbour counts (`num_nn_*`, which the
+    reference's eval loop never reads) are not materialised here."""
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -166,6 +174,7 @@ def rollout_and_render(transition_model, renderer, pos, vel, box, box_normals, c
     rays = [shard_rows(ops.generate_rays(H, W, f, c2w).view(H, W, 6), rank, world).reshape(-1, 6).contiguous()
             for c2w, f in cams]
     frames, psnr, pos_hist = [], [], []
+    want_nn, renderer.return_num_nn = getattr(renderer, "return_num_nn", True), False
     for fidx in range(n_frames):
         if transition == "sharded" and world > 1:
             pos, vel, _ = transition_step_sharded(transition_model, pos, vel, box, box_normals, group)
@@ -188,6 +197,7 @@ def rollout_and_render(transition_model, renderer, pos, vel, box, box_normals, c
             views.append(img)
         frames.append(views)
         pos_hist.append(pos)
+    renderer.return_num_nn = want_nn
     if hasattr(transition_model, "check_neighbor_overflow"):
         transition_model.check_neighbor_overflow()               # the one host sync of the rollout
     out = {"positions": pos_hist, "images": frames, "fluid_errors": fe}

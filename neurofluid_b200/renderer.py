@@ -55,7 +55,12 @@ class RenderNet(nn.Module):
         self._packed = {}      # net name -> (version key, packed tensor)
         self._ws = None
         self._tables = {}
+        self._grid_cache = None    # (key, Grid, particles tensor kept alive so that its address cannot be reused)
         self.last_stats = None
+        self.return_num_nn = True  # False: skip the int64 num_nn_* tensors (20 % of the fine stage's DRAM writes);
+                                   # evaluation loops that only read rgb / mask switch it off (pipeline.rollout_and_render)
+        self.save_neighbors = False  # True: keep every record row's neighbour list (debug_view(); parity tests)
+        self._debug = None
 
     # ------------------------------------------------------------------ reference helpers
     def set_ro(self, cw):
@@ -80,11 +85,43 @@ class RenderNet(nn.Module):
             self._tables[key] = (z.float().to(device), u.float().to(device))
         return self._tables[key]
 
-    def _workspace(self, n_rays, n_imp, device):
-        need = lib().nf_render_workspace_bytes(n_rays, self.N_samples, n_imp)
+    def _workspace(self, n_rays, n_imp, device, flags=0):
+        need = lib().nf_render_workspace_bytes_ex(n_rays, self.N_samples, n_imp, int(self.num_neighbor), int(flags))
         if self._ws is None or self._ws.numel() < need or self._ws.device != device:
             self._ws = torch.empty(need, dtype=torch.uint8, device=device)
         return self._ws
+
+    def _grid(self, particles):
+        """Cell-sorted grid of the particle set, rebuilt only when the tensor changes: a caller that renders one
+        particle set in many ray chunks (trainer/basetrainer.py:282-289: 625 chunks per 800x800 image) builds it once."""
+        key = (particles.data_ptr(), particles._version, tuple(particles.shape), str(particles.device), float(self.raduis))
+        hit = self._grid_cache
+        if hit is None or hit[0] != key:
+            self._grid_cache = (key, Grid(particles, CELL_SCALE * self.raduis), particles)
+        return self._grid_cache[1]
+
+    def debug_view(self):
+        """After a forward with `save_neighbors=True` (single launch): the evaluated rows of both passes as tensors --
+        {"rec0","rowid0","nbr0","rec1","rowid1","nbr1"}: geometry records (rows,16), rowid = ray*S + sample, neighbour
+        indices (rows,K) int32, -1 padded (the production search's answer; tests compare it with the oracle)."""
+        if self._debug is None:
+            raise NFError("debug_view(): run a forward with save_neighbors=True first")
+        ws, R, NI = self._debug
+        v = _lib.RenderWsView()
+        check(lib().nf_render_workspace_view(R, self.N_samples, NI, int(self.num_neighbor), _lib.NF_RENDER_SAVE_NEIGHBORS,
+                                             C.byref(v)), "nf_render_workspace_view")
+        cnt = ws[v.counters: v.counters + 64].view(torch.int32).tolist()
+        K = int(self.num_neighbor)
+        out = {}
+        for tag, n in (("0", cnt[0]), ("1", cnt[1] if NI > 0 else 0)):
+            rec, rid, nbr = getattr(v, "rec" + tag), getattr(v, "rowid" + tag), getattr(v, "nbr" + tag)
+            out["rec" + tag] = ws[rec: rec + n * 64].view(torch.float32).view(n, 16).clone()
+            out["rowid" + tag] = ws[rid: rid + n * 4].view(torch.int32).clone()
+            out["nbr" + tag] = ws[nbr: nbr + n * K * 4].view(torch.int32).view(n, K).clone()
+        if NI > 0:
+            S1 = self.N_samples + NI
+            out["z1"] = ws[v.z1: v.z1 + R * S1 * 4].view(torch.float32).view(R, S1).clone()   # merged depths (rays that miss: unset)
+        return out
 
     def _run(self, mode, physical_particles, ro, rays, use_disp, perturb, noise_std, white_background):
         if perturb != 0 or noise_std != 0:
@@ -94,7 +131,10 @@ class RenderNet(nn.Module):
         dev = rays.device
         particles = physical_particles.detach().to(torch.float32).contiguous()
         rays = rays.detach().to(torch.float32).contiguous()
-        ro_host = [float(v) for v in ro.detach().float().cpu().tolist()]
+        # the camera position stays on the device (no stream drain per call); a CPU tensor / list is passed by value
+        ro_t = torch.as_tensor(ro).detach()
+        ro_dev = ro_t.to(torch.float32).contiguous() if ro_t.is_cuda else None
+        ro_host = [0.0, 0.0, 0.0] if ro_dev is not None else [float(v) for v in ro_t.float().tolist()]
         R, S0 = rays.shape[0], self.N_samples
         fine = mode != _lib.NF_RENDER_COARSE
         NI = self.N_importance if fine else 0
@@ -104,7 +144,7 @@ class RenderNet(nn.Module):
             mode, fine, NI = _lib.NF_RENDER_COARSE, False, 0
         S1 = S0 + NI
         z_tab, u_tab = self._sample_tables(dev, use_disp)
-        grid = Grid(particles, CELL_SCALE * self.raduis)
+        grid = self._grid(particles)
         wc = self._packed_weights("nerf_coarse")
         wf = self._packed_weights("nerf_fine") if fine else None
         want0 = mode != _lib.NF_RENDER_FINE
@@ -114,16 +154,21 @@ class RenderNet(nn.Module):
             out["rgb0"] = torch.empty((R, 3), **f32)
             out["depth0"] = torch.empty((R,), **f32)
             out["opacity0"] = torch.empty((R,), **f32)
-            out["num_nn_0"] = torch.empty((R, S0, 1), dtype=torch.int64, device=dev)
+            if self.return_num_nn:
+                out["num_nn_0"] = torch.empty((R, S0, 1), dtype=torch.int64, device=dev)
             out["mask_0"] = torch.empty((R, 1), **f32)
         if fine:
             out["rgb1"] = torch.empty((R, 3), **f32)
             out["depth1"] = torch.empty((R,), **f32)
             out["opacity1"] = torch.empty((R,), **f32)
-            out["num_nn_1"] = torch.empty((R, S1, 1), dtype=torch.int64, device=dev)
+            if self.return_num_nn:
+                out["num_nn_1"] = torch.empty((R, S1, 1), dtype=torch.int64, device=dev)
             out["mask_1"] = torch.empty((R, 1), **f32)
         chunk = max(1, min(self.max_rays_per_launch, R))
-        ws = self._workspace(chunk, NI, dev)
+        flags = _lib.NF_RENDER_SAVE_NEIGHBORS if self.save_neighbors else 0
+        if self.save_neighbors and R > chunk:
+            raise NFError("save_neighbors needs the whole call in one launch (raise max_rays_per_launch)")
+        ws = self._workspace(chunk, NI, dev, flags)
         nchunks = (R + chunk - 1) // chunk
         stats = torch.zeros((max(nchunks, 1), 16), dtype=torch.int32, device=dev)
         st = stream_ptr()
@@ -133,6 +178,8 @@ class RenderNet(nn.Module):
             a.grid_ws, a.particles, a.n_particles = ptr(grid.ws), ptr(particles), particles.shape[0]
             a.rays, a.n_rays = C.c_void_p(rays.data_ptr() + r0 * 24), r1 - r0
             a.ro = (C.c_float * 3)(*ro_host)
+            a.ro_dev = ptr(ro_dev)
+            a.flags = flags
             a.z_coarse, a.u_importance, a.n_coarse, a.n_importance = ptr(z_tab), ptr(u_tab), S0, NI
             a.radius, a.K, a.search = float(self.raduis), int(self.num_neighbor), self.search
             a.mode, a.use_mask, a.white_background = int(mode), int(bool(self.cfg.use_mask)), int(bool(white_background))
@@ -150,7 +197,8 @@ class RenderNet(nn.Module):
             a.stats = C.c_void_p(stats.data_ptr() + ci * 64)
             check(lib().nf_render_forward(C.byref(a), st), "nf_render_forward")
         self.last_stats = stats       # device tensor; .sum(0) = [rows0, rows1, active0, active1]
-        self._keep = (grid, particles, rays)
+        self._keep = (grid, particles, rays, ro_dev)
+        self._debug = (ws, R, NI) if self.save_neighbors and R > 0 else None
         return _lib.forward_only([physical_particles, *self.parameters()], out)
 
     # ------------------------------------------------------------------ reference API

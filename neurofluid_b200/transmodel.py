@@ -63,6 +63,8 @@ class ParticleNet(nn.Module):
         self.num_fluid_neighbors = None
         self.pos_correction = None
         self._overflow = None      # device int32[2]: particles whose fluid / box neighbour list was truncated
+        self._ovf_host = None      # pinned int32[2] + event: the counter is copied out after every step and looked at
+        self._ovf_event = None     # (without blocking) at the start of the next one
 
     # ------------------------------------------------------------------ internals
     def ordered_params(self):
@@ -129,14 +131,45 @@ class ParticleNet(nn.Module):
             self._box_grid_cache = (key, Grid(box, cell), box)
         return self._box_grid_cache[1]
 
-    def check_neighbor_overflow(self):
-        """The kernels keep at most 128 fluid and 128 box neighbours per particle (the reference has no cap).  Returns
-        silently while no list was ever truncated, raises otherwise.  Synchronises: call it once per rollout."""
-        if self._overflow is not None:
-            nf, nb = self._overflow.tolist()
+    def _raise_overflow(self, nf, nb):
+        self._overflow.zero_()      # one report per incident: later rollouts start clean
+        raise NFError(f"neighbour lists truncated at 128 entries for {nf} (fluid) / {nb} (box) particle-steps: "
+                      "results differ from the reference (Open3D's FixedRadiusSearch has no cap); the scene is denser "
+                      "than the kernels support")
+
+    def _poll_overflow(self):
+        """Non-blocking look at the overflow counter copied out after the previous step: a truncated neighbour list
+        surfaces as an NFError on the next `forward` at the latest, without a device synchronisation per step."""
+        ev = self._ovf_event
+        if ev is not None and ev.query():
+            self._ovf_event = None
+            nf, nb = self._ovf_host.tolist()
             if nf or nb:
-                raise NFError(f"neighbour lists truncated at 128 entries for {nf} (fluid) / {nb} (box) particle-steps: "
-                              "results differ from the reference; the scene is denser than the kernels support")
+                self._raise_overflow(nf, nb)
+
+    def _post_overflow(self):
+        if self._ovf_host is None:
+            self._ovf_host = torch.zeros(2, dtype=torch.int32).pin_memory()
+        if self._ovf_event is None:           # the previous copy has been consumed: the pinned buffer is free again
+            self._ovf_host.copy_(self._overflow, non_blocking=True)
+            self._ovf_event = torch.cuda.Event()
+            self._ovf_event.record()
+
+    def check_neighbor_overflow(self, group=None):
+        """The kernels keep at most 128 fluid and 128 box neighbours per particle (the reference has no cap).  Returns
+        silently while no list was truncated since the last check, raises otherwise (and clears the counter).
+        Synchronises.  With torch.distributed initialised every rank of `group` sees the sum over ranks, so a sharded
+        rollout fails on all ranks together instead of leaving the others inside the next collective."""
+        if self._overflow is None:
+            return
+        import torch.distributed as dist
+        cnt = self._overflow.clone()
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(cnt, group=group)
+        self._ovf_event = None
+        nf, nb = cnt.tolist()
+        if nf or nb:
+            self._raise_overflow(nf, nb)
 
     def _prepare(self, pos, vel, box, box_feats, feats):
         if feats is not None:
@@ -155,13 +188,19 @@ class ParticleNet(nn.Module):
 
     # ------------------------------------------------------------------ reference API
     def forward(self, pos, vel, box, box_feats, feats=None, fixed_radius_search_hash_table=None, debug=None):
-        """models/transmodel.py:151-163.  `fixed_radius_search_hash_table` is accepted and ignored, as upstream."""
+        """models/transmodel.py:151-163.  `fixed_radius_search_hash_table` is accepted and ignored, as upstream.
+
+        Neighbour lists hold at most 128 fluid and 128 box neighbours per particle (Open3D has no cap; a 0.05-spaced
+        fluid has ~42).  If a list is ever truncated, `num_fluid_neighbors` still reports the true count, and an NFError
+        is raised by the next `forward` (non-blocking poll) or by `check_neighbor_overflow()` (blocking)."""
+        self._poll_overflow()
         pos_in, vel_in = pos, vel
         pos, vel, box, box_feats, outs, ws = self._prepare(pos, vel, box, box_feats, feats)
         if debug is not None:
             debug["feats0"] = torch.empty((pos.shape[0], 96), device=pos.device)
         a = self._args(pos, vel, box, box_feats, outs, ws, debug=debug)
         check(lib().nf_transition_step(C.byref(a), stream_ptr()), "nf_transition_step")
+        self._post_overflow()
         self.num_fluid_neighbors, self.pos_correction = outs[2], outs[3]
         self._keep = (pos, vel, box, box_feats)
         return _lib.forward_only([pos_in, vel_in, *self.parameters()], (outs[0], outs[1], outs[2]))
@@ -170,27 +209,3 @@ class ParticleNet(nn.Module):
 
 
 TransModel = ParticleNet
-
-
-def smoke_check(dev):
-    """One small step on `dev` checked against the CPU oracle (used by __graft_entry__.smoke)."""
-    from . import scenes
-    from oracle import transition as otrans
-    sd = scenes.init_particle_state(0)
-    net = ParticleNet(gravity=(0.0, 0.0, -9.81))
-    net.load_state_dict(sd)
-    net = net.to(dev)
-    half = 7 / 2 * 0.05
-    pos = torch.from_numpy(scenes.lattice_particles(8, 0, center=(0.0, 0.0, -1 + 0.03 + half)))
-    vel = torch.zeros_like(pos)
-    bp, bn = scenes.box_points(0.1)
-    box, box_n = torch.from_numpy(bp), torch.from_numpy(bn)
-    p1, v1, nn1 = net(pos.to(dev), vel.to(dev), box.to(dev), box_n.to(dev))
-    torch.cuda.synchronize()
-    net.check_neighbor_overflow()
-    rp, rv, rn, dbg = otrans.particle_step(sd, pos, vel, box, box_n, debug=True)
-    assert torch.equal(nn1.cpu(), rn), "fluid neighbour counts differ from the oracle"
-    err = float(torch.norm(net.pos_correction.cpu() - dbg["feats"][-1] / 128) / torch.norm(dbg["feats"][-1] / 128))
-    assert err < 5e-3, err
-    assert float(torch.norm(p1.cpu() - rp) / torch.norm(rp)) < 1e-6
-    print("smoke: transition ok (position-correction rel L2 %.2e)" % err)

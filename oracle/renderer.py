@@ -130,6 +130,25 @@ def importance_samples(z, weights, n_importance, rays):
     return xyz, z_all
 
 
+# the 16 raw (not yet encoded) values per sample behind the feature row of models/renderer.py:125-179, in the column
+# order the CUDA path stores them: [x(3), density, smoothed(3), variance(3), ray dir(3), smoothed dir(3)]
+def local_geometry_records(d2, nn, xyz, rays, ro, radius):
+    R, S, K = d2.shape
+    valid = d2 != 0
+    num_nn = valid.sum(-1, keepdim=True)
+    dist = torch.norm(nn - xyz.unsqueeze(-2), dim=-1)                       # :97-98 (padded slots sit at the origin)
+    w = torch.clamp(1 - (dist / radius) ** 3, min=0)
+    density = w.sum(-1, keepdim=True)
+    smoothed = (w.unsqueeze(-1) * nn).sum(-2) / (density + 1e-12)
+    sdir = smoothed - ro.view(1, 1, 3)
+    sdir = sdir / torch.norm(sdir, dim=-1, keepdim=True)
+    v = (nn - xyz.unsqueeze(-2)) * valid.unsqueeze(-1)                      # :160-166 two-pass variance
+    mean = v.sum(-2) / (num_nn + 1e-12)
+    var = (((v - mean.unsqueeze(-2)) ** 2) * valid.unsqueeze(-1)).sum(-2) / (num_nn + 1e-12)
+    rd = rays[:, None, 3:6].expand(R, S, 3)
+    return torch.cat([xyz, density, smoothed, var, rd, sdir], -1)
+
+
 def feature_widths(enc):
     in_xyz = 63 + (9 if enc.density else 0) + (63 if enc.var else 0) + (63 if enc.smoothed_pos else 0)
     in_dir = 27 + (27 if enc.smoothed_dir else 0)

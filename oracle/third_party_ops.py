@@ -56,8 +56,18 @@ def _lib():
     return _LIB
 
 
+_DEFAULT_THREADS = 0
+
+
+def set_default_threads(n: int) -> None:
+    """Thread count the compiled operators use when a call passes nthreads=0.  bench.py sets it to the host's core count:
+    torchrun exports OMP_NUM_THREADS=1, which would otherwise make the CPU baseline single-threaded."""
+    global _DEFAULT_THREADS
+    _DEFAULT_THREADS = int(n)
+
+
 def max_threads() -> int:
-    return int(_lib().nfo_max_threads())
+    return _DEFAULT_THREADS if _DEFAULT_THREADS > 0 else int(_lib().nfo_max_threads())
 
 
 def _f32(t: torch.Tensor) -> torch.Tensor:
@@ -77,7 +87,7 @@ def ball_query_shared(queries: torch.Tensor, points: torch.Tensor, K: int, radiu
     idx = torch.empty((nq, K), dtype=torch.int64)
     d2 = torch.empty((nq, K), dtype=torch.float32)
     _lib().nfo_ball_query(q.data_ptr(), nq, p.data_ptr(), p.shape[0], float(radius), int(K), idx.data_ptr(),
-                          d2.data_ptr(), int(nthreads))
+                          d2.data_ptr(), int(nthreads or _DEFAULT_THREADS))
     return d2, idx
 
 
@@ -158,6 +168,7 @@ def radius_search(in_pos, out_pos, radius, ignore_same_pos=True, nthreads=0):
     n_out = op.shape[0]
     counts = torch.zeros(n_out, dtype=torch.int64)
     lib = _lib()
+    nthreads = nthreads or _DEFAULT_THREADS
     lib.nfo_radius_search(ip.data_ptr(), ip.shape[0], op.data_ptr(), n_out, float(radius), int(ignore_same_pos),
                           counts.data_ptr(), None, None, None, int(nthreads))
     rs = torch.zeros(n_out + 1, dtype=torch.int64)
@@ -251,7 +262,7 @@ def cconv_forward(in_feat, in_pos, out_pos, extent, kernel, bias, offset, ignore
     _lib().nfo_cconv_forward(ip.data_ptr(), ft.data_ptr(), ip.shape[0], cin, op.data_ptr(), op.shape[0],
                              float(extent), size, kr.data_ptr(), b.data_ptr() if b is not None else None,
                              off.data_ptr(), cout, int(ignore_same_pos), int(use_window), out.data_ptr(),
-                             counts.data_ptr(), int(nthreads))
+                             counts.data_ptr(), int(nthreads or _DEFAULT_THREADS))
     return out, counts
 
 

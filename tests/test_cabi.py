@@ -37,13 +37,31 @@ def test_size_queries_and_version_without_device():
     assert L.nf_render_workspace_bytes(0, 64, 128) == 0
 
 
-def test_struct_layout_matches_header():
-    # nf_render_args: 32 fields; pointers are 8-byte aligned -> size is a multiple of 8 and stable
-    assert ctypes.sizeof(_lib.RenderArgs) % 8 == 0
-    assert _lib.RenderArgs.rays.offset == 24 and _lib.RenderArgs.ro.offset == 36
-    assert _lib.RenderArgs.z_coarse.offset == 48 and _lib.RenderArgs.weights_coarse.offset == 104
-    assert _lib.RenderArgs.workspace.offset == 200 and _lib.RenderArgs.stats.offset == 216
-    assert ctypes.sizeof(_lib.RenderArgs) == 224
+STRUCTS = {"nf_render_args": "RenderArgs", "nf_transition_args": "TransitionArgs", "nf_render_ws_view": "RenderWsView",
+           "nf_cconv_args": "CConvArgs"}
+
+
+def test_struct_layout_matches_header(tmp_path):
+    """Every ctypes mirror has the size and field offsets the C compiler gives the header's struct (gcc compiles a
+    probe that prints offsetof() for every field)."""
+    import subprocess
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "nf_b200.h"', 'int main(void) {']
+    for cname, pyname in STRUCTS.items():
+        cls = getattr(_lib, pyname)
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['return 0; }']
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, pyname in STRUCTS.items():
+        cls = getattr(_lib, pyname)
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
 
 
 def test_rendernet_state_dict_layout_and_errors():

@@ -121,3 +121,63 @@ def test_rollout_and_render_is_the_eval_loop(dev):
     out2 = pipeline.rollout_and_render(tn, rn, pos, vel, box, box_n, cams[:1], H, W, 1, gt_positions=shifted)
     e = out2["fluid_errors"].errors[1]
     assert abs(e["mean"] - 4.0) < 1e-3 and e["gt2pred_mean"] <= e["mean"] + 1e-6
+
+
+def test_config3_rollout_and_render_against_the_oracle(dev):
+    """BASELINE config[3] shape (eval_e2e.py:58-120: per frame one transition step, then a rendered view) against the
+    CPU oracle running the same loop on its OWN trajectory: 23^3 = 12,167 particles, 3 frames, a strided sample of the
+    400x400 image per frame.  Positions <= 1e-5, rgb <= 1e-3 relative L2 (north_star)."""
+    from oracle import renderer as orender
+    from oracle import transition as otrans
+    from helpers import rel_l2
+    n, H = 23, 400
+    half = (n - 1) / 2 * 0.05
+    sd_t, sd_r, cfg = scenes.init_particle_state(0), scenes.init_render_state(0, 5.0), scenes.render_cfg()
+    tn = nb.ParticleNet(gravity=(0.0, 0.0, -9.81)); tn.load_state_dict(sd_t); tn = tn.to(dev)
+    rn = nb.RenderNet(cfg, scenes.NEAR, scenes.FAR); rn.load_state_dict(sd_r); rn = rn.to(dev)
+    pos = torch.from_numpy(scenes.lattice_particles(n, 0, center=(0.0, 0.0, -1 + 0.03 + half)))
+    vel = torch.zeros_like(pos)
+    bp, bn = scenes.box_points(0.032)
+    box, box_n = torch.from_numpy(bp), torch.from_numpy(bn)
+    rays, focal, cw = scenes.camera_rays(H, H)
+    cw = cw.clone(); cw[2, 3] += -1 + 0.03 + half                  # aim the camera at the block on the box floor
+    out = pipeline.rollout_and_render(tn, rn, pos.to(dev), vel.to(dev), box.to(dev), box_n.to(dev), [(cw, focal)], H, H, 3)
+    rays = ops.generate_rays(H, H, focal, cw.to(dev)).cpu()
+    sel = torch.arange(0, H * H, (H * H) // 300)[:300]
+    op, ov = pos, vel
+    for f in range(3):
+        op, ov, _ = otrans.particle_step(sd_t, op, ov, box, box_n)
+        assert rel_l2(out["positions"][f].cpu(), op) < 1e-5, f
+        ref = orender.render_forward(sd_r, cfg, scenes.NEAR, scenes.FAR, op, cw[:, 3], rays[sel])
+        got = out["images"][f][0].cpu()[sel]
+        assert (ref["rgb1"] < 0.999).any()                         # the sample does see the fluid
+        assert rel_l2(got, ref["rgb1"]) < 1e-3, (f, rel_l2(got, ref["rgb1"]))
+
+
+def test_config4_50k_particles_800x800_spot_check(dev):
+    """BASELINE config[4] size on one GPU: 37^3 = 50,653 particles (the sweep search's bitmap grows with P: fewer
+    resident blocks), whole 800x800 image in one call, 512 strided rays against the CPU oracle."""
+    from oracle import renderer as orender
+    from helpers import rel_l2
+    H = 800
+    rays, focal, cw = scenes.camera_rays(H, H)
+    particles = torch.from_numpy(scenes.lattice_particles(37, 0))
+    cfg, sd = scenes.render_cfg(), scenes.init_render_state(0, 5.0)
+    net = nb.RenderNet(cfg, scenes.NEAR, scenes.FAR); net.load_state_dict(sd); net = net.to(dev)
+    out = net(particles.to(dev), cw[:, 3].to(dev), rays.to(dev), focal, cw.to(dev))
+    o = {k: v.cpu() for k, v in out.items()}
+    assert torch.isfinite(o["rgb1"]).all()
+    assert torch.equal(o["mask_1"].view(-1), (o["num_nn_1"] == 20).sum(1).view(-1).float())
+    sel = torch.arange(0, H * H, (H * H) // 512)[:512]
+    ref = orender.render_forward(sd, cfg, scenes.NEAR, scenes.FAR, particles, cw[:, 3], rays[sel])
+    assert torch.equal(o["num_nn_0"][sel], ref["num_nn_0"])
+    assert (ref["num_nn_0"] == 20).any()
+    assert rel_l2(o["rgb0"][sel], ref["rgb0"]) < 1e-3 and rel_l2(o["rgb1"][sel], ref["rgb1"]) < 1e-3
+    assert (o["num_nn_1"][sel] != ref["num_nn_1"]).float().mean() < 2e-4
+    # both search flavours at this size, on the rays through the fluid
+    sub = rays.view(H, H, 6)[300:500:4, 300:500:4].reshape(-1, 6).contiguous()
+    a = nb.RenderNet(cfg, scenes.NEAR, scenes.FAR, search="stream"); a.load_state_dict(sd); a = a.to(dev)
+    ra = a(particles.to(dev), cw[:, 3].to(dev), sub.to(dev), focal, cw.to(dev))
+    rb = net(particles.to(dev), cw[:, 3].to(dev), sub.to(dev), focal, cw.to(dev))
+    for k in ra:
+        assert torch.equal(ra[k], rb[k]), k

@@ -123,6 +123,46 @@ def test_render_forward_matches_reference_golden(dev, name):
     assert rel_l2(fi["rgb1"].cpu(), g["forward.rgb1"]) < RGB_TOL
 
 
+@pytest.mark.parametrize("search", ["sweep", "stream"])
+@pytest.mark.parametrize("name", RENDER_CASES)
+def test_production_search_sets_and_records_vs_oracle(dev, name, search):
+    """The searches the renderer actually runs (search_scs / search_stream inside k_stage_q0 / k_stage_mid), not the
+    standalone nf_ballquery_firstk: every evaluated sample's neighbour list must equal pytorch3d's first-K-by-index
+    answer bit for bit, and its 16-float geometry record (models/renderer.py:96-109,125-179) must match the oracle's
+    two-pass fp32 arithmetic to 1e-5.  use_mask=False makes every sample a record row, so partial neighbourhoods (and
+    the padded-slot-at-origin quirk) are covered as well; the fine pass is checked on the kernel's own merged depths
+    (they depend on fp16-operand sigmas, the sets given the depths do not)."""
+    c = load_render_case(name)
+    K, radius = 20, 0.225
+    R = c["rays"].shape[0]
+    for use_mask in sorted({bool(c["g"]["use_mask"]), False}):
+        cfg = scenes.render_cfg(use_mask=use_mask)
+        net = make_net(cfg, c["sd"], dev, search=search)
+        net.save_neighbors = True
+        out = net(c["particles"].to(dev), c["ro"].to(dev), c["rays"].to(dev), 0.0, c["cw"].to(dev))
+        dbg = {k: v.cpu() for k, v in net.debug_view().items()}
+        z0, xyz0 = orender.coarse_samples(scenes.NEAR, scenes.FAR, c["rays"], 64)
+        hit = (out["num_nn_1"].sum((1, 2)) + out["num_nn_0"].sum((1, 2)) > 0).cpu()      # rays whose merged depths exist
+        z1 = torch.where(hit[:, None], dbg["z1"], torch.zeros_like(dbg["z1"])) if use_mask else dbg["z1"]
+        xyz1 = c["rays"][:, None, 0:3] + c["rays"][:, None, 3:6] * z1[:, :, None]
+        for tag, xyz in (("0", xyz0), ("1", xyz1)):
+            S = xyz.shape[1]
+            d2, idx, nn = orender.search(xyz, c["particles"], radius, K)
+            rid = dbg["rowid" + tag].long()
+            assert rid.numel() == (R * S if not use_mask else int((idx >= 0).all(-1).sum())), (tag, use_mask)
+            assert rid.unique().numel() == rid.numel()
+            ray, smp = rid // S, rid % S
+            assert torch.equal(dbg["nbr" + tag].long(), idx[ray, smp]), (tag, use_mask)       # sets AND order, bit exact
+            ref = orender.local_geometry_records(d2, nn, xyz, c["rays"], c["ro"], radius)[ray, smp]
+            got = dbg["rec" + tag]
+            assert torch.equal(got[:, 0:3], ref[:, 0:3])                                      # sample positions, bit exact
+            for name_, sl, tol in (("density", slice(3, 4), 1e-5), ("smoothed", slice(4, 7), 1e-5), ("variance", slice(7, 10), 1e-4),
+                                   ("ray dir", slice(10, 13), 1e-6), ("smoothed dir", slice(13, 16), 1e-5)):
+                assert rel_l2(got[:, sl], ref[:, sl]) < tol, (tag, use_mask, name_, rel_l2(got[:, sl], ref[:, sl]))
+            # per-row worst case of the one-pass variance against the reference's two-pass form
+            assert float((got[:, 7:10] - ref[:, 7:10]).abs().max()) < 1e-6 + 1e-4 * float(ref[:, 7:10].abs().max())
+
+
 def test_render_chunking_and_ray_order_invariance(dev):
     c = load_render_case("cfg0_sub")
     args = lambda rays: (c["particles"].to(dev), c["ro"].to(dev), rays.to(dev), 0.0, c["cw"].to(dev))
