@@ -164,7 +164,7 @@ typedef struct nf_render_args {
  * nf_render_backward reads them).  Row r of rec/rowid/nbr (r < counters[0] coarse, counters[1] fine) is one evaluated
  * sample: rec (16 floats, layout of nf_nerf_mlp_forward), rowid = ray * S + sample, nbr = K neighbour indices (-1 padded). */
 typedef struct nf_render_ws_view {
-    size_t counters, act0, act1, z1, rec0, rowid0, out0, rec1, rowid1, out1, nbr0, nbr1, total;
+    size_t counters, act0, act1, z1, rec0, rowid0, out0, rec1, rowid1, out1, nbr0, nbr1, miss, total;
     int32_t act_stride0, act_stride1, cap0, cap1;
 } nf_render_ws_view;
 
@@ -172,6 +172,51 @@ NF_API size_t nf_render_workspace_bytes(int n_rays, int n_coarse, int n_importan
 NF_API size_t nf_render_workspace_bytes_ex(int n_rays, int n_coarse, int n_importance, int K, int flags);
 NF_API int nf_render_workspace_view(int n_rays, int n_coarse, int n_importance, int K, int flags, nf_render_ws_view* view_host);
 NF_API int nf_render_forward(const nf_render_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Renderer backward (training)
+ * replaces: autograd through RenderNet.forward, i.e. loss.backward() at trainer/trainer_e2e.py:277 and
+ *           trainer/trainer_renderer.py:96: gradients w.r.t. both NeRF MLPs' parameters and w.r.t. the particle positions
+ *           (through the K neighbour positions of every evaluated sample; sample positions are detached,
+ *           utils/ray_utils.py:224).
+ * Parameter gradients use one flat fp32 buffer per network of nf_render_param_count() floats: the 24 tensors of
+ * nf_render_pack_weights in the same order (weight (out,in) row-major, then bias), concatenated.  All gradient outputs are
+ * ACCUMULATED into (zero them first).  nf_render_backward synchronises the stream once (it reads the row counts).
+ * ------------------------------------------------------------------------------------------- */
+NF_API size_t nf_render_param_count(void);
+NF_API size_t nf_render_packed_weights_bwd_bytes(void);
+/* transposed bf16 weight slabs for the data-gradient GEMMs; params as for nf_render_pack_weights */
+NF_API int nf_render_pack_weights_bwd(const float* const* params_host /*[24] device pointers*/, void* packed_out, void* stream);
+/* Backward of nf_nerf_mlp_forward (parity / debug entry point, and the MLP stage of nf_render_backward):
+ * dout4 (n,4): gradient w.r.t. (pre-sigmoid r, g, b, sigma), read at index rowid[row] (rowid NULL: row);
+ * dfeat (n_rows,272) out: gradient w.r.t. the encoded features [xyz-like 198 | 10 pad | dir-like 54 | 10 pad];
+ * dparams: flat parameter gradients (accumulated). */
+NF_API size_t nf_nerf_mlp_backward_workspace_bytes(int n_rows);
+NF_API int nf_nerf_mlp_backward(const void* packed_fwd, const void* packed_bwd, int dtype, const float* records,
+                                const int32_t* rowid, const float* dout4, int n_rows, float* dfeat, float* dparams,
+                                void* workspace, size_t workspace_bytes, void* stream);
+
+typedef struct nf_render_bwd_args {
+    const nf_render_args* fwd; /* the arguments of the forward call (flags & NF_RENDER_SAVE_NEIGHBORS); its workspace must
+                                  be untouched since */
+    const void* weights_coarse_bwd; /* nf_render_pack_weights_bwd */
+    const void* weights_fine_bwd;
+    /* upstream gradients, shapes as the forward outputs; any may be NULL (= zero) */
+    const float* d_rgb0;
+    const float* d_depth0;
+    const float* d_opacity0;
+    const float* d_rgb1;
+    const float* d_depth1;
+    const float* d_opacity1;
+    /* outputs, accumulated */
+    float* d_particles;     /* (n_particles,3) */
+    float* d_params_coarse; /* nf_render_param_count() floats */
+    float* d_params_fine;
+    void* workspace;        /* nf_render_backward_workspace_bytes(..., rows of the two passes = counters[0], counters[1]) */
+    size_t workspace_bytes;
+} nf_render_bwd_args;
+NF_API size_t nf_render_backward_workspace_bytes(int n_rays, int n_coarse, int n_importance, int rows_coarse, int rows_fine);
+NF_API int nf_render_backward(const nf_render_bwd_args* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Transition model
@@ -231,6 +276,32 @@ NF_API int nf_transition_step(const nf_transition_args* args, void* stream);
  * layer 0: 96 channels, 1 and 2: 64 channels.  Used by the sharded execution to all-gather rows. */
 NF_API int nf_transition_layer_buffer(int n_fluid, int n_box, int layer, size_t* offset_bytes_host,
                                       size_t* row_bytes_host);
+
+/* ---------------------------------------------------------------------------------------------
+ * Transition model backward (training)
+ * replaces: autograd through ParticleNet.forward: loss.backward() at trainer/trainer_transmodel.py:197 (two-step unroll:
+ *           gradients flow through pos and vel into the previous step) and trainer/trainer_e2e.py:277.  ContinuousConv
+ *           gradients exist w.r.t. filters and input features only (as in Open3D); positions get theirs through
+ *           pos_new + delta and vel = (pos_out - pos) / dt (models/transmodel.py:144-148).
+ * d_params: one flat fp32 buffer of nf_transition_param_count() floats = the 18 tensors of nf_transition_pack_weights
+ * in that order, concatenated; ACCUMULATED into.  d_pos / d_vel are overwritten.
+ * ------------------------------------------------------------------------------------------- */
+NF_API size_t nf_transition_param_count(void);
+NF_API size_t nf_transition_packed_weights_bwd_bytes(void);
+NF_API int nf_transition_pack_weights_bwd(const float* const* params_host /*[18] device pointers*/, void* packed_out, void* stream);
+NF_API size_t nf_transition_backward_workspace_bytes(int n_fluid);
+typedef struct nf_transition_bwd_args {
+    const nf_transition_args* fwd; /* the forward call's arguments (phase -1); its workspace must be untouched since */
+    const void* weights_bwd;       /* nf_transition_pack_weights_bwd */
+    const float* g_pos_out;        /* (n_fluid,3) upstream gradient w.r.t. pos_out, or NULL */
+    const float* g_vel_out;        /* (n_fluid,3) upstream gradient w.r.t. vel_out, or NULL */
+    float* d_pos;                  /* (n_fluid,3) */
+    float* d_vel;                  /* (n_fluid,3) */
+    float* d_params;               /* nf_transition_param_count() floats, accumulated */
+    void* workspace;
+    size_t workspace_bytes;
+} nf_transition_bwd_args;
+NF_API int nf_transition_backward(const nf_transition_bwd_args* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * One ContinuousConv (operator-level drop-in for a maintainer who keeps models/transmodel.py and swaps only the layer)

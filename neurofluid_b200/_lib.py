@@ -37,7 +37,7 @@ NF_RENDER_SAVE_NEIGHBORS = 1
 
 class RenderWsView(C.Structure):
     _fields_ = [(n, _sz) for n in ("counters", "act0", "act1", "z1", "rec0", "rowid0", "out0", "rec1", "rowid1", "out1",
-                                   "nbr0", "nbr1", "total")] + \
+                                   "nbr0", "nbr1", "miss", "total")] + \
                [(n, _i32) for n in ("act_stride0", "act_stride1", "cap0", "cap1")]
 
 
@@ -51,6 +51,22 @@ class TransitionArgs(C.Structure):
         ("feats0_out", _vp), ("delta_out", _vp),
         ("workspace", _vp), ("workspace_bytes", _sz),
         ("shard_begin", _i32), ("shard_end", _i32), ("box_grid_ws", _vp), ("overflow_out", _vp), ("phase", _i32),
+    ]
+
+
+class RenderBwdArgs(C.Structure):
+    _fields_ = [
+        ("fwd", C.POINTER(RenderArgs)), ("weights_coarse_bwd", _vp), ("weights_fine_bwd", _vp),
+        ("d_rgb0", _vp), ("d_depth0", _vp), ("d_opacity0", _vp), ("d_rgb1", _vp), ("d_depth1", _vp), ("d_opacity1", _vp),
+        ("d_particles", _vp), ("d_params_coarse", _vp), ("d_params_fine", _vp),
+        ("workspace", _vp), ("workspace_bytes", _sz),
+    ]
+
+
+class TransitionBwdArgs(C.Structure):
+    _fields_ = [
+        ("fwd", C.POINTER(TransitionArgs)), ("weights_bwd", _vp), ("g_pos_out", _vp), ("g_vel_out", _vp),
+        ("d_pos", _vp), ("d_vel", _vp), ("d_params", _vp), ("workspace", _vp), ("workspace_bytes", _sz),
     ]
 
 
@@ -81,12 +97,24 @@ SIGNATURES = {
     "nf_render_workspace_bytes_ex": (_sz, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "nf_render_workspace_view": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(RenderWsView)]),
     "nf_render_forward": (C.c_int, [C.POINTER(RenderArgs), _vp]),
+    "nf_render_param_count": (_sz, []),
+    "nf_render_packed_weights_bwd_bytes": (_sz, []),
+    "nf_render_pack_weights_bwd": (C.c_int, [C.POINTER(_vp), _vp, _vp]),
+    "nf_nerf_mlp_backward_workspace_bytes": (_sz, [C.c_int]),
+    "nf_nerf_mlp_backward": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _sz, _vp]),
+    "nf_render_backward_workspace_bytes": (_sz, [C.c_int] * 5),
+    "nf_render_backward": (C.c_int, [C.POINTER(RenderBwdArgs), _vp]),
     "nf_transition_packed_weights_bytes": (_sz, []),
     "nf_transition_pack_weights": (C.c_int, [C.POINTER(_vp), C.c_int, _vp, _vp]),
     "nf_transition_workspace_bytes": (_sz, [C.c_int, C.c_int]),
     "nf_transition_num_phases": (C.c_int, []),
     "nf_transition_step": (C.c_int, [C.POINTER(TransitionArgs), _vp]),
     "nf_transition_layer_buffer": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(_sz), C.POINTER(_sz)]),
+    "nf_transition_param_count": (_sz, []),
+    "nf_transition_packed_weights_bwd_bytes": (_sz, []),
+    "nf_transition_pack_weights_bwd": (C.c_int, [C.POINTER(_vp), _vp, _vp]),
+    "nf_transition_backward_workspace_bytes": (_sz, [C.c_int]),
+    "nf_transition_backward": (C.c_int, [C.POINTER(TransitionBwdArgs), _vp]),
     "nf_cconv_packed_weights_bytes": (_sz, [C.c_int, C.c_int]),
     "nf_cconv_pack_weights": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "nf_cconv_workspace_bytes": (_sz, [C.c_int, C.c_int, C.c_int, C.c_int]),

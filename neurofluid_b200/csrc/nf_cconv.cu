@@ -523,6 +523,9 @@ struct ConvArgs {
     int cout;                              // real output channels (<= COUT_PAD)
     int dense;                             // 1: the 17th slab is the dense (nn.Linear) branch on the particle's own row;
                                            // 0: plain ContinuousConv (operator-level entry point; in / out sets may differ)
+    const float* mask_src;                 // backward: (N, ld_mask) fp32 pre-activations; the result is zeroed where <= 0
+    int ld_mask;                           //           (ReLU backward), BEFORE the residual is added.  NULL: no mask
+    int relu_out;                          // 1: x_out = relu(ans) (forward);  0: x_out = ans (backward: next gradient)
 };
 
 template <int CIN, int COUT_PAD>
@@ -568,7 +571,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_cconv_tc(const ConvArgs a) 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < COUT_PAD) sbias[threadIdx.x] = __ldg(reinterpret_cast<const float*>(a.w_packed + C::W_BYTES) + threadIdx.x);
-    if (warp == WORKER_WARPS) tmem_alloc(smem_u32(tmem_slot), 64);
+    constexpr uint32_t TMEM_COLS = COUT_PAD <= 64 ? 64 : 128;
+    if (warp == WORKER_WARPS) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -766,12 +770,14 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_cconv_tc(const ConvArgs a) 
                     for (int i = 0; i < 16; ++i) {
                         const int c = c0 + i;
                         float o = __uint_as_float(v[i]) + sbias[c];
+                        if (a.mask_src && !(a.mask_src[(size_t)row * a.ld_mask + c] > 0.f)) o = 0.f;
                         if (a.residual && c < a.cout) o += a.residual[(size_t)row * a.ld_res + c];
                         if (c >= a.cout) o = 0.f;
                         a.ans[(size_t)row * COUT_PAD + c] = o;
                         if (a.x_out) {
-                            if (BF16) reinterpret_cast<__nv_bfloat16*>(a.x_out)[(size_t)row * COUT_PAD + c] = __float2bfloat16(fmaxf(o, 0.f));
-                            else reinterpret_cast<__half*>(a.x_out)[(size_t)row * COUT_PAD + c] = __float2half(fmaxf(o, 0.f));
+                            const float xo = a.relu_out ? fmaxf(o, 0.f) : o;
+                            if (BF16) reinterpret_cast<__nv_bfloat16*>(a.x_out)[(size_t)row * COUT_PAD + c] = __float2bfloat16(xo);
+                            else reinterpret_cast<__half*>(a.x_out)[(size_t)row * COUT_PAD + c] = __float2half(xo);
                         }
                     }
                 }
@@ -781,7 +787,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_cconv_tc(const ConvArgs a) 
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == WORKER_WARPS) tmem_dealloc(tmem_base, 64);
+    if (warp == WORKER_WARPS) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -984,8 +990,51 @@ static int launch_conv(const ConvArgs& a, int dtype, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 constexpr int SMALL_MAX = 768;
 
+// features in one of three storage types (kind 0: fp32, 1: fp16, 2: bf16), row stride ld elements
+__device__ __forceinline__ float load_feat(const void* p, size_t idx, int kind) {
+    if (kind == 0) return __ldg(reinterpret_cast<const float*>(p) + idx);
+    if (kind == 1) return __half2float(reinterpret_cast<const __half*>(p)[idx]);
+    return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[idx]);
+}
+
+// patch[cell * cin + ch] = sum over the pair list of out point i of  w_c * feature_j[ch]   (one warp, patch in smem)
+__device__ __forceinline__ void build_patch(const Pair* __restrict__ pr, int n, const void* __restrict__ in_feat, int ld_in, int kind,
+                                            int cin, float* patch, int lane) {
+    const int pn = NCELL * cin;
+    for (int k = lane; k < pn; k += 32) patch[k] = 0.f;
+    __syncwarp();
+    for (int t0 = 0; t0 < n; t0 += 32) {
+        uint4 h0 = make_uint4(0u, 0u, 0u, 0u);
+        float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
+        if (t0 + lane < n) {
+            h0 = __ldg(reinterpret_cast<const uint4*>(pr + t0 + lane));
+            w0 = __ldg(reinterpret_cast<const float4*>(pr + t0 + lane) + 1);
+            w1 = __ldg(reinterpret_cast<const float4*>(pr + t0 + lane) + 2);
+        }
+        const int m = min(32, n - t0);
+        for (int u = 0; u < m; ++u) {            // pairs in list order: the patch sums run like a walk over the list
+            const int j = __shfl_sync(NF_FULL, (int)h0.x, u);
+            const unsigned c03 = __shfl_sync(NF_FULL, h0.y, u), c47 = __shfl_sync(NF_FULL, h0.z, u);
+            float w[8];
+            w[0] = __shfl_sync(NF_FULL, w0.x, u); w[1] = __shfl_sync(NF_FULL, w0.y, u);
+            w[2] = __shfl_sync(NF_FULL, w0.z, u); w[3] = __shfl_sync(NF_FULL, w0.w, u);
+            w[4] = __shfl_sync(NF_FULL, w1.x, u); w[5] = __shfl_sync(NF_FULL, w1.y, u);
+            w[6] = __shfl_sync(NF_FULL, w1.z, u); w[7] = __shfl_sync(NF_FULL, w1.w, u);
+            for (int ch = lane; ch < cin; ch += 32) {
+                const float f = load_feat(in_feat, (size_t)j * ld_in + ch, kind);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const unsigned cell = ((c < 4 ? c03 : c47) >> (8 * (c & 3))) & 0xffu;
+                    patch[cell * cin + ch] += w[c] * f;       // a lane owns its channels: no conflicts between lanes
+                }
+            }
+        }
+    }
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(256) k_cconv_small(const Pair* __restrict__ pairs, const int* __restrict__ cnt,
-                                                     const float* __restrict__ in_feat, int cin, int cout,
+                                                     const void* __restrict__ in_feat, int ld_in, int kind, int cin, int cout,
                                                      const float* __restrict__ kern /*(64, cin, cout)*/,
                                                      const float* __restrict__ bias /*(cout)*/, int n_out,
                                                      float* __restrict__ out /*(n_out, cout)*/) {
@@ -998,38 +1047,7 @@ __global__ void __launch_bounds__(256) k_cconv_small(const Pair* __restrict__ pa
     __syncthreads();
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_out; i += nwarps) {
-        for (int k = lane; k < pn; k += 32) patch[k] = 0.f;
-        __syncwarp();
-        const int n = cnt[i];
-        const Pair* pr = pairs + (size_t)i * MAXNBR;
-        for (int t0 = 0; t0 < n; t0 += 32) {
-            uint4 h0 = make_uint4(0u, 0u, 0u, 0u);
-            float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
-            if (t0 + lane < n) {
-                h0 = __ldg(reinterpret_cast<const uint4*>(pr + t0 + lane));
-                w0 = __ldg(reinterpret_cast<const float4*>(pr + t0 + lane) + 1);
-                w1 = __ldg(reinterpret_cast<const float4*>(pr + t0 + lane) + 2);
-            }
-            const int m = min(32, n - t0);
-            for (int u = 0; u < m; ++u) {            // pairs in list order: the patch sums run like a walk over the list
-                const int j = __shfl_sync(NF_FULL, (int)h0.x, u);
-                const unsigned c03 = __shfl_sync(NF_FULL, h0.y, u), c47 = __shfl_sync(NF_FULL, h0.z, u);
-                float w[8];
-                w[0] = __shfl_sync(NF_FULL, w0.x, u); w[1] = __shfl_sync(NF_FULL, w0.y, u);
-                w[2] = __shfl_sync(NF_FULL, w0.z, u); w[3] = __shfl_sync(NF_FULL, w0.w, u);
-                w[4] = __shfl_sync(NF_FULL, w1.x, u); w[5] = __shfl_sync(NF_FULL, w1.y, u);
-                w[6] = __shfl_sync(NF_FULL, w1.z, u); w[7] = __shfl_sync(NF_FULL, w1.w, u);
-                for (int ch = lane; ch < cin; ch += 32) {
-                    const float f = __ldg(in_feat + (size_t)j * cin + ch);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const unsigned cell = ((c < 4 ? c03 : c47) >> (8 * (c & 3))) & 0xffu;
-                        patch[cell * cin + ch] += w[c] * f;       // a lane owns its channels: no conflicts between lanes
-                    }
-                }
-            }
-        }
-        __syncwarp();
+        build_patch(pairs + (size_t)i * MAXNBR, cnt[i], in_feat, ld_in, kind, cin, patch, lane);
         for (int co = 0; co < cout; ++co) {
             float acc = 0.f;
             for (int k = lane; k < pn; k += 32) acc += patch[k] * sk[k * cout + co];
@@ -1073,6 +1091,426 @@ inline OpWs op_ws(int n_in, int n_out, int cin, int cout) {
     L.flags = take(256);
     L.total = o;
     return L;
+}
+
+// ================================================================================================
+// Backward pass of ParticleNet.forward (training: loss.backward() at trainer/trainer_transmodel.py:197 and, through the
+// renderer, trainer/trainer_e2e.py:277).  As in Open3D, a ContinuousConv has gradients w.r.t. its filter and its input
+// features only -- positions enter the geometry without gradient and reach the loss through pos_new + delta
+// (models/transmodel.py:146) and vel = (pos_out - pos) / dt (:147).
+//
+//   feature gradient of a fluid->fluid conv = the SAME conv over the same (symmetric) neighbour lists with the filter
+//     flipped in all three axes and transposed: dX_j = sum_i sum_c w_ijc K_c g_i and w_ijc = w_ji,flip(c) because the
+//     ball-to-cube map is odd and trilinear weights mirror.  conv1 / conv2 therefore reuse k_cconv_tc (bf16 operands:
+//     gradients need the range) with re-packed weights; its epilogue applies the ReLU mask and adds the residual gradient.
+//   filter gradient dK_c = sum_i P_i[c]^T g_i (P_i = the patch of layer inputs around particle i):
+//     conv1 / conv2: k_cconv_wgrad rebuilds the patch slabs like the forward kernel and contracts them with the gradient
+//       tile on tcgen05 with MN-major operands (K = the 128 particles of a tile), accumulating over tiles in TMEM;
+//     small layers (4->32, 3->32, 64->3): fp32 patch in shared memory, outer product accumulated per block.
+// ================================================================================================
+struct CWgradArgs {
+    const int* slab_j; const float4* slab_w; const unsigned short* slab_off;
+    const void* x_in;      // (N, CIN) layer input, forward operand dtype
+    const void* g;         // (N, 64) bf16: gradient w.r.t. the layer's pre-activation
+    int n, ntiles, nsplit;
+    float* dK;             // (64 cells, CIN, 64) accumulated
+    float* dWd;            // (64, CIN) accumulated (nn.Linear layout)
+};
+
+template <int CIN>
+struct WgCfg {
+    static constexpr int KSLAB = 4 * CIN;
+    static constexpr int MB = KSLAB / 128;
+    static constexpr int SM_A = 0;                              // 128 x KSLAB bf16 (tile image)
+    static constexpr int SM_G = SM_A + 128 * KSLAB * 2;          // 128 x 64 bf16 (tile image)
+    static constexpr int SM_BAR = SM_G + 8 * 2048;
+    static constexpr int SM_TOTAL = SM_BAR + 64;
+};
+
+template <int CIN, bool XBF16>
+__global__ void __launch_bounds__(CONV_THREADS, 1) k_cconv_wgrad(const CWgradArgs a) {
+    using C = WgCfg<CIN>;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x / a.nsplit, split = blockIdx.x % a.nsplit;      // s: filter row 0..15, 16 = dense branch
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t s_a = s_base + C::SM_A, s_g = s_base + C::SM_G, s_bar = s_base + C::SM_BAR;
+    const uint32_t bar_a_ready = s_bar, bar_mma_done = s_bar + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::SM_BAR + 32);
+    if (threadIdx.x == 0) {
+        mbar_init(bar_a_ready, WORKER_WARPS * 32);
+        mbar_init(bar_mma_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == WORKER_WARPS) tmem_alloc(smem_u32(tmem_slot), 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    const int my_tiles = a.ntiles > split ? (a.ntiles - split + a.nsplit - 1) / a.nsplit : 0;
+    const int nmb = s < 16 ? C::MB : 1;
+
+    if (warp == WORKER_WARPS) {
+        if (lane == 0) {
+            // A = patch slab^T (MN-major: M = slab column), B = gradient tile^T (MN-major: N = output channel), K = particle
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) |
+                                   ((uint32_t)(128 >> 4) << 24);
+            for (int it = 0; it < my_tiles; ++it) {
+                mbar_wait(bar_a_ready, it & 1);
+                tc_fence_after();
+                for (int mb = 0; mb < nmb; ++mb)
+                    for (int j = 0; j < 8; ++j)
+                        umma_f16(tmem_base + mb * 64, umma_desc(s_a + mb * 16 * 2048 + j * 256, 128, 2048),
+                                 umma_desc(s_g + j * 256, 128, 2048), idesc, (it > 0 || j > 0) ? 1u : 0u);
+                umma_commit(bar_mma_done);
+            }
+        }
+    } else {
+        const int rbase = warp * ROWS_PER_WARP;
+        constexpr bool THIRD = (CIN == 96);
+        const uint32_t* xin32 = reinterpret_cast<const uint32_t*>(a.x_in);
+        const unsigned short* xin16 = reinterpret_cast<const unsigned short*>(a.x_in);
+        auto cvt2 = [](uint32_t v, float& lo, float& hi) {
+            if (XBF16) { lo = __uint_as_float(v << 16); hi = __uint_as_float(v & 0xffff0000u); }
+            else { const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&v)); lo = t.x; hi = t.y; }
+        };
+        auto cvt1 = [](unsigned short v) {
+            if (XBF16) return __uint_as_float((uint32_t)v << 16);
+            return __half2float(*reinterpret_cast<const __half*>(&v));
+        };
+        auto packb = [](float lo, float hi) -> uint32_t {
+            __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+            return *reinterpret_cast<uint32_t*>(&h);
+        };
+        for (int it = 0; it < my_tiles; ++it) {
+            const int row0 = (split + it * a.nsplit) * 128;
+            if (it > 0) mbar_wait(bar_mma_done, (it - 1) & 1);       // the previous tile's operands have been consumed
+            // gradient tile: (row, 8-column group) pieces of 16 bytes, row-major in HBM -> tile image
+            for (int p = threadIdx.x; p < 128 * 8; p += WORKER_WARPS * 32) {
+                const int r = p >> 3, q = p & 7;
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (row0 + r < a.n) v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(a.g) + (size_t)(row0 + r) * 128 + q * 16);
+                *reinterpret_cast<uint4*>(smem + C::SM_G + q * 2048 + r * 16) = v;
+            }
+#pragma unroll 1
+            for (int r = 0; r < ROWS_PER_WARP; ++r) {
+                const int rl = rbase + r, row = row0 + rl;
+                float acc[4][3];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) acc[x][0] = acc[x][1] = acc[x][2] = 0.f;
+                if (s < 16) {
+                    int beg = 0, end = 0;
+                    if (row < a.n) {
+                        beg = __ldg(a.slab_off + (size_t)row * SLABOFF + s);
+                        end = __ldg(a.slab_off + (size_t)row * SLABOFF + s + 1);
+                    }
+#pragma unroll 1
+                    for (int e0 = beg; e0 < end; e0 += 32) {
+                        int ej = 0;
+                        float4 ew = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (e0 + lane < end) {
+                            ej = __ldg(a.slab_j + (size_t)row * SLABCAP + e0 + lane);
+                            ew = __ldg(a.slab_w + (size_t)row * SLABCAP + e0 + lane);
+                        }
+                        const int cnt = min(32, end - e0);
+#pragma unroll 1
+                        for (int u0 = 0; u0 < cnt; u0 += 8) {
+                            uint32_t fp[8];
+                            unsigned short fs[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) {
+                                const int j = __shfl_sync(NF_FULL, ej, (u0 + u) & 31);
+                                fp[u] = __ldg(xin32 + (((size_t)j * CIN) >> 1) + lane);
+                                if (THIRD) fs[u] = __ldg(xin16 + (size_t)j * CIN + 64 + lane);
+                            }
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) {
+                                const int src = (u0 + u) & 31;
+                                const float wx = __shfl_sync(NF_FULL, ew.x, src), wy = __shfl_sync(NF_FULL, ew.y, src);
+                                const float wz = __shfl_sync(NF_FULL, ew.z, src), ww = __shfl_sync(NF_FULL, ew.w, src);
+                                float f0, f1;
+                                cvt2(fp[u], f0, f1);
+                                acc[0][0] += wx * f0; acc[1][0] += wy * f0; acc[2][0] += wz * f0; acc[3][0] += ww * f0;
+                                acc[0][1] += wx * f1; acc[1][1] += wy * f1; acc[2][1] += wz * f1; acc[3][1] += ww * f1;
+                                if (THIRD) {
+                                    const float f2 = cvt1(fs[u]);
+                                    acc[0][2] += wx * f2; acc[1][2] += wy * f2; acc[2][2] += wz * f2; acc[3][2] += ww * f2;
+                                }
+                            }
+                        }
+                    }
+                } else if (row < a.n) {
+                    cvt2(__ldg(xin32 + (((size_t)row * CIN) >> 1) + lane), acc[0][0], acc[0][1]);
+                    if (THIRD) acc[0][2] = cvt1(__ldg(xin16 + (size_t)row * CIN + 64 + lane));
+                }
+                const int nx = (s < 16) ? 4 : 1;
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    if (x < nx) {
+                        {
+                            const int k = x * CIN + 2 * lane;
+                            const uint32_t addr = s_a + (uint32_t)(k >> 3) * 2048 + (uint32_t)rl * 16 + (uint32_t)(k & 7) * 2;
+                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(packb(acc[x][0], acc[x][1])) : "memory");
+                        }
+                        if (THIRD) {
+                            const int k = x * CIN + 64 + lane;
+                            const uint32_t addr = s_a + (uint32_t)(k >> 3) * 2048 + (uint32_t)rl * 16 + (uint32_t)(k & 7) * 2;
+                            const uint32_t bits = packb(acc[x][2], 0.f);
+                            asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)(bits & 0xffffu)) : "memory");
+                        }
+                    }
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(bar_a_ready);
+        }
+        if (warp < 4 && my_tiles > 0) {
+            mbar_wait(bar_mma_done, (my_tiles - 1) & 1);
+            tc_fence_after();
+            const int ml = warp * 32 + lane;
+            for (int mb = 0; mb < nmb; ++mb) {
+                const int m = mb * 128 + ml;
+                const bool ok = s < 16 ? (m < C::KSLAB) : (m < CIN);
+#pragma unroll
+                for (int c0 = 0; c0 < 64; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + mb * 64 + c0, v);
+                    tmem_ld_wait();
+                    if (ok) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            if (s < 16) atomicAdd(a.dK + ((size_t)s * C::KSLAB + m) * 64 + c0 + i, __uint_as_float(v[i]));
+                            else atomicAdd(a.dWd + (size_t)(c0 + i) * CIN + m, __uint_as_float(v[i]));
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == WORKER_WARPS) tmem_dealloc(tmem_base, 256);
+}
+
+// ---- small layers: filter gradient = sum_i patch_i (64 cells x cin) (x) g_i (cout), accumulated per block in smem
+__global__ void __launch_bounds__(256) k_cconv_small_wgrad(const Pair* __restrict__ pairs, const int* __restrict__ cnt,
+                                                           const void* __restrict__ in_feat, int ld_in, int kind, int cin, int cout,
+                                                           const float* __restrict__ g, int ld_g, int n_out, float* __restrict__ dK) {
+    extern __shared__ __align__(16) float sm[];
+    const int kn = NCELL * cin * cout, pn = NCELL * cin;
+    float* acc = sm;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    float* patch = sm + kn + wib * pn;
+    for (int k = threadIdx.x; k < kn; k += blockDim.x) acc[k] = 0.f;
+    __syncthreads();
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_out; i += nwarps) {
+        build_patch(pairs + (size_t)i * MAXNBR, cnt[i], in_feat, ld_in, kind, cin, patch, lane);
+        for (int idx = lane; idx < kn; idx += 32) {
+            const float p = patch[idx / cout];
+            if (p != 0.f) atomicAdd(acc + idx, p * __ldg(g + (size_t)i * ld_g + idx % cout));
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < kn; k += blockDim.x)
+        if (acc[k] != 0.f) atomicAdd(dK + k, acc[k]);
+}
+
+// dW (cout, cin) += g^T x over all particles; db (cout) += column sums of g (optional, may alias a second target)
+__global__ void __launch_bounds__(256) k_dense_wgrad(const float* __restrict__ g, int ld_g, int cout, const void* __restrict__ x, int ld_x,
+                                                     int kind, int cin, int n, float* __restrict__ dW, float* __restrict__ db0,
+                                                     float* __restrict__ db1) {
+    extern __shared__ float sm[];
+    constexpr int TP = 32;                     // particles per tile
+    float* sg = sm;                            // TP x cout
+    float* sx = sm + TP * cout;                // TP x cin
+    const int nout = cout * cin;
+    float accw[24];
+#pragma unroll
+    for (int t = 0; t < 24; ++t) accw[t] = 0.f;
+    float accb = 0.f;
+    for (int i0 = blockIdx.x * TP; i0 < n; i0 += gridDim.x * TP) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < TP * cout; k += blockDim.x) {
+            const int r = k / cout, c = k % cout;
+            sg[k] = i0 + r < n ? g[(size_t)(i0 + r) * ld_g + c] : 0.f;
+        }
+        for (int k = threadIdx.x; k < TP * cin; k += blockDim.x) {
+            const int r = k / cin, c = k % cin;
+            sx[k] = i0 + r < n ? load_feat(x, (size_t)(i0 + r) * ld_x + c, kind) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < 24; ++t) {
+            const int o = threadIdx.x + t * 256;
+            if (o < nout) {
+                const int co = o / cin, ci = o % cin;
+                float a = 0.f;
+                for (int r = 0; r < TP; ++r) a += sg[r * cout + co] * sx[r * cin + ci];
+                accw[t] += a;
+            }
+        }
+        if ((int)threadIdx.x < cout)
+            for (int r = 0; r < TP; ++r) accb += sg[r * cout + threadIdx.x];
+    }
+#pragma unroll
+    for (int t = 0; t < 24; ++t) {
+        const int o = threadIdx.x + t * 256;
+        if (o < nout && accw[t] != 0.f) atomicAdd(dW + o, accw[t]);
+    }
+    if ((int)threadIdx.x < cout && accb != 0.f) {
+        if (db0) atomicAdd(db0 + threadIdx.x, accb);
+        if (db1) atomicAdd(db1 + threadIdx.x, accb);
+    }
+}
+
+// K (64, cin, cout) -> K' (64, cout, cin) with the cell index mirrored: K'[c][co][ci] = K[63 - c][ci][co];  Wd (cout, cin) -> Wd^T
+__global__ void k_flip_transpose(const float* __restrict__ K, int cin, int cout, float* __restrict__ Kt, const float* __restrict__ Wd,
+                                 float* __restrict__ Wdt) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < NCELL * cin * cout) {
+        const int ci = t % cin, co = (t / cin) % cout, c = t / (cin * cout);
+        Kt[t] = K[((size_t)(NCELL - 1 - c) * cin + ci) * cout + co];
+    }
+    if (Wd && t < cin * cout) {
+        const int co = t % cout, ci = t / cout;
+        Wdt[t] = Wd[(size_t)co * cin + ci];
+    }
+}
+
+// start of the backward pass: gpt = g_pos_out + g_vel_out / dt;  g_ans3 = gpt / 128;  d_pos = g_pos_out;  d_vel = dt * gpt
+// (+ the feature path, added by k_bwd_tail);  ff = [1, vel_new]
+__global__ void k_bwd_head(const float* __restrict__ g_pos_out, const float* __restrict__ g_vel_out, const float* __restrict__ vel_new,
+                           int n, float dt, float* __restrict__ g_ans3, float* __restrict__ d_pos, float* __restrict__ d_vel,
+                           float* __restrict__ ff) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ff[4 * i] = 1.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float gp = g_pos_out ? g_pos_out[3 * i + a] : 0.f, gv = g_vel_out ? g_vel_out[3 * i + a] : 0.f;
+        const float gpt = gp + gv / dt;
+        g_ans3[3 * i + a] = gpt * (1.0f / 128);
+        d_pos[3 * i + a] = gp;
+        d_vel[3 * i + a] = dt * gpt;
+        ff[4 * i + 1 + a] = vel_new[3 * i + a];
+    }
+}
+
+// g_ans2 = (conv3^T(g_ans3) + g_ans3 Wd3) * (ans2 > 0)  -> fp32 + bf16
+__global__ void k_bwd_l3_finish(const float* __restrict__ t2, const float* __restrict__ g_ans3, const float* __restrict__ wd3 /*(3,64)*/,
+                                const float* __restrict__ ans2, int n, float* __restrict__ g_ans2, __nv_bfloat16* __restrict__ g_ans2_h) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * 64) return;
+    const int i = t >> 6, c = t & 63;
+    float v = t2[t] + g_ans3[3 * i] * wd3[c] + g_ans3[3 * i + 1] * wd3[64 + c] + g_ans3[3 * i + 2] * wd3[128 + c];
+    if (!(ans2[t] > 0.f)) v = 0.f;
+    g_ans2[t] = v;
+    g_ans2_h[t] = __float2bfloat16(v);
+}
+
+// d_vel += conv0_fluid^T(g)[1:4] + (g_ans0[:, 64:96] Wd0)[1:4]     (fluid features are [1, vel_new]; vel_new = vel + g dt)
+__global__ void k_bwd_tail(const float* __restrict__ g_ffc /*(N,4)*/, const float* __restrict__ g_ans0 /*(N,96)*/,
+                           const float* __restrict__ wd0 /*(32,4)*/, int n, float* __restrict__ d_vel) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float v = g_ffc[4 * i + 1 + a];
+        for (int o = 0; o < 32; ++o) v += g_ans0[(size_t)i * 96 + 64 + o] * wd0[o * 4 + 1 + a];
+        d_vel[3 * i + a] += v;
+    }
+}
+
+struct BwdPackLayout {
+    size_t scratch_k, scratch_w, l1, l2, k3t, k0ft, total;
+};
+inline BwdPackLayout bwd_pack_layout() {
+    BwdPackLayout L;
+    size_t o = 0;
+    auto take = [&](size_t b) { size_t r = o; o += align_up(b, 256); return r; };
+    L.scratch_k = take((size_t)NCELL * 96 * 64 * 4);
+    L.scratch_w = take((size_t)96 * 64 * 4);
+    L.l1 = take(ConvCfg<64, 96>::PACKED_BYTES);
+    L.l2 = take(ConvCfg<64, 64>::PACKED_BYTES);
+    L.k3t = take((size_t)NCELL * 3 * 64 * 4);
+    L.k0ft = take((size_t)NCELL * 32 * 4 * 4);
+    L.total = o;
+    return L;
+}
+
+struct BwdWsLayout {
+    size_t g_ans3, t2, g_ans2, g_ans2_h, g_ans1, g_ans1_h, g_ans0, ff, g_ffc, total;
+};
+inline BwdWsLayout bwd_ws_layout(int n) {
+    BwdWsLayout L;
+    size_t o = 0;
+    auto take = [&](size_t b) { size_t r = o; o += align_up(b, 256); return r; };
+    const size_t N = (size_t)(n > 0 ? n : 1);
+    L.g_ans3 = take(N * 3 * 4); L.t2 = take(N * 64 * 4);
+    L.g_ans2 = take(N * 64 * 4); L.g_ans2_h = take(N * 64 * 2);
+    L.g_ans1 = take(N * 64 * 4); L.g_ans1_h = take(N * 64 * 2);
+    L.g_ans0 = take(N * 96 * 4);
+    L.ff = take(N * 4 * 4); L.g_ffc = take(N * 4 * 4);
+    L.total = o;
+    return L;
+}
+
+// flat parameter(-gradient) layout of ParticleNet: nf_transition_pack_weights order, tensors concatenated
+struct TParamOff {
+    int off[18], total;
+};
+inline TParamOff tparam_offsets() {
+    const int sz[18] = {NCELL * 4 * 32, 32, NCELL * 3 * 32, 32, 32 * 4, 32, NCELL * 96 * 64, 64, 64 * 96, 64,
+                        NCELL * 64 * 64, 64, 64 * 64, 64, NCELL * 64 * 3, 3, 3 * 64, 3};
+    TParamOff P;
+    int o = 0;
+    for (int i = 0; i < 18; ++i) { P.off[i] = o; o += sz[i]; }
+    P.total = o;
+    return P;
+}
+
+template <int CIN>
+static int launch_wgrad(const CWgradArgs& a, bool xbf16, cudaStream_t st) {
+    using C = WgCfg<CIN>;
+    if (a.ntiles <= 0) return NF_OK;
+    if (xbf16) {
+        NF_CUDA_OK(cudaFuncSetAttribute(k_cconv_wgrad<CIN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SM_TOTAL));
+        k_cconv_wgrad<CIN, true><<<17 * a.nsplit, CONV_THREADS, C::SM_TOTAL, st>>>(a);
+    } else {
+        NF_CUDA_OK(cudaFuncSetAttribute(k_cconv_wgrad<CIN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SM_TOTAL));
+        k_cconv_wgrad<CIN, false><<<17 * a.nsplit, CONV_THREADS, C::SM_TOTAL, st>>>(a);
+    }
+    NF_LAUNCH_OK();
+    return NF_OK;
+}
+
+static int launch_small(const Pair* pairs, const int* cnt, const void* in_feat, int ld_in, int kind, int cin, int cout, const float* kern,
+                        int n_out, float* out, cudaStream_t st) {
+    const size_t smem = (size_t)NCELL * cin * cout * 4 + (size_t)8 * NCELL * cin * 4;
+    NF_CUDA_OK(cudaFuncSetAttribute(k_cconv_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_cconv_small<<<min((n_out + 7) / 8, 2 * num_sms()), 256, smem, st>>>(pairs, cnt, in_feat, ld_in, kind, cin, cout, kern, nullptr, n_out, out);
+    NF_LAUNCH_OK();
+    return NF_OK;
+}
+
+static int launch_small_wgrad(const Pair* pairs, const int* cnt, const void* in_feat, int ld_in, int kind, int cin, int cout, const float* g,
+                              int ld_g, int n_out, float* dK, cudaStream_t st) {
+    const size_t smem = (size_t)NCELL * cin * cout * 4 + (size_t)8 * NCELL * cin * 4;
+    NF_CUDA_OK(cudaFuncSetAttribute(k_cconv_small_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_cconv_small_wgrad<<<min((n_out + 7) / 8, num_sms()), 256, smem, st>>>(pairs, cnt, in_feat, ld_in, kind, cin, cout, g, ld_g, n_out, dK);
+    NF_LAUNCH_OK();
+    return NF_OK;
+}
+
+static int launch_dense_wgrad(const float* g, int ld_g, int cout, const void* x, int ld_x, int kind, int cin, int n, float* dW, float* db0,
+                              float* db1, cudaStream_t st) {
+    const size_t smem = (size_t)32 * (cout + cin) * 4;
+    k_dense_wgrad<<<min((n + 31) / 32, num_sms()), 256, smem, st>>>(g, ld_g, cout, x, ld_x, kind, cin, n, dW, db0, db1);
+    NF_LAUNCH_OK();
+    return NF_OK;
 }
 
 }  // namespace cconv
@@ -1217,14 +1655,131 @@ extern "C" int nf_cconv_forward(const nf_cconv_args* a, void* stream_) {
         c.slab_off = (const unsigned short*)(b + L.slab_off);
         c.x_in = b + L.x16; c.w_packed = (const uint8_t*)a->weights; c.residual = nullptr; c.ld_res = 0;
         c.ans = a->out; c.x_out = nullptr; c.n = a->n_in; c.begin = 0; c.end = a->n_out; c.cout = 64; c.dense = 0;
+        c.mask_src = nullptr; c.ld_mask = 0; c.relu_out = 1;
         return a->cin == 96 ? launch_conv<96, 64>(c, a->dtype, st) : launch_conv<64, 64>(c, a->dtype, st);
     }
     const size_t kb = (size_t)NCELL * a->cin * a->cout * 4;
     const size_t smem = kb + (size_t)8 * NCELL * a->cin * 4;
     NF_CUDA_OK(cudaFuncSetAttribute(k_cconv_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = min(blocks, 2 * num_sms());
-    k_cconv_small<<<grid, 256, smem, st>>>(pairs, cnt, a->in_feat, a->cin, a->cout, (const float*)a->weights,
+    k_cconv_small<<<grid, 256, smem, st>>>(pairs, cnt, a->in_feat, a->cin, 0, a->cin, a->cout, (const float*)a->weights,
                                           (const float*)((const char*)a->weights + align_up(kb, 256)), a->n_out, a->out);
+    NF_LAUNCH_OK();
+    return NF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward entry points
+// ------------------------------------------------------------------------------------------------
+extern "C" size_t nf_transition_param_count(void) { return (size_t)tparam_offsets().total; }
+extern "C" size_t nf_transition_packed_weights_bwd_bytes(void) { return bwd_pack_layout().total; }
+extern "C" size_t nf_transition_backward_workspace_bytes(int n_fluid) { return n_fluid < 0 ? 0 : bwd_ws_layout(n_fluid).total; }
+
+extern "C" int nf_transition_pack_weights_bwd(const float* const* p, void* packed_out, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    NF_REQUIRE(p && packed_out, NF_E_INVALID, "nf_transition_pack_weights_bwd: null argument");
+    for (int i = 0; i < 18; ++i) NF_REQUIRE(p[i], NF_E_INVALID, "nf_transition_pack_weights_bwd: null parameter %d", i);
+    const BwdPackLayout L = bwd_pack_layout();
+    uint8_t* b = (uint8_t*)packed_out;
+    float* sk = (float*)(b + L.scratch_k);
+    float* sw = (float*)(b + L.scratch_w);
+    // conv1 (96 -> 64) backward: a 64 -> 96 conv with the flipped, transposed filter and dense1^T
+    k_flip_transpose<<<(NCELL * 96 * 64 + 255) / 256, 256, 0, st>>>(p[6], 96, 64, sk, p[8], sw);
+    NF_LAUNCH_OK();
+    {
+        using C = ConvCfg<64, 96>;
+        const int tot = (16 * C::KSTEPS + C::KSTEPS_DENSE) * 2 * 96;
+        k_pack_conv<64, 96, true><<<(tot + 255) / 256, 256, 0, st>>>(sk, nullptr, sw, nullptr, 96, b + L.l1);
+        NF_LAUNCH_OK();
+    }
+    k_flip_transpose<<<(NCELL * 64 * 64 + 255) / 256, 256, 0, st>>>(p[10], 64, 64, sk, p[12], sw);
+    NF_LAUNCH_OK();
+    {
+        using C = ConvCfg<64, 64>;
+        const int tot = (16 * C::KSTEPS + C::KSTEPS_DENSE) * 2 * 64;
+        k_pack_conv<64, 64, true><<<(tot + 255) / 256, 256, 0, st>>>(sk, nullptr, sw, nullptr, 64, b + L.l2);
+        NF_LAUNCH_OK();
+    }
+    k_flip_transpose<<<(NCELL * 64 * 3 + 255) / 256, 256, 0, st>>>(p[14], 64, 3, (float*)(b + L.k3t), nullptr, nullptr);
+    NF_LAUNCH_OK();
+    k_flip_transpose<<<(NCELL * 4 * 32 + 255) / 256, 256, 0, st>>>(p[0], 4, 32, (float*)(b + L.k0ft), nullptr, nullptr);
+    NF_LAUNCH_OK();
+    return NF_OK;
+}
+
+extern "C" int nf_transition_backward(const nf_transition_bwd_args* b, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    NF_REQUIRE(b && b->fwd, NF_E_INVALID, "nf_transition_backward: null args");
+    const nf_transition_args* a = b->fwd;
+    NF_REQUIRE(a->phase == -1, NF_E_UNSUPPORTED, "nf_transition_backward: only the whole-step forward (phase -1) has a backward");
+    const int N = a->n_fluid, M = a->n_box;
+    if (N == 0) return NF_OK;
+    NF_REQUIRE(a->workspace && a->weights && b->weights_bwd && b->workspace && b->d_pos && b->d_vel && b->d_params, NF_E_INVALID,
+               "nf_transition_backward: null pointer");
+    const WsLayout L = ws_layout(N, M);
+    const BwdWsLayout B = bwd_ws_layout(N);
+    NF_REQUIRE(b->workspace_bytes >= B.total, NF_E_WORKSPACE, "nf_transition_backward: workspace %zu < %zu", b->workspace_bytes, B.total);
+    const PackedLayout PL = packed_layout();
+    const BwdPackLayout BL = bwd_pack_layout();
+    const TParamOff PO = tparam_offsets();
+    char* ws = (char*)a->workspace;
+    char* bw = (char*)b->workspace;
+    const uint8_t* w = (const uint8_t*)a->weights;
+    const uint8_t* wb = (const uint8_t*)b->weights_bwd;
+    float* dP = b->d_params;
+    const Pair* pairs_ff = (const Pair*)(ws + L.pairs_ff); const int* cnt_ff = (const int*)(ws + L.cnt_ff);
+    const Pair* pairs_fb = (const Pair*)(ws + L.pairs_fb); const int* cnt_fb = (const int*)(ws + L.cnt_fb);
+    const float* vel_new = (const float*)(ws + L.vel_new);
+    const float* ans0 = (const float*)(ws + L.ans0); const void* x0 = ws + L.x0;
+    const float* ans1 = (const float*)(ws + L.ans1); const void* x1 = ws + L.x1;
+    const float* ans2 = (const float*)(ws + L.ans2); const void* x2 = ws + L.x2;
+    float* g_ans3 = (float*)(bw + B.g_ans3); float* t2 = (float*)(bw + B.t2);
+    float* g_ans2 = (float*)(bw + B.g_ans2); __nv_bfloat16* g_ans2_h = (__nv_bfloat16*)(bw + B.g_ans2_h);
+    float* g_ans1 = (float*)(bw + B.g_ans1); void* g_ans1_h = bw + B.g_ans1_h;
+    float* g_ans0 = (float*)(bw + B.g_ans0);
+    float* ff = (float*)(bw + B.ff); float* g_ffc = (float*)(bw + B.g_ffc);
+    const bool xbf = a->dtype == NF_DTYPE_BF16;
+    const int xkind = xbf ? 2 : 1;
+    const int ntiles = (N + 127) / 128;
+    const int nsplit = ntiles < 8 ? ntiles : 8;
+    int rc;
+
+    k_bwd_head<<<(N + 255) / 256, 256, 0, st>>>(b->g_pos_out, b->g_vel_out, vel_new, N, a->dt, g_ans3, b->d_pos, b->d_vel, ff);
+    NF_LAUNCH_OK();
+    // ---- layer 3: ans3 = conv3(x2) + dense3(x2)
+    if ((rc = launch_small_wgrad(pairs_ff, cnt_ff, x2, 64, xkind, 64, 3, g_ans3, 3, N, dP + PO.off[14], st)) != NF_OK) return rc;
+    if ((rc = launch_dense_wgrad(g_ans3, 3, 3, x2, 64, xkind, 64, N, dP + PO.off[16], dP + PO.off[15], dP + PO.off[17], st)) != NF_OK) return rc;
+    if ((rc = launch_small(pairs_ff, cnt_ff, g_ans3, 3, 0, 3, 64, (const float*)(wb + BL.k3t), N, t2, st)) != NF_OK) return rc;
+    k_bwd_l3_finish<<<(N * 64 + 255) / 256, 256, 0, st>>>(t2, g_ans3, (const float*)(w + PL.w_dense3), ans2, N, g_ans2, g_ans2_h);
+    NF_LAUNCH_OK();
+    // ---- layer 2: ans2 = conv2(x1) + dense2(x1) + ans1
+    CWgradArgs wg;
+    wg.slab_j = (const int*)(ws + L.slab_j); wg.slab_w = (const float4*)(ws + L.slab_w); wg.slab_off = (const unsigned short*)(ws + L.slab_off);
+    wg.n = N; wg.ntiles = ntiles; wg.nsplit = nsplit;
+    wg.x_in = x1; wg.g = g_ans2_h; wg.dK = dP + PO.off[10]; wg.dWd = dP + PO.off[12];
+    if ((rc = launch_wgrad<64>(wg, xbf, st)) != NF_OK) return rc;
+    if ((rc = launch_dense_wgrad(g_ans2, 64, 64, x1, 64, xkind, 0, N, dP /*unused: cin = 0*/, dP + PO.off[11], dP + PO.off[13], st)) != NF_OK) return rc;
+    ConvArgs c;
+    c.slab_j = wg.slab_j; c.slab_w = wg.slab_w; c.slab_off = wg.slab_off; c.n = N; c.begin = 0; c.end = N; c.dense = 1; c.relu_out = 0;
+    c.x_in = g_ans2_h; c.w_packed = wb + BL.l2; c.residual = g_ans2; c.ld_res = 64; c.ans = g_ans1; c.x_out = g_ans1_h; c.cout = 64;
+    c.mask_src = ans1; c.ld_mask = 64;
+    if ((rc = launch_conv<64, 64>(c, NF_DTYPE_BF16, st)) != NF_OK) return rc;
+    // ---- layer 1: ans1 = conv1(x0) + dense1(x0)
+    wg.x_in = x0; wg.g = g_ans1_h; wg.dK = dP + PO.off[6]; wg.dWd = dP + PO.off[8];
+    if ((rc = launch_wgrad<96>(wg, xbf, st)) != NF_OK) return rc;
+    if ((rc = launch_dense_wgrad(g_ans1, 64, 64, x0, 96, xkind, 0, N, dP, dP + PO.off[7], dP + PO.off[9], st)) != NF_OK) return rc;
+    c.x_in = g_ans1_h; c.w_packed = wb + BL.l1; c.residual = nullptr; c.ld_res = 0; c.ans = g_ans0; c.x_out = nullptr; c.cout = 96;
+    c.mask_src = ans0; c.ld_mask = 96;
+    if ((rc = launch_conv<64, 96>(c, NF_DTYPE_BF16, st)) != NF_OK) return rc;
+    // ---- layer 0: ans0 = [conv0_obstacle(box normals), conv0_fluid([1, vel']), dense0([1, vel'])]
+    if (M > 0)
+        if ((rc = launch_small_wgrad(pairs_fb, cnt_fb, a->box_normals, 3, 0, 3, 32, g_ans0, 96, N, dP + PO.off[2], st)) != NF_OK) return rc;
+    if ((rc = launch_small_wgrad(pairs_ff, cnt_ff, ff, 4, 0, 4, 32, g_ans0 + 32, 96, N, dP + PO.off[0], st)) != NF_OK) return rc;
+    if ((rc = launch_dense_wgrad(g_ans0, 96, 32, ff, 4, 0, 0, N, dP, dP + PO.off[3], nullptr, st)) != NF_OK) return rc;        // db conv0_obstacle
+    if ((rc = launch_dense_wgrad(g_ans0 + 32, 96, 32, ff, 4, 0, 0, N, dP, dP + PO.off[1], nullptr, st)) != NF_OK) return rc;   // db conv0_fluid
+    if ((rc = launch_dense_wgrad(g_ans0 + 64, 96, 32, ff, 4, 0, 4, N, dP + PO.off[4], dP + PO.off[5], nullptr, st)) != NF_OK) return rc;   // dense0
+    if ((rc = launch_small(pairs_ff, cnt_ff, g_ans0 + 32, 96, 0, 32, 4, (const float*)(wb + BL.k0ft), N, g_ffc, st)) != NF_OK) return rc;
+    k_bwd_tail<<<(N + 255) / 256, 256, 0, st>>>(g_ffc, g_ans0, (const float*)(w + PL.w_dense0), N, b->d_vel);
     NF_LAUNCH_OK();
     return NF_OK;
 }
@@ -1314,6 +1869,7 @@ extern "C" int nf_transition_step(const nf_transition_args* a, void* stream_) {
     }
     ConvArgs c;
     c.slab_j = slab_j; c.slab_w = slab_w; c.slab_off = slab_off; c.n = N; c.begin = begin; c.end = end; c.dense = 1;
+    c.mask_src = nullptr; c.ld_mask = 0; c.relu_out = 1;
     if (all || a->phase == 1) {     // conv1 + dense1 : 96 -> 64 (no residual: widths differ, :127-130)
         c.x_in = x0; c.w_packed = w + PL.l1; c.residual = nullptr; c.ld_res = 0; c.ans = ans1; c.x_out = x1; c.cout = 64;
         int rc = launch_conv<96, 64>(c, a->dtype, st);

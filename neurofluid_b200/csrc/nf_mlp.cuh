@@ -10,6 +10,24 @@ constexpr int RECORD_FLOATS = 16;
 // algorithmic multiply-accumulates per evaluated row (models/nerf.py layer shapes)
 constexpr long long MAC_PER_ROW = 665984;
 
+constexpr int TILE_M = 128;
+constexpr int KX_STEPS = 13;   // xyz-like features 198 -> 208 = 13 K-steps of 16
+constexpr int KD_STEPS = 4;    // dir-like features 54 -> 64
+constexpr int KH_STEPS = 16;   // hidden width 256
+constexpr int STAGE_BYTES = 8192;  // one K-step of a 256-row weight slab: 2 k-chunks x 256 rows x 16 B
+constexpr int N256_STEPS = 154;
+constexpr int N128_STEPS = 20;
+constexpr int W_BYTES = N256_STEPS * 8192 + N128_STEPS * 4096;
+// small fp32 params appended after the weight slabs
+constexpr int SP_BIAS = 0;       // [10][256]
+constexpr int SP_WSIG = 2560;    // [256]
+constexpr int SP_BSIG = 2816;    // [1] (+3 pad)
+constexpr int SP_WRGB = 2820;    // [3][128]
+constexpr int SP_BRGB = 3204;    // [3] (+1 pad)
+constexpr int SP_FLOATS = 3208;
+static_assert(PACKED_BYTES == W_BYTES + SP_FLOATS * 4, "packed size");
+
+
 struct KernelArgs {
     const uint8_t* packed;   // weight slabs + small params
     const float* records;    // (n_rows,16)

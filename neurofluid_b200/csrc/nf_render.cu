@@ -1056,7 +1056,7 @@ extern "C" int nf_render_workspace_view(int n_rays, int n_coarse, int n_importan
     v->counters = L.counters; v->act0 = L.act0; v->act1 = L.act1; v->z1 = L.z1;
     v->rec0 = L.rec0; v->rowid0 = L.rowid0; v->out0 = L.out0;
     v->rec1 = L.rec1; v->rowid1 = L.rowid1; v->out1 = L.out1;
-    v->nbr0 = L.nbr0; v->nbr1 = L.nbr1;
+    v->nbr0 = L.nbr0; v->nbr1 = L.nbr1; v->miss = L.miss;
     v->act_stride0 = L.ns0; v->act_stride1 = L.ns1; v->cap0 = L.cap0; v->cap1 = L.cap1;
     v->total = L.total;
     return NF_OK;

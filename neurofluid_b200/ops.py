@@ -71,6 +71,33 @@ def nerf_mlp(packed: torch.Tensor, records: torch.Tensor, dtype=_lib.NF_DTYPE_F1
     return out
 
 
+def pack_nerf_weights_bwd(params) -> torch.Tensor:
+    """Transposed bf16 slabs for the data-gradient GEMMs of the NeRF MLP backward."""
+    assert len(params) == 24
+    ps = [p.detach().to(torch.float32).contiguous() for p in params]
+    require_cuda(*ps)
+    out = torch.empty(lib().nf_render_packed_weights_bwd_bytes(), dtype=torch.uint8, device=ps[0].device)
+    arr = (C.c_void_p * 24)(*[p.data_ptr() for p in ps])
+    check(lib().nf_render_pack_weights_bwd(arr, ptr(out), stream_ptr()), "nf_render_pack_weights_bwd")
+    out._keepalive = ps
+    return out
+
+
+def nerf_mlp_backward(packed_fwd, packed_bwd, records, dout4, dtype=_lib.NF_DTYPE_F16):
+    """Backward of `nerf_mlp`: dout4 (n,4) = gradient w.r.t. (pre-sigmoid r, g, b, sigma).  Returns (dfeat (n,272):
+    gradient w.r.t. the encoded features [xyz-like 198 | pad 10 | dir-like 54 | pad 10], flat parameter gradients)."""
+    require_cuda(packed_fwd, packed_bwd, records, dout4)
+    rec = records.detach().to(torch.float32).contiguous()
+    g = dout4.detach().to(torch.float32).contiguous()
+    n = rec.shape[0]
+    dfeat = torch.zeros((n, 272), dtype=torch.float32, device=rec.device)
+    dpar = torch.zeros(lib().nf_render_param_count(), dtype=torch.float32, device=rec.device)
+    ws = torch.empty(max(lib().nf_nerf_mlp_backward_workspace_bytes(n), 256), dtype=torch.uint8, device=rec.device)
+    check(lib().nf_nerf_mlp_backward(ptr(packed_fwd), ptr(packed_bwd), int(dtype), ptr(rec), None, ptr(g), n, ptr(dfeat), ptr(dpar),
+                                     ptr(ws), ws.numel(), stream_ptr()), "nf_nerf_mlp_backward")
+    return dfeat, dpar
+
+
 def generate_rays(H: int, W: int, focal: float, c2w: torch.Tensor) -> torch.Tensor:
     """get_ray_directions + get_rays (utils/ray_utils.py:85-130) for one view, on the device: (H*W, 6)."""
     require_cuda(c2w)

@@ -9,7 +9,8 @@ Differences a caller can observe (all documented in DESIGN.md):
   * any number of rays per call (the reference needs `ray_chunk=1024` to bound its O(R*P) repeat);
   * tensor-core operands are fp16 (or bf16) with fp32 accumulation -> outputs agree with the fp32
     reference to ~1e-4 relative L2, not bit for bit;  integer outputs (num_nn_*, mask_*) are exact;
-  * forward only: outputs carry no autograd graph (backward kernels are SURVEY.md section 8f-1);
+  * training: when autograd is recording and the particles or parameters require grad, the call becomes one autograd
+    node whose backward runs nf_render_backward (tcgen05 dgrad / wgrad of both MLPs, gradient to the particle positions);
   * `fine_rendering` works (the reference's raises on every shipped config, models/renderer.py:175,322).
 """
 from __future__ import annotations
@@ -123,7 +124,27 @@ class RenderNet(nn.Module):
             out["z1"] = ws[v.z1: v.z1 + R * S1 * 4].view(torch.float32).view(R, S1).clone()   # merged depths (rays that miss: unset)
         return out
 
-    def _run(self, mode, physical_particles, ro, rays, use_disp, perturb, noise_std, white_background):
+    def _packed_weights_bwd(self, name):
+        """Transposed bf16 slabs for the data-gradient GEMMs (nf_render_pack_weights_bwd), cached like the forward pack."""
+        net = getattr(self, name)
+        params = net.ordered_params()
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        hit = self._packed.get(name + "/bwd")
+        if hit is None or hit[0] != key:
+            ps = [p.detach().to(torch.float32).contiguous() for p in params]
+            require_cuda(*ps)
+            out = torch.empty(lib().nf_render_packed_weights_bwd_bytes(), dtype=torch.uint8, device=ps[0].device)
+            arr = (C.c_void_p * 24)(*[p.data_ptr() for p in ps])
+            check(lib().nf_render_pack_weights_bwd(arr, ptr(out), stream_ptr()), "nf_render_pack_weights_bwd")
+            out._keepalive = ps
+            self._packed[name + "/bwd"] = (key, out)
+        return self._packed[name + "/bwd"][1]
+
+    def _run(self, mode, physical_particles, ro, rays, use_disp, perturb, noise_std, white_background, _train=False):
+        if not _train and torch.is_grad_enabled() and (
+                (isinstance(physical_particles, torch.Tensor) and physical_particles.requires_grad)
+                or any(p.requires_grad for p in self.parameters())):
+            return _render_with_grad(self, mode, physical_particles, ro, rays, use_disp, perturb, noise_std, white_background)
         if perturb != 0 or noise_std != 0:
             raise NFError("perturb / noise_std are training-time jitter the reference's trainers never enable "
                           "(trainer/basetrainer.py:284-289); only the deterministic path is implemented")
@@ -165,10 +186,15 @@ class RenderNet(nn.Module):
                 out["num_nn_1"] = torch.empty((R, S1, 1), dtype=torch.int64, device=dev)
             out["mask_1"] = torch.empty((R, 1), **f32)
         chunk = max(1, min(self.max_rays_per_launch, R))
-        flags = _lib.NF_RENDER_SAVE_NEIGHBORS if self.save_neighbors else 0
-        if self.save_neighbors and R > chunk:
-            raise NFError("save_neighbors needs the whole call in one launch (raise max_rays_per_launch)")
-        ws = self._workspace(chunk, NI, dev, flags)
+        flags = _lib.NF_RENDER_SAVE_NEIGHBORS if (self.save_neighbors or _train) else 0
+        if flags and R > chunk:
+            raise NFError("a forward that keeps its neighbour lists (training, save_neighbors) must fit one launch: "
+                          f"{R} rays > max_rays_per_launch = {self.max_rays_per_launch}")
+        if _train:     # several forwards may precede one backward (trainer/trainer_e2e.py:219-244): each keeps its own workspace
+            ws = torch.empty(max(lib().nf_render_workspace_bytes_ex(max(chunk, 1), S0, NI, int(self.num_neighbor), flags), 256),
+                             dtype=torch.uint8, device=dev)
+        else:
+            ws = self._workspace(chunk, NI, dev, flags)
         nchunks = (R + chunk - 1) // chunk
         stats = torch.zeros((max(nchunks, 1), 16), dtype=torch.int32, device=dev)
         st = stream_ptr()
@@ -198,8 +224,12 @@ class RenderNet(nn.Module):
             check(lib().nf_render_forward(C.byref(a), st), "nf_render_forward")
         self.last_stats = stats       # device tensor; .sum(0) = [rows0, rows1, active0, active1]
         self._keep = (grid, particles, rays, ro_dev)
-        self._debug = (ws, R, NI) if self.save_neighbors and R > 0 else None
-        return _lib.forward_only([physical_particles, *self.parameters()], out)
+        self._debug = (ws, R, NI) if flags and R > 0 else None
+        if _train:
+            saved = dict(args=a if R > 0 else None, ws=ws, R=R, NI=NI, S0=S0, n_particles=particles.shape[0],
+                         keep=(grid, particles, rays, ro_dev, z_tab, u_tab, wc, wf, stats))
+            return out, saved
+        return out
 
     # ------------------------------------------------------------------ reference API
     def forward(self, physical_particles, ro, rays, focal=None, c2w=None, use_disp=False, perturb=0, noise_std=0.,
@@ -219,6 +249,66 @@ class RenderNet(nn.Module):
         """models/renderer.py:310-369 (sigma-only coarse pass, then the fine pass)."""
         return self._run(_lib.NF_RENDER_FINE, physical_particles, ro, rays, use_disp, perturb, noise_std,
                          white_background)
+
+
+class _RenderFunction(torch.autograd.Function):
+    """Autograd node of one RenderNet call: forward = nf_render_forward with the neighbour lists kept, backward =
+    nf_render_backward (csrc/nf_render_bwd.cu, nf_mlp_bwd.cu).  Inputs that get gradients: the particle positions and the
+    48 parameter tensors of the two NeRF MLPs (models/renderer.py:43-44)."""
+
+    @staticmethod
+    def forward(ctx, net, call, particles, *params):
+        mode, ro, rays, use_disp, white_background = call
+        with torch.no_grad():
+            out, saved = net._run(mode, particles, ro, rays, use_disp, 0, 0., white_background, _train=True)
+        keys = list(out.keys())
+        ctx.net, ctx.saved, ctx.keys = net, saved, keys
+        ctx.mark_non_differentiable(*[out[k] for k in keys if k.startswith(("num_nn", "mask"))])
+        net._train_keys = keys
+        return tuple(out[k] for k in keys)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        net, sv = ctx.net, ctx.saved
+        n_par = int(lib().nf_render_param_count())
+        dev = sv["ws"].device
+        d_particles = torch.zeros((sv["n_particles"], 3), dtype=torch.float32, device=dev)
+        flats = [torch.zeros(n_par, dtype=torch.float32, device=dev) for _ in range(2)]
+        if sv["args"] is not None:
+            g = {k: (None if t is None else t.detach().to(torch.float32).contiguous()) for k, t in zip(ctx.keys, grads)}
+            v = _lib.RenderWsView()
+            check(lib().nf_render_workspace_view(sv["R"], sv["S0"], sv["NI"], int(net.num_neighbor), _lib.NF_RENDER_SAVE_NEIGHBORS,
+                                                 C.byref(v)), "nf_render_workspace_view")
+            rows = sv["ws"][v.counters: v.counters + 8].view(torch.int32).tolist()          # syncs: sizes the backward
+            need = lib().nf_render_backward_workspace_bytes(sv["R"], sv["S0"], sv["NI"], int(rows[0]), int(rows[1]))
+            bws = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
+            b = _lib.RenderBwdArgs()
+            b.fwd = C.pointer(sv["args"])
+            wbc = net._packed_weights_bwd("nerf_coarse")
+            wbf = net._packed_weights_bwd("nerf_fine") if sv["NI"] > 0 else None
+            b.weights_coarse_bwd, b.weights_fine_bwd = ptr(wbc), ptr(wbf)
+            b.d_rgb0, b.d_depth0, b.d_opacity0 = ptr(g.get("rgb0")), ptr(g.get("depth0")), ptr(g.get("opacity0"))
+            b.d_rgb1, b.d_depth1, b.d_opacity1 = ptr(g.get("rgb1")), ptr(g.get("depth1")), ptr(g.get("opacity1"))
+            b.d_particles, b.d_params_coarse, b.d_params_fine = ptr(d_particles), ptr(flats[0]), ptr(flats[1])
+            b.workspace, b.workspace_bytes = ptr(bws), bws.numel()
+            check(lib().nf_render_backward(C.byref(b), stream_ptr()), "nf_render_backward")
+        pgrads = []
+        for flat, name in zip(flats, ("nerf_coarse", "nerf_fine")):
+            o = 0
+            for p in getattr(net, name).ordered_params():
+                pgrads.append(flat[o:o + p.numel()].view(p.shape))
+                o += p.numel()
+        need_in = ctx.needs_input_grad
+        return (None, None, d_particles if need_in[2] else None) + tuple(gp if need_in[3 + i] else None for i, gp in enumerate(pgrads))
+
+
+def _render_with_grad(net, mode, physical_particles, ro, rays, use_disp, perturb, noise_std, white_background):
+    if perturb != 0 or noise_std != 0:
+        raise NFError("perturb / noise_std are training-time jitter the reference's trainers never enable "
+                      "(trainer/basetrainer.py:284-289); only the deterministic path is implemented")
+    params = list(net.nerf_coarse.ordered_params()) + list(net.nerf_fine.ordered_params())
+    outs = _RenderFunction.apply(net, (mode, ro, rays, use_disp, white_background), physical_particles, *params)
+    return dict(zip(net._train_keys, outs))
 
 
 Renderer = RenderNet      # BASELINE.json's wording

@@ -5,7 +5,8 @@ fixed_radius_search_hash_table=None) -> (pos, vel, num_fluid_neighbors)`, same s
 (`conv0_fluid.kernel/bias/offset`, `dense0_fluid.weight/bias`, ..., `gravity`).  The arithmetic runs in
 libnf_b200.so (csrc/nf_cconv.cu, nf_grid.cu): fixed-radius neighbour lists on the shared spatial grid,
 layer 0 in fp32, layers 1-3 as fused gather + trilinear-scatter + tcgen05 GEMM kernels.
-No CPU or eager fallback.  Forward only (no autograd graph): see DESIGN.md.
+No CPU or eager fallback.  Under autograd (pos / vel / parameters requiring grad) a step is one differentiable node whose
+backward runs nf_transition_backward (feature and filter gradients of the five ContinuousConvs, as Open3D's).
 """
 from __future__ import annotations
 
@@ -94,6 +95,21 @@ class ParticleNet(nn.Module):
             out._keepalive = ps
             self._packed = (key, out)
         return self._packed[1]
+
+    def _packed_weights_bwd(self):
+        """Flipped / transposed filters for the feature-gradient convs (nf_transition_pack_weights_bwd), cached by version."""
+        params = self.ordered_params()
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        hit = getattr(self, "_packed_bwd", None)
+        if hit is None or hit[0] != key:
+            ps = [p.detach().to(torch.float32).contiguous() for p in params]
+            require_cuda(*ps)
+            out = torch.empty(lib().nf_transition_packed_weights_bwd_bytes(), dtype=torch.uint8, device=ps[0].device)
+            arr = (C.c_void_p * 18)(*[p.data_ptr() for p in ps])
+            check(lib().nf_transition_pack_weights_bwd(arr, ptr(out), stream_ptr()), "nf_transition_pack_weights_bwd")
+            out._keepalive = ps
+            self._packed_bwd = (key, out)
+        return self._packed_bwd[1]
 
     def _workspace(self, n, m, device):
         need = lib().nf_transition_workspace_bytes(n, m)
@@ -194,8 +210,16 @@ class ParticleNet(nn.Module):
         fluid has ~42).  If a list is ever truncated, `num_fluid_neighbors` still reports the true count, and an NFError
         is raised by the next `forward` (non-blocking poll) or by `check_neighbor_overflow()` (blocking)."""
         self._poll_overflow()
-        pos_in, vel_in = pos, vel
+        if debug is None and torch.is_grad_enabled() and (
+                any(isinstance(t, torch.Tensor) and t.requires_grad for t in (pos, vel)) or any(p.requires_grad for p in self.parameters())):
+            return _TransitionFunction.apply(self, (box, box_feats, feats), pos, vel, *self.ordered_params())
+        return self._forward_impl(pos, vel, box, box_feats, feats, debug)
+
+    def _forward_impl(self, pos, vel, box, box_feats, feats=None, debug=None, train=False):
         pos, vel, box, box_feats, outs, ws = self._prepare(pos, vel, box, box_feats, feats)
+        if train:      # the backward pass reads this step's neighbour lists and activations: a workspace of its own
+            ws = torch.empty(max(lib().nf_transition_workspace_bytes(pos.shape[0], box.shape[0]), 256), dtype=torch.uint8,
+                             device=pos.device)
         if debug is not None:
             debug["feats0"] = torch.empty((pos.shape[0], 96), device=pos.device)
         a = self._args(pos, vel, box, box_feats, outs, ws, debug=debug)
@@ -203,9 +227,52 @@ class ParticleNet(nn.Module):
         self._post_overflow()
         self.num_fluid_neighbors, self.pos_correction = outs[2], outs[3]
         self._keep = (pos, vel, box, box_feats)
-        return _lib.forward_only([pos_in, vel_in, *self.parameters()], (outs[0], outs[1], outs[2]))
+        if train:
+            return (outs[0], outs[1], outs[2]), dict(args=a, ws=ws, keep=(pos, vel, box, box_feats, outs, self._packed_weights(),
+                                                                           self._box_grid(box)), n=pos.shape[0])
+        return outs[0], outs[1], outs[2]
 
     step = forward      # BASELINE.json's wording: TransModel.step
+
+
+class _TransitionFunction(torch.autograd.Function):
+    """Autograd node of one ParticleNet step: forward = nf_transition_step on a workspace of its own, backward =
+    nf_transition_backward (csrc/nf_cconv.cu).  Differentiable inputs: pos, vel and the 18 parameter tensors."""
+
+    @staticmethod
+    def forward(ctx, net, static, pos, vel, *params):
+        box, box_feats, feats = static
+        with torch.no_grad():
+            outs, saved = net._forward_impl(pos, vel, box, box_feats, feats, None, train=True)
+        ctx.net, ctx.saved = net, saved
+        ctx.mark_non_differentiable(outs[2])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_pos, g_vel, _g_nn):
+        net, sv = ctx.net, ctx.saved
+        n, dev = sv["n"], sv["ws"].device
+        d_pos = torch.zeros((n, 3), dtype=torch.float32, device=dev)
+        d_vel = torch.zeros((n, 3), dtype=torch.float32, device=dev)
+        flat = torch.zeros(int(lib().nf_transition_param_count()), dtype=torch.float32, device=dev)
+        if n > 0:
+            f = lambda t: None if t is None else t.detach().to(torch.float32).contiguous()
+            g_pos, g_vel = f(g_pos), f(g_vel)
+            bws = torch.empty(max(lib().nf_transition_backward_workspace_bytes(n), 256), dtype=torch.uint8, device=dev)
+            b = _lib.TransitionBwdArgs()
+            b.fwd = C.pointer(sv["args"])
+            b.weights_bwd = ptr(net._packed_weights_bwd())
+            b.g_pos_out, b.g_vel_out = ptr(g_pos), ptr(g_vel)
+            b.d_pos, b.d_vel, b.d_params = ptr(d_pos), ptr(d_vel), ptr(flat)
+            b.workspace, b.workspace_bytes = ptr(bws), bws.numel()
+            check(lib().nf_transition_backward(C.byref(b), stream_ptr()), "nf_transition_backward")
+        grads, o = [], 0
+        for p in net.ordered_params():
+            grads.append(flat[o:o + p.numel()].view(p.shape))
+            o += p.numel()
+        need = ctx.needs_input_grad
+        return (None, None, d_pos if need[2] else None, d_vel if need[3] else None) + \
+            tuple(gp if need[4 + i] else None for i, gp in enumerate(grads))
 
 
 TransModel = ParticleNet

@@ -23,20 +23,32 @@ def positional_encoding(x: torch.Tensor, n_freqs: int) -> torch.Tensor:
 
 
 # models/nerf.py:83-124
-def nerf_mlp(sd, net: str, x: torch.Tensor, in_xyz: int, in_dir: int, sigma_only=False, D=8, skips=(4,)):
-    lin = lambda name, v: torch.nn.functional.linear(v, sd[f"{net}.{name}.weight"], sd[f"{net}.{name}.bias"])
+def operand_rounding(dtype=torch.float16):
+    """Straight-through rounding of a tensor to a 16-bit operand type: what the CUDA path's tensor-core layers see."""
+    return lambda t: t + (t.to(dtype).to(t.dtype) - t).detach()
+
+
+def nerf_mlp(sd, net: str, x: torch.Tensor, in_xyz: int, in_dir: int, sigma_only=False, D=8, skips=(4,), quant=None):
+    """`quant` (None = the reference's fp32): a straight-through rounding applied to the operands of the ten layers that
+    run on the tensor cores in the CUDA path (fp16 inputs and weights, fp32 accumulate; the sigma / rgb heads stay fp32).
+    Gradient tests use it to compare like with like: the ReLU kinks of an fp16-operand network sit elsewhere."""
+    q = quant or (lambda t: t)
+    def lin(name, v, tc=True):
+        w = sd[f"{net}.{name}.weight"]
+        return torch.nn.functional.linear(q(v), q(w), sd[f"{net}.{name}.bias"]) if tc else \
+            torch.nn.functional.linear(v, w, sd[f"{net}.{name}.bias"])
     xyz = x[:, :in_xyz]
     h = xyz
     for i in range(D):
         if i in skips:
             h = torch.cat([xyz, h], -1)
         h = torch.relu(lin(f"xyz_encoding_{i + 1}.0", h))
-    sigma = lin("sigma", h)
+    sigma = lin("sigma", h, tc=False)
     if sigma_only:
         return sigma
     final = lin("xyz_encoding_final", h)
     d = torch.relu(lin("dir_encoding.0", torch.cat([final, x[:, in_xyz:in_xyz + in_dir]], -1)))
-    rgb = torch.sigmoid(lin("rgb.0", d))
+    rgb = torch.sigmoid(lin("rgb.0", d, tc=False))
     return torch.cat([rgb, sigma], -1)
 
 
@@ -155,16 +167,16 @@ def feature_widths(enc):
     return in_xyz, in_dir
 
 
-def _pass(sd, net, cfg, radius, K, particles, ro, rays, xyz, z, sigma_only=False):
+def _pass(sd, net, cfg, radius, K, particles, ro, rays, xyz, z, sigma_only=False, quant=None):
     in_xyz, in_dir = feature_widths(cfg.encoding)
     d2, idx, nn = search(xyz, particles, radius, K)
     fx, fd, num_nn = local_geometry_features(d2, nn, xyz, rays, ro, radius, cfg.encoding, sigma_only)
     mask = (d2 != 0).all(-1, keepdim=True).float()
     S = xyz.shape[1]
     if sigma_only:
-        out = nerf_mlp(sd, net, fx, in_xyz, in_dir, sigma_only=True).view(-1, S, 1)
+        out = nerf_mlp(sd, net, fx, in_xyz, in_dir, sigma_only=True, quant=quant).view(-1, S, 1)
     else:
-        out = nerf_mlp(sd, net, torch.cat([fx, fd], 1), in_xyz, in_dir).view(-1, S, 4)
+        out = nerf_mlp(sd, net, torch.cat([fx, fd], 1), in_xyz, in_dir, quant=quant).view(-1, S, 4)
     if cfg.use_mask:
         out = out * mask
     return out, num_nn, mask, idx
@@ -173,6 +185,21 @@ def _pass(sd, net, cfg, radius, K, particles, ro, rays, xyz, z, sigma_only=False
 @torch.no_grad()
 def render_forward(sd, cfg, near, far, particles, ro, rays, mode="forward", white_background=True, debug=False):
     """mode: 'forward' (models/renderer.py:211-270), 'coarse' (:273-307), 'fine' (:310-369)."""
+    return _render_forward(sd, cfg, near, far, particles, ro, rays, mode, white_background, debug)
+
+
+def render_forward_grad(sd, cfg, near, far, particles, ro, rays, mode="forward", white_background=True, z1_override=None,
+                        quant=None):
+    """The same forward with autograd recording: gradients flow to `sd`'s tensors and to `particles` (through the
+    gathered neighbour positions, as through pytorch3d's masked_gather); the importance samples are detached
+    (utils/ray_utils.py:224).  `z1_override` (R, S0+S_imp): use these merged depths instead of resampling (parity tests
+    feed the CUDA path's own depths, which depend on its fp16-operand coarse sigmas)."""
+    with torch.enable_grad():
+        return _render_forward(sd, cfg, near, far, particles, ro, rays, mode, white_background, False, z1_override, quant)
+
+
+def _render_forward(sd, cfg, near, far, particles, ro, rays, mode="forward", white_background=True, debug=False, z1_override=None,
+                    quant=None):
     particles, ro, rays = particles.float().cpu(), ro.float().cpu(), rays.float().cpu()
     radius = cfg.NN_search.search_raduis_scale * cfg.NN_search.particle_radius
     K = cfg.NN_search.N_neighbor
@@ -180,18 +207,22 @@ def render_forward(sd, cfg, near, far, particles, ro, rays, mode="forward", whit
     res = {}
     z0, xyz0 = coarse_samples(near, far, rays, S)
     if mode == "fine":
-        sig, num0, mask0, idx0 = _pass(sd, "nerf_coarse", cfg, radius, K, particles, ro, rays, xyz0, z0, True)
+        sig, num0, mask0, idx0 = _pass(sd, "nerf_coarse", cfg, radius, K, particles, ro, rays, xyz0, z0, True, quant)
         fake = torch.cat([torch.zeros(sig.shape[0], S, 3), sig], -1)
         _, _, w0 = composite(fake, z0, rays, white_background)
     else:
-        out0, num0, mask0, idx0 = _pass(sd, "nerf_coarse", cfg, radius, K, particles, ro, rays, xyz0, z0)
+        out0, num0, mask0, idx0 = _pass(sd, "nerf_coarse", cfg, radius, K, particles, ro, rays, xyz0, z0, False, quant)
         rgb0, depth0, w0 = composite(out0, z0, rays, white_background)
         res.update(rgb0=rgb0, depth0=depth0, opacity0=w0.sum(1), num_nn_0=num0, mask_0=mask0.sum(1))
     if debug:
         res.update(dbg_idx0=idx0, dbg_w0=w0)
     if mode != "coarse" and S_imp > 0:
-        xyz1, z1 = importance_samples(z0, w0, S_imp, rays)
-        out1, num1, mask1, idx1 = _pass(sd, "nerf_fine", cfg, radius, K, particles, ro, rays, xyz1, z1)
+        xyz1, z1 = importance_samples(z0, w0.detach(), S_imp, rays)
+        if z1_override is not None:
+            z1 = z1_override.float().cpu()
+            xyz1 = rays[:, None, 0:3] + rays[:, None, 3:6] * z1[:, :, None]
+        xyz1, z1 = xyz1.detach(), z1.detach()                                  # utils/ray_utils.py:224
+        out1, num1, mask1, idx1 = _pass(sd, "nerf_fine", cfg, radius, K, particles, ro, rays, xyz1, z1, False, quant)
         rgb1, depth1, w1 = composite(out1, z1, rays, white_background)
         res.update(rgb1=rgb1, depth1=depth1, opacity1=w1.sum(1), num_nn_1=num1, mask_1=mask1.sum(1))
         if debug:

@@ -60,3 +60,46 @@ def particle_step(sd, pos, vel, box, box_feats, timestep=1 / 50, radius_scale=1.
     if debug:
         return pos_out, vel_out, nnbr, dict(pos_new=pos_new, vel_new=vel_new, feats=ans)
     return pos_out, vel_out, nnbr
+
+
+def particle_step_grad(sd, pos, vel, box, box_feats, timestep=1 / 50, radius_scale=1.5, particle_radius=0.025, quant=None):
+    """The same step with autograd recording (pure-torch ContinuousConv, oracle/third_party_ops.py::cconv_forward_torch):
+    gradients flow to `sd`'s tensors and to pos / vel exactly as through the reference -- Open3D's ContinuousConv has
+    gradients w.r.t. filter and input features only, positions get theirs through pos_new + delta and
+    vel = (pos_out - pos) / dt (models/transmodel.py:144-148).  `quant`: straight-through rounding applied to the operands
+    of the layers the CUDA path runs with 16-bit operands (conv1/dense1, conv2/dense2: inputs and weights; conv3/dense3:
+    inputs only), so that both evaluations sit on the same side of every ReLU kink."""
+    q = quant or (lambda t: t)
+    window = lambda r: torch.clamp((1 - r) ** 3, 0, 1)                     # models/transmodel.py:73-77
+    with torch.enable_grad():
+        dt = timestep
+        g = sd["gravity"].float()
+        vel_new = vel + g * dt
+        pos_new = pos + (vel + vel_new) / 2 * dt
+        extent = filter_extent(radius_scale, particle_radius)
+        pn = pos_new.detach()
+        nns_ff = tpo.radius_search(pn, pn, 0.5 * extent, True)
+        nns_fb = tpo.radius_search(box, pn, 0.5 * extent, True)
+
+        def conv(name, feats, in_pos, nns, qw=False):
+            k = sd[f"{name}.kernel"]
+            return tpo.cconv_forward_torch(feats, in_pos, pn, extent, q(k) if qw else k, sd[f"{name}.bias"], sd[f"{name}.offset"],
+                                           True, window, nns)[0]
+
+        fluid_feats = torch.cat([torch.ones_like(pos_new[:, 0:1]), vel_new], -1)
+        c0f = conv("conv0_fluid", fluid_feats, pn, nns_ff)
+        d0 = _dense(sd, "dense0_fluid", fluid_feats)
+        c0o = conv("conv0_obstacle", box_feats, box, nns_fb)
+        ans = [torch.cat([c0o, c0f, d0], -1)]
+        for i in range(1, len(LAYER_CHANNELS)):
+            x = q(torch.relu(ans[-1]))
+            tc = i < 3                                                     # conv3 / dense3 run in fp32 on fp16-stored inputs
+            c = conv(f"conv{i}", x, pn, nns_ff, qw=tc)
+            w = sd[f"dense{i}.weight"]
+            d = torch.nn.functional.linear(x, q(w) if tc else w, sd[f"dense{i}.bias"])
+            ans.append(c + d + ans[-1] if d.shape[-1] == ans[-1].shape[-1] else c + d)
+        delta = ans[-1] * (1.0 / 128)
+        pos_out = pos_new + delta
+        vel_out = (pos_out - pos) / dt
+        counts = (nns_ff[1][1:] - nns_ff[1][:-1]).to(torch.float32)
+        return pos_out, vel_out, counts

@@ -38,7 +38,8 @@ def test_size_queries_and_version_without_device():
 
 
 STRUCTS = {"nf_render_args": "RenderArgs", "nf_transition_args": "TransitionArgs", "nf_render_ws_view": "RenderWsView",
-           "nf_cconv_args": "CConvArgs"}
+           "nf_cconv_args": "CConvArgs", "nf_render_bwd_args": "RenderBwdArgs",
+           "nf_transition_bwd_args": "TransitionBwdArgs"}
 
 
 def test_struct_layout_matches_header(tmp_path):

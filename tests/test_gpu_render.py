@@ -271,12 +271,10 @@ def test_render_operand_dtype_switch_and_errors(dev):
         net(c["particles"], c["ro"], c["rays"], 0.0, c["cw"])       # CPU tensors: no fallback
     with pytest.raises(_lib.NFError):
         net(c["particles"].to(dev), c["ro"].to(dev), c["rays"].to(dev), 0.0, c["cw"].to(dev), perturb=1.0)
-    # forward-only this round: a backward through the result fails loudly, not silently
+    # under autograd the call is one differentiable node (tests/test_gpu_backward.py checks the gradients)
     with torch.enable_grad():
         live = net(c["particles"].to(dev), c["ro"].to(dev), c["rays"].to(dev), 0.0, c["cw"].to(dev))
         assert live["rgb1"].requires_grad and not live["num_nn_1"].requires_grad
-        with pytest.raises(_lib.NFError, match="backward"):
-            live["rgb1"].sum().backward()
     assert not net(c["particles"].to(dev), c["ro"].to(dev), c["rays"].to(dev), 0.0, c["cw"].to(dev))["rgb1"].requires_grad
     empty = net(c["particles"].to(dev), c["ro"].to(dev), c["rays"][:0].to(dev), 0.0, c["cw"].to(dev))
     assert empty["rgb1"].shape == (0, 3)
