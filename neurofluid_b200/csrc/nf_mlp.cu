@@ -34,15 +34,14 @@
 namespace nf {
 namespace mlp {
 
-// Weight ring: one stage holds a GROUP of up to G consecutive K-steps of one CTA's share of the weight slabs
-// (16 KB): the issuer waits once and commits once per group, not per MMA.
-template <bool PAIR> struct Ring {
-    static constexpr int G = PAIR ? 4 : 2;                            // K-steps per group
-    static constexpr int STEP = PAIR ? STAGE_BYTES / 2 : STAGE_BYTES;  // bytes of one N=256 K-step held by one CTA
-    static constexpr int STAGE = G * STEP;                             // 16 KB
-};
+// Weight ring: one stage holds one weight UNIT (nf_mlp.cuh): up to 8 consecutive K-steps of one N-HALF of a layer
+// (128 of its 256 output features; 64 of 128 for the dir layer), one CTA's 64 (32) rows of it = 16 KB.  The issuer
+// waits once and commits once per unit, and runs each layer as [half 0, K low] [half 1, K low] [half 0, K high]
+// [half 1, K high]: half 0's accumulator is complete -- and its epilogue running -- while the tensor pipe still works
+// on half 1, and the next layer's low-K units only need the activations half 0's epilogue produces.
 constexpr int NSTAGE = 4;
-constexpr int RING_BYTES = NSTAGE * 16384;
+constexpr int STAGE = 16384;
+constexpr int RING_BYTES = NSTAGE * STAGE;
 
 // shared memory map
 constexpr int SM_HIDDEN = 0;                          // 128 x 256 halves
@@ -52,7 +51,7 @@ constexpr int SM_WRING = SM_PEDIR + 2 * 8 * 2048;     // NSTAGE x 16 KB
 constexpr int SM_SPARAM = SM_WRING + RING_BYTES;
 constexpr int SM_PART = SM_SPARAM + SP_FLOATS * 4;    // 128 x float4: head partial sums of epilogue group B
 constexpr int SM_BAR = SM_PART + 128 * 16;
-constexpr int NUM_BARS = 2 * NSTAGE + 12;
+constexpr int NUM_BARS = 2 * NSTAGE + 14;
 constexpr int SM_TMEM_SLOT = SM_BAR + NUM_BARS * 8;
 constexpr int SM_TOTAL = SM_TMEM_SLOT + 16;
 static_assert(SM_TOTAL <= 232448, "shared memory budget");
@@ -66,9 +65,9 @@ enum Bar {
     B_PEDIR_READY,  // 2
     B_PEDIR_FREE = B_PEDIR_READY + 2,  // 2
     B_ACT_READY = B_PEDIR_FREE + 2,    // 4
-    B_ACC_FULL = B_ACT_READY + 4,      // 2
+    B_ACC_FULL = B_ACT_READY + 4,      // 4: [accumulator buffer (layer parity)][N-half]
 };
-static_assert(B_ACC_FULL + 2 == NUM_BARS, "barrier count");
+static_assert(B_ACC_FULL + 4 == NUM_BARS, "barrier count");
 
 // warp roles
 constexpr int W_EPI = 0;        // warps 0-7: epilogue, two groups of four (TMEM lane quarter = warp & 3)
@@ -77,13 +76,10 @@ constexpr int W_LOAD = 9;       // weight producer
 constexpr int W_PE = 10;        // warps 10-13: positional-encoding producers
 constexpr int NUM_THREADS = 14 * 32;
 
-__device__ __forceinline__ int layer_pe_steps(int l) { return (l == 0 || l == 4) ? KX_STEPS : (l == 9 ? KD_STEPS : 0); }
-// number of weight groups (ring stages) one tile consumes: every layer's PE segment and hidden segment is cut
-// into groups of G K-steps (last group of a segment may be shorter)
-template <int G>
-__device__ __forceinline__ int weight_groups(int nl) {
+// number of weight units (ring stages) one tile consumes
+__device__ __forceinline__ int weight_units(int nl) {
     int n = 0;
-    for (int l = 0; l < nl; ++l) n += (layer_pe_steps(l) + G - 1) / G + (l > 0 ? KH_STEPS / G : 0);
+    for (int l = 0; l < nl; ++l) n += 2 * ((layer_pe_steps(l) + WU_KSTEPS - 1) / WU_KSTEPS + (l > 0 ? KH_STEPS / WU_KSTEPS : 0));
     return n;
 }
 
@@ -99,21 +95,32 @@ __device__ __forceinline__ int weight_groups(int nl) {
 // and barrier addresses stay in uniform registers; it waits and commits once per GROUP of K-steps (one ring
 // stage), not per MMA.  (Round-1 build: one divergent lane, wait + commit per MMA = ~70 SASS instructions
 // and ~360 cycles per 178-cycle MMA -- the kernel was issue-bound, profiles/r01_notes.md.)
-template <bool BF16, bool PAIR>
+// CL = cluster size: 2 = one CTA pair; 4 = two pairs that share every weight unit: each CTA fetches a QUARTER of a unit's
+// rows and multicasts it to the CTA of the other pair that needs the same rows, halving the L2 -> SM weight traffic per
+// FLOP once more (the kernel sat at the ~6.9 TB/s L2 -> SM ceiling: every pair streamed the whole 1.34 MB network per
+// 256 rows).  Both pairs then walk the ring in lockstep: a stage is free when BOTH pairs' MMAs have read it (their
+// commits are multicast to all four CTAs), so every pair of the grid runs the same number of passes (a pair without a
+// real tile computes an empty one).
+template <bool BF16, int CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp(const KernelArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    constexpr int G = Ring<PAIR>::G;
-    constexpr int STEP = Ring<PAIR>::STEP;
-    constexpr int STAGE = Ring<PAIR>::STAGE;
-    constexpr int TPU = PAIR ? 2 : 1;   // tiles per unit (CTA or CTA pair) per pass
+    static_assert(CL == 2 || CL == 4, "cluster of one or two CTA pairs");
+    constexpr bool PAIR = true;
+    constexpr int TPU = 2;              // tiles per unit (CTA pair) per pass
     const int warp = uniform((int)(threadIdx.x >> 5)), lane = threadIdx.x & 31;
-    const uint32_t crank = PAIR ? uniform(cluster_ctarank()) : 0u;
-    const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-    const int nunits = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const uint32_t crank = uniform(cluster_ctarank());
+    const uint32_t prank = crank & 1u;                          // rank inside the pair
+    const uint32_t pbase = crank & ~1u;                         // cluster rank of the pair's first CTA (its MMA issuer)
+    const uint16_t pair_mask = (uint16_t)(3u << pbase);         // commits that concern this pair only
+    const uint16_t all_mask = (uint16_t)((1u << CL) - 1u);      // "weight stage consumed": every CTA that shares the ring
+    const int unit = (int)(blockIdx.x >> 1);
+    const int nunits = (int)(gridDim.x >> 1);
     const int n_rows = uniform(a.n_rows_dev ? min(*a.n_rows_dev, a.n_rows_cap) : a.n_rows_host);
     const int ntiles = (n_rows + TILE_M - 1) / TILE_M;
-    const int npass = (ntiles + TPU - 1) / TPU;
-    if (unit >= npass) return;          // both CTAs of a pair leave together
+    // every pair runs the same number of passes (CL = 4: the two pairs of a cluster share the weight ring); a pass beyond
+    // the last tile pair works on rows >= n_rows: zero records in, nothing written
+    const int npass = ((ntiles + TPU - 1) / TPU + nunits - 1) / nunits * nunits;
+    if (ntiles == 0) return;
     const int nl = a.n_layers;
 #ifdef NF_TUNING
     const bool no_weights = (a.desc_swap & 16) != 0;   // tuning builds only: do not stream / wait for weights (timing only)
@@ -128,22 +135,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp(const KernelArgs a)
     float4* part = reinterpret_cast<float4*>(smem + SM_PART);
     auto bar = [&](int i) { return s_bar + 8u * (uint32_t)i; };
     // "operand ready" barriers are consumed by the issuer in CTA rank 0
-    auto ready_bar = [&](int i) { return PAIR ? mapa_rank(bar(i), 0) : bar(i); };
+    auto ready_bar = [&](int i) { return mapa_rank(bar(i), pbase); };
     constexpr uint32_t READY_COUNT = PAIR ? 8 : 4;   // PE tiles: one arrive per producing warp (4 per CTA)
     constexpr uint32_t ACT_COUNT = PAIR ? 16 : 8;    // activation chunks: all 8 epilogue warps of a CTA
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSTAGE; ++i) {
-            mbar_init(bar(B_WFULL + i), (PAIR && crank == 0) ? 2 : 1);   // own bulk copies (+ the peer's relay)
-            mbar_init(bar(B_WEMPTY + i), 1);
+            mbar_init(bar(B_WFULL + i), prank == 0 ? 2 : 1);   // own expect_tx arrive (+ the pair peer's relay)
+            mbar_init(bar(B_WEMPTY + i), CL / 2);              // one commit per pair sharing the ring
         }
         mbar_init(bar(B_PEXYZ_READY), READY_COUNT);
         mbar_init(bar(B_PEXYZ_FREE), 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar(B_PEDIR_READY + i), READY_COUNT);
             mbar_init(bar(B_PEDIR_FREE + i), 1);
-            mbar_init(bar(B_ACC_FULL + i), 1);
         }
+        for (int i = 0; i < 4; ++i) mbar_init(bar(B_ACC_FULL + i), 1);
         for (int i = 0; i < 4; ++i) mbar_init(bar(B_ACT_READY + i), ACT_COUNT);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -160,89 +167,84 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp(const KernelArgs a)
     const uint32_t tmem_base = uniform(*reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM_SLOT));
 
     if (warp == W_ISSUE) {
-        if (crank == 0) {
+        if (prank == 0) {
             // ================================================================ MMA issuer (rank 0; converged warp)
             const uint64_t adesc_hidden = umma_desc(s_hidden, 2048u, 128u);
             const uint64_t adesc_pexyz = umma_desc(s_pexyz, 2048u, 128u);
             const uint64_t adesc_pedir = umma_desc(s_pedir, 2048u, 128u);
-            const uint32_t idesc256 = umma_idesc(256, BF16, PAIR ? 2 * TILE_M : TILE_M);
-            const uint32_t idesc128 = umma_idesc(128, BF16, PAIR ? 2 * TILE_M : TILE_M);
-            const uint64_t bdesc256 = umma_desc(s_wring, (PAIR ? 128u : 256u) * 16u, 128u);
-            const uint64_t bdesc128 = umma_desc(s_wring, (PAIR ? 64u : 128u) * 16u, 128u);
+            const uint32_t idesc128 = umma_idesc(128, BF16, 2 * TILE_M);
+            const uint32_t idesc64 = umma_idesc(64, BF16, 2 * TILE_M);
             uint32_t ws = 0, wph = 0, hidw = 0, lc = 0;
             int ti = 0;
             for (int pass = unit; pass < npass; pass += nunits, ++ti) {
                 const bool tracing = a.trace && blockIdx.x == 0 && ti == 2 && lane == 0;
                 for (int l = 0; l < nl; ++l, ++lc) {
-                    const uint32_t d_tmem = tmem_base + (lc & 1) * 256;
                     const bool n128 = (l == 9);
-                    const uint32_t idesc = n128 ? idesc128 : idesc256;
-                    const uint64_t bdesc0 = n128 ? bdesc128 : bdesc256;
-                    const uint32_t bstep = (n128 ? STEP / 2 : STEP) >> 4;      // descriptor units (16 B) per K-step
-                    uint32_t acc = 0;
+                    const uint32_t nhalf = n128 ? 64u : 128u;                  // N of one MMA = one N-half of the layer
+                    const uint32_t rpc = nhalf >> 1;                           // rows of B each CTA of the pair supplies
+                    const uint32_t d_tmem = tmem_base + (lc & 1) * 256;
+                    const uint32_t idesc = n128 ? idesc64 : idesc128;
+                    const uint64_t bdesc0 = umma_desc(s_wring, rpc * 16u, 128u);
+                    const uint32_t bstep = (2u * rpc * 16u) >> 4;              // descriptor units (16 B) per K-step of a unit
+                    uint32_t acc0 = 0, acc1 = 0;
                     NF_TRACE(100 + l * 8);
                     const int npe = layer_pe_steps(l);
-                    if (npe) {
-                        uint64_t adesc;
-                        if (l == 9) {
-                            mbar_wait(bar(B_PEDIR_READY + (ti & 1)), (ti >> 1) & 1);
-                            adesc = adesc_pedir + (uint64_t)((ti & 1) * ((8 * 2048) >> 4));
-                        } else {
-                            mbar_wait(bar(B_PEXYZ_READY), ti & 1);
-                            adesc = adesc_pexyz;
-                        }
-                        for (int j0 = 0; j0 < npe; j0 += G) {
-                            const int g = min(G, npe - j0);
-                            if (!no_weights) mbar_wait(bar(B_WFULL + ws), wph);
-                            tc_fence_after();
-                            if (elect_one()) {
-                                const uint64_t bd = bdesc0 + (uint64_t)(ws * (STAGE >> 4));
-#pragma unroll
-                                for (int j = 0; j < G; ++j) {
-                                    if (j < g) {
-                                        umma_f16<PAIR>(d_tmem, adesc + (uint64_t)((j0 + j) * (4096 >> 4)), bd + (uint64_t)(j * bstep),
-                                                       idesc, acc);
-                                        acc = 1;
-                                    }
-                                }
-                                umma_commit<PAIR>(bar(B_WEMPTY + ws));
+                    for (int seg = 0; seg < 2; ++seg) {
+                        const int nsteps = seg == 0 ? npe : (l > 0 ? KH_STEPS : 0);
+                        if (nsteps == 0) continue;
+                        uint64_t adesc = adesc_hidden;
+                        if (seg == 0) {
+                            if (l == 9) {
+                                mbar_wait(bar(B_PEDIR_READY + (ti & 1)), (ti >> 1) & 1);
+                                adesc = adesc_pedir + (uint64_t)((ti & 1) * ((8 * 2048) >> 4));
+                            } else {
+                                mbar_wait(bar(B_PEXYZ_READY), ti & 1);
+                                adesc = adesc_pexyz;
                             }
-                            __syncwarp();
-                            acc = 1;
-                            if (++ws == NSTAGE) { ws = 0; wph ^= 1; }
                         }
-                        if (l == 4 && elect_one()) umma_commit<PAIR>(bar(B_PEXYZ_FREE));
+                        const bool last_seg = (seg == 1) || (l == 0);
+                        for (int k0 = 0; k0 < nsteps; k0 += WU_KSTEPS) {
+                            const int g = min(WU_KSTEPS, nsteps - k0);
+                            if (seg == 1) {      // the 8 K-steps of this block read activation chunks k0/4 and k0/4 + 1
+                                mbar_wait(bar(B_ACT_READY + (k0 >> 2)), hidw & 1);
+                                NF_TRACE(100 + l * 8 + 1 + (k0 >> 2));
+                                mbar_wait(bar(B_ACT_READY + (k0 >> 2) + 1), hidw & 1);
+                                NF_TRACE(100 + l * 8 + 2 + (k0 >> 2));
+                            }
+                            const bool last_blk = last_seg && (k0 + WU_KSTEPS >= nsteps);
+#pragma unroll
+                            for (uint32_t nh = 0; nh < 2; ++nh) {
+                                if (!no_weights) mbar_wait(bar(B_WFULL + ws), wph);
+                                tc_fence_after();
+                                if (elect_one()) {
+                                    const uint64_t bd = bdesc0 + (uint64_t)(ws * (STAGE >> 4));
+                                    uint32_t acc = nh ? acc1 : acc0;
+#pragma unroll
+                                    for (int j = 0; j < WU_KSTEPS; ++j) {
+                                        if (j < g) {
+                                            umma_f16<PAIR>(d_tmem + nh * nhalf, adesc + (uint64_t)((k0 + j) * (4096 >> 4)), bd + (uint64_t)(j * bstep),
+                                                           idesc, acc);
+                                            acc = 1;
+                                        }
+                                    }
+                                    umma_commit<PAIR>(bar(B_WEMPTY + ws), all_mask);
+                                    if (last_blk) umma_commit<PAIR>(bar(B_ACC_FULL + (lc & 1) * 2 + nh), pair_mask);
+                                }
+                                __syncwarp();
+                                if (nh) acc1 = 1; else acc0 = 1;
+                                if (++ws == NSTAGE) { ws = 0; wph ^= 1; }
+                            }
+                        }
+                        if (seg == 0 && l == 4) {
+                            if (elect_one()) umma_commit<PAIR>(bar(B_PEXYZ_FREE), pair_mask);
+                            __syncwarp();
+                        }
+                    }
+                    if (l > 0) ++hidw;
+                    if (l == 9) {
+                        if (elect_one()) umma_commit<PAIR>(bar(B_PEDIR_FREE + (ti & 1)), pair_mask);
                         __syncwarp();
                     }
-                    if (l > 0) {
-                        for (int j0 = 0; j0 < KH_STEPS; j0 += G) {
-                            if ((j0 & 3) == 0) {
-                                mbar_wait(bar(B_ACT_READY + (j0 >> 2)), hidw & 1);
-                                NF_TRACE(100 + l * 8 + 1 + (j0 >> 2));
-                            }
-                            if (!no_weights) mbar_wait(bar(B_WFULL + ws), wph);
-                            tc_fence_after();
-                            if (elect_one()) {
-                                const uint64_t bd = bdesc0 + (uint64_t)(ws * (STAGE >> 4));
-#pragma unroll
-                                for (int j = 0; j < G; ++j) {
-                                    umma_f16<PAIR>(d_tmem, adesc_hidden + (uint64_t)((j0 + j) * (4096 >> 4)), bd + (uint64_t)(j * bstep),
-                                                   idesc, acc);
-                                    acc = 1;
-                                }
-                                umma_commit<PAIR>(bar(B_WEMPTY + ws));
-                            }
-                            __syncwarp();
-                            acc = 1;
-                            if (++ws == NSTAGE) { ws = 0; wph ^= 1; }
-                        }
-                        ++hidw;
-                    }
-                    if (elect_one()) {
-                        umma_commit<PAIR>(bar(B_ACC_FULL + (lc & 1)));
-                        if (l == 9) umma_commit<PAIR>(bar(B_PEDIR_FREE + (ti & 1)));
-                    }
-                    __syncwarp();
                     NF_TRACE(100 + l * 8 + 5);
                 }
             }
@@ -250,8 +252,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp(const KernelArgs a)
             // ================================================================ relay (rank 1): tells the issuer
             // that this CTA's share of a weight group has landed
             uint32_t ws = 0, wph = 0;
-            const int ngroups = weight_groups<G>(nl);
-            const uint32_t remote0 = mapa_rank(bar(B_WFULL), 0);
+            const int ngroups = weight_units(nl);
+            const uint32_t remote0 = mapa_rank(bar(B_WFULL), pbase);
             for (int pass = unit; pass < npass; pass += nunits) {
                 for (int s = 0; s < ngroups; ++s) {
                     mbar_wait(bar(B_WFULL + ws), wph);
@@ -267,20 +269,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp(const KernelArgs a)
             for (int pass = unit; pass < npass; pass += nunits) {
                 const uint8_t* src = a.packed;
                 for (int l = 0; l < nl; ++l) {
-                    const uint32_t full = (l == 9) ? 4096u : 8192u;          // bytes of one K-step of this layer
-                    const uint32_t mine = PAIR ? full / 2 : full;            // PAIR layout: [half][k-chunk][row][8]
+                    const uint32_t rpc = (l == 9) ? 32u : 64u;
                     const int npe = layer_pe_steps(l);
                     for (int seg = 0; seg < 2; ++seg) {
                         const int nsteps = seg == 0 ? npe : (l > 0 ? KH_STEPS : 0);
-                        for (int j0 = 0; j0 < nsteps; j0 += G) {
-                            const int g = min(G, nsteps - j0);
-                            mbar_wait(bar(B_WEMPTY + ws), wph ^ 1);
-                            mbar_arrive_expect_tx(bar(B_WFULL + ws), (uint32_t)g * mine);
-                            for (int j = 0; j < g; ++j)
-                                bulk_g2s(s_wring + ws * STAGE + j * mine, src + (size_t)j * full + (PAIR ? crank * mine : 0u), mine,
-                                         bar(B_WFULL + ws));
-                            src += (size_t)g * full;
-                            if (++ws == NSTAGE) { ws = 0; wph ^= 1; }
+                        for (int k0 = 0; k0 < nsteps; k0 += WU_KSTEPS) {
+                            const uint32_t mine = (uint32_t)min(WU_KSTEPS, nsteps - k0) * 2u * rpc * 16u;   // this CTA's rows of the unit
+                            for (int nh = 0; nh < 2; ++nh) {
+                                mbar_wait(bar(B_WEMPTY + ws), wph ^ 1);
+                                mbar_arrive_expect_tx(bar(B_WFULL + ws), mine);
+                                if constexpr (CL == 4) {       // my quarter -> me and the CTA with my pair rank in the other pair
+                                    const uint32_t q = mine >> 1, sub = crank >> 1;
+                                    bulk_g2s_multicast(s_wring + ws * STAGE + sub * q, src + prank * mine + sub * q, q, bar(B_WFULL + ws),
+                                                       (uint16_t)((1u << prank) | (1u << (prank + 2))));
+                                } else {
+                                    bulk_g2s(s_wring + ws * STAGE, src + prank * mine, mine, bar(B_WFULL + ws));
+                                }
+                                src += 2 * mine;
+                                if (++ws == NSTAGE) { ws = 0; wph ^= 1; }
+                            }
                         }
                     }
                 }
@@ -303,11 +310,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp(const KernelArgs a)
         const uint32_t act_ready0 = ready_bar(B_ACT_READY);
         for (int pass = unit; pass < npass; pass += nunits, ++ti) {
             const bool tracing = a.trace && blockIdx.x == 0 && ti == 2 && (tr == 0);
-            const int row = (pass * TPU + (int)crank) * TILE_M + tr;
+            const int row = (pass * TPU + (int)prank) * TILE_M + tr;
             float sigma = 0.f;
             for (int l = 0; l < nl; ++l, ++lc) {
                 const uint32_t buf = lc & 1;
-                mbar_wait(bar(B_ACC_FULL + buf), (lc >> 1) & 1);
+                mbar_wait(bar(B_ACC_FULL + buf * 2), (lc >> 1) & 1);          // N-half 0 complete (half 1 still accumulating)
                 tc_fence_after();
                 if (grp == 0) NF_TRACE(l * 8);
                 const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + buf * 256 + grp * 32;
@@ -319,6 +326,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp(const KernelArgs a)
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         tmem_ld_wait();
+                        if (c == 1) {       // columns 128.. belong to N-half 1
+                            mbar_wait(bar(B_ACC_FULL + buf * 2 + 1), (lc >> 1) & 1);
+                            tc_fence_after();
+                        }
                         if (c < 3) tmem_ld32(taddr + (c + 1) * 64, v[(c + 1) & 1]);
                         const uint32_t* vc = v[c & 1];
                         float f[32];
@@ -377,6 +388,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp(const KernelArgs a)
                     const float* wrgb = sp + SP_WRGB + grp * 32;
                     uint32_t v[2][32];
                     tmem_ld32(taddr, v[0]);
+                    mbar_wait(bar(B_ACC_FULL + buf * 2 + 1), (lc >> 1) & 1);   // the dir layer's halves are 64 columns each
+                    tc_fence_after();
                     tmem_ld32(taddr + 64, v[1]);
                     tmem_ld_wait();
 #pragma unroll
@@ -416,7 +429,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp(const KernelArgs a)
         const uint32_t pedir_ready0 = ready_bar(B_PEDIR_READY), pedir_ready1 = ready_bar(B_PEDIR_READY + 1);
         for (int pass = unit; pass < npass; pass += nunits, ++ti) {
             const bool tracing = a.trace && blockIdx.x == 0 && ti == 2 && tp == 0;
-            const int row = (pass * TPU + (int)crank) * TILE_M + tp;
+            const int row = (pass * TPU + (int)prank) * TILE_M + tp;
             float r[16];
             if (row < n_rows) {
                 const float4* src = reinterpret_cast<const float4*>(a.records + (size_t)row * 16);
@@ -490,37 +503,59 @@ __device__ __forceinline__ void step_source(int s, int& layer, int& k0, int& src
     else { layer = 9; k0 = (s - 158) * 16; src_off = 0; src_valid = 256; ld = 310; }
 }
 
-// pair != 0: rows of every slab are split in two halves, one per CTA of a pair: [half][kc][n % (nrows/2)][e]
+// byte offset of weight unit (layer, segment, K-block k0, N-half nh) in the packed stream (see nf_mlp.cuh)
+__device__ __forceinline__ size_t unit_offset(int layer, int seg, int k0, int nh) {
+    size_t off = 0;
+    for (int l = 0; l <= layer; ++l) {
+        const int rpc = (l == 9) ? 32 : 64;
+        for (int sg = 0; sg < 2; ++sg) {
+            const int nsteps = sg == 0 ? layer_pe_steps(l) : (l > 0 ? KH_STEPS : 0);
+            for (int kb = 0; kb < nsteps; kb += WU_KSTEPS) {
+                const int g = min(WU_KSTEPS, nsteps - kb);
+                for (int h = 0; h < 2; ++h) {
+                    if (l == layer && sg == seg && kb == k0 && h == nh) return off;
+                    off += (size_t)2 * g * 2 * rpc * 16;
+                }
+            }
+        }
+    }
+    return off;
+}
+
 template <bool BF16>
-__global__ void k_pack_weights(PackArgs p, uint8_t* out, int pair) {
-    // one thread per (step, kc, n): writes 8 halves (16 B)
+__global__ void k_pack_weights(PackArgs p, uint8_t* out) {
+    // one thread per (K-step, kc, n): writes 8 halves (16 B)
     const int total = N256_STEPS * 2 * 256 + N128_STEPS * 2 * 128;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < total) {
-        int s, kc, n, nrows;
-        size_t byte_off;
+        int s, kc, n;
         if (t < N256_STEPS * 512) {
-            s = t / 512; kc = (t % 512) / 256; n = t % 256; nrows = 256;
-            byte_off = (size_t)s * 8192;
+            s = t / 512; kc = (t % 512) / 256; n = t % 256;
         } else {
             const int u = t - N256_STEPS * 512;
-            s = N256_STEPS + u / 256; kc = (u % 256) / 128; n = u % 128; nrows = 128;
-            byte_off = (size_t)N256_STEPS * 8192 + (size_t)(s - N256_STEPS) * 4096;
+            s = N256_STEPS + u / 256; kc = (u % 256) / 128; n = u % 128;
         }
-        int layer, k0, src_off, src_valid, ld;
-        step_source(s, layer, k0, src_off, src_valid, ld);
+        int layer, k0c, src_off, src_valid, ld;
+        step_source(s, layer, k0c, src_off, src_valid, ld);
         const float* W = p.w[layer];
         uint32_t pk[4];
 #pragma unroll
         for (int e = 0; e < 8; e += 2) {
-            const int ka = k0 + kc * 8 + e, kb = ka + 1;
+            const int ka = k0c + kc * 8 + e, kb = ka + 1;
             const float va = ka < src_valid ? W[(size_t)n * ld + src_off + ka] : 0.f;
             const float vb = kb < src_valid ? W[(size_t)n * ld + src_off + kb] : 0.f;
             pk[e >> 1] = pack2<BF16>(va, vb);
         }
-        const int nh = pair ? nrows / 2 : nrows;
-        uint4* dst = reinterpret_cast<uint4*>(out + byte_off + ((size_t)((n / nh) * 2 + kc) * nh + (n % nh)) * 16);
-        *dst = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        // destination: the unit of (layer, segment, K-block, N-half) this (K-step, row) belongs to
+        const int seg = (layer_pe_steps(layer) > 0 && src_valid != 256) ? 0 : 1;      // encoded-feature segments are 198 / 54 wide
+        const int kseg = k0c / 16;
+        const int rpc = (layer == 9) ? 32 : 64;
+        const int kblk = (kseg / WU_KSTEPS) * WU_KSTEPS;
+        const int nsteps = seg == 0 ? layer_pe_steps(layer) : KH_STEPS;
+        const int g = min(WU_KSTEPS, nsteps - kblk);
+        const int nh = n / (2 * rpc), r = (n / rpc) % 2, row = n % rpc;
+        const size_t off = unit_offset(layer, seg, kblk, nh) + ((((size_t)r * g + (kseg - kblk)) * 2 + kc) * rpc + row) * 16;
+        *reinterpret_cast<uint4*>(out + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
     // small params
     float* sp = reinterpret_cast<float*>(out + W_BYTES);
@@ -537,33 +572,19 @@ __global__ void k_pack_weights(PackArgs p, uint8_t* out, int pair) {
     }
 }
 
-// CTA pairs (cta_group::2) always; a build with -DNF_TUNING can fall back to single CTAs through NF_MLP_PAIR=0
-bool pair_mode() {
-#ifdef NF_TUNING
-    static int mode = -1;
-    if (mode < 0) {
-        const char* v = getenv("NF_MLP_PAIR");
-        mode = v ? (atoi(v) != 0) : 1;
-    }
-    return mode != 0;
-#else
-    return true;
-#endif
-}
-
-template <bool BF16, bool PAIR>
-static int launch_t(const KernelArgs& a, cudaStream_t st) {
-    auto* kern = k_nerf_mlp<BF16, PAIR>;
+template <bool BF16, int CL>
+static int launch_t(const KernelArgs& a, cudaStream_t st, int grid) {
+    auto* kern = k_nerf_mlp<BF16, CL>;
     // per device, not per process: set it on every launch (a few hundred ns) instead of caching a flag
     NF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(num_sms() & ~1), 1, 1);
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
     cfg.blockDim = dim3(NUM_THREADS, 1, 1);
     cfg.dynamicSmemBytes = SM_TOTAL;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+    attr[0].val.clusterDim.x = CL;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
@@ -573,10 +594,48 @@ static int launch_t(const KernelArgs& a, cudaStream_t st) {
     return NF_OK;
 }
 
+// How many clusters of four CTAs (one CTA per SM: 227 KB of shared memory each) the device can hold at once: a cluster
+// lives inside one GPC, so GPCs whose SM count is not a multiple of four leave SMs idle.  Queried once per device.
+template <bool BF16>
+static int max_clusters4() {
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 0;
+    if (cached[dev] == 0) {
+        auto* kern = k_nerf_mlp<BF16, 4>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(num_sms() & ~3), 1, 1);
+        cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = SM_TOTAL;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { n = 0; cudaGetLastError(); }
+        cached[dev] = n > 0 ? n : -1;
+    }
+    return cached[dev] > 0 ? cached[dev] : 0;
+}
+
+// Clusters of two CTA pairs when (nearly) every SM fits into one, else plain CTA pairs (cluster of 2)
 int launch(const KernelArgs& a, int dtype, cudaStream_t st) {
     const bool bf = dtype == NF_DTYPE_BF16;
-    if (pair_mode()) return bf ? launch_t<true, true>(a, st) : launch_t<false, true>(a, st);
-    return bf ? launch_t<true, false>(a, st) : launch_t<false, false>(a, st);
+    const int c4 = bf ? max_clusters4<true>() : max_clusters4<false>();
+    const int pairs_grid = num_sms() & ~1;
+#ifdef NF_TUNING
+    const char* e = getenv("NF_MLP_CLUSTER");
+    const bool want4 = e ? atoi(e) == 4 : true;
+#else
+    const bool want4 = true;
+#endif
+    if (want4 && c4 * 4 * 10 >= pairs_grid * 9) {       // at most 10 % of the SMs left without a cluster
+        const int grid = 4 * (c4 < num_sms() / 4 ? c4 : num_sms() / 4);
+        return bf ? launch_t<true, 4>(a, st, grid) : launch_t<false, 4>(a, st, grid);
+    }
+    return bf ? launch_t<true, 2>(a, st, pairs_grid) : launch_t<false, 2>(a, st, pairs_grid);
 }
 
 }  // namespace mlp
@@ -598,9 +657,9 @@ extern "C" int nf_render_pack_weights(const float* const* params, int dtype, voi
     }
     const int total = mlp::N256_STEPS * 512 + mlp::N128_STEPS * 256;
     if (dtype == NF_DTYPE_BF16)
-        mlp::k_pack_weights<true><<<(total + 255) / 256, 256, 0, st>>>(p, (uint8_t*)packed_out, mlp::pair_mode());
+        mlp::k_pack_weights<true><<<(total + 255) / 256, 256, 0, st>>>(p, (uint8_t*)packed_out);
     else
-        mlp::k_pack_weights<false><<<(total + 255) / 256, 256, 0, st>>>(p, (uint8_t*)packed_out, mlp::pair_mode());
+        mlp::k_pack_weights<false><<<(total + 255) / 256, 256, 0, st>>>(p, (uint8_t*)packed_out);
     NF_LAUNCH_OK();
     return NF_OK;
 }

@@ -27,6 +27,14 @@ constexpr int SP_BRGB = 3204;    // [3] (+1 pad)
 constexpr int SP_FLOATS = 3208;
 static_assert(PACKED_BYTES == W_BYTES + SP_FLOATS * 4, "packed size");
 
+// Packed weight stream = a sequence of UNITS in consumption order:
+//   for layer l (0..9; 8 = xyz_encoding_final, 9 = dir_encoding), for segment (0: encoded-feature columns, 1: hidden columns),
+//   for K-block k0 = 0, 8, ... of the segment's K-steps (16 input columns each), for N-half nh = 0, 1 of the layer's outputs:
+//   unit = [CTA r of the pair (2)][K-step j < g][8-column chunk kc (2)][row (rpc)][8 halves]
+//   with rpc = 64 (32 for the dir layer) rows per CTA: output feature nh * 2 rpc + r * rpc + row.
+constexpr int WU_KSTEPS = 8;
+__host__ __device__ inline int layer_pe_steps(int l) { return (l == 0 || l == 4) ? KX_STEPS : (l == 9 ? KD_STEPS : 0); }
+
 
 struct KernelArgs {
     const uint8_t* packed;   // weight slabs + small params

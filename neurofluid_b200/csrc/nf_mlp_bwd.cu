@@ -220,12 +220,31 @@ __global__ void __launch_bounds__(DG_THREADS, 1) k_mlp_bwd_dgrad(const DgradArgs
                 for (int k = 0; k < 20; ++k) {
                     int npe, nh, slab;
                     step_shape(k, npe, nh, slab);
-                    const int fills = (npe + nh) * (k < 10 ? 1 : 2);      // backward K-steps: a "hi" and a "lo" slab
+                    if (k < 10) {
+                        // forward weights: the forward kernel's unit stream (nf_mlp.cuh); every unit holds the two CTA-pair
+                        // halves one after the other -- each is one 16 KB stage here
+                        const uint32_t rpc = (k == 9) ? 32u : 64u;
+                        for (int seg = 0; seg < 2; ++seg) {
+                            const int nsteps = seg == 0 ? npe : nh;
+                            for (int k0 = 0; k0 < nsteps; k0 += WU_KSTEPS) {
+                                const uint32_t piece = (uint32_t)min(WU_KSTEPS, nsteps - k0) * 2u * rpc * 16u;
+                                for (int q = 0; q < 4; ++q) {          // (N-half, CTA half) = 4 pieces per K-block
+                                    mbar_wait(bar(B_WEMPTY + ws), wph ^ 1);
+                                    mbar_arrive_expect_tx(bar(B_WFULL + ws), piece);
+                                    bulk_g2s(s_wring + ws * WSTAGE, srcf, piece, bar(B_WFULL + ws));
+                                    srcf += piece;
+                                    if (++ws == NST) { ws = 0; wph ^= 1; }
+                                }
+                            }
+                        }
+                        continue;
+                    }
+                    const int fills = nh * 2;      // backward K-steps: a "hi" and a "lo" slab
                     for (int j = 0; j < fills; ++j) {
                         mbar_wait(bar(B_WEMPTY + ws), wph ^ 1);
                         mbar_arrive_expect_tx(bar(B_WFULL + ws), (uint32_t)slab);
-                        bulk_g2s(s_wring + ws * WSTAGE, k < 10 ? srcf : srcb, (uint32_t)slab, bar(B_WFULL + ws));
-                        if (k < 10) srcf += slab; else srcb += slab;
+                        bulk_g2s(s_wring + ws * WSTAGE, srcb, (uint32_t)slab, bar(B_WFULL + ws));
+                        srcb += slab;
                         if (++ws == NST) { ws = 0; wph ^= 1; }
                     }
                 }
@@ -235,7 +254,6 @@ __global__ void __launch_bounds__(DG_THREADS, 1) k_mlp_bwd_dgrad(const DgradArgs
         // ================================================================ MMA issuer (one lane)
         if (lane == 0) {
             uint32_t ws = 0, wph = 0, gstep = 0;
-            const uint32_t idf128 = umma_idesc(128, FBF16, TILE_M), idf64 = umma_idesc(64, FBF16, TILE_M);
             const uint32_t idb256 = umma_idesc(256, true, TILE_M), idb208 = umma_idesc(208, true, TILE_M), idb64 = umma_idesc(64, true, TILE_M);
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 for (int k = 0; k < 20; ++k, ++gstep) {
@@ -244,23 +262,35 @@ __global__ void __launch_bounds__(DG_THREADS, 1) k_mlp_bwd_dgrad(const DgradArgs
                     int npe, nh, slab;
                     step_shape(k, npe, nh, slab);
                     uint32_t acc = 0;
-                    for (int j = 0; j < npe + nh; ++j) {
+                    if (k < 10) {
+                        const uint32_t rpc = (k == 9) ? 32u : 64u;
+                        const uint32_t idf = umma_idesc((int)rpc, FBF16, TILE_M);
+                        uint32_t accq[4] = {0u, 0u, 0u, 0u};
+                        for (int seg = 0; seg < 2; ++seg) {
+                            const int nsteps = seg == 0 ? npe : nh;
+                            const uint32_t abase = seg == 0 ? (k == 9 ? s_pedir : s_pexyz) : s_hidden;
+                            for (int k0 = 0; k0 < nsteps; k0 += WU_KSTEPS) {
+                                const int g = min(WU_KSTEPS, nsteps - k0);
+                                for (uint32_t q = 0; q < 4; ++q) {      // q = N-half * 2 + CTA half: output columns q * rpc ...
+                                    mbar_wait(bar(B_WFULL + ws), wph);
+                                    tc_fence_after();
+                                    const uint32_t sw = s_wring + ws * WSTAGE;
+                                    for (int j = 0; j < g; ++j) {
+                                        umma_f16<false>(tmem_base + TM_H + q * rpc, umma_desc(abase + (uint32_t)(k0 + j) * 4096u, 2048u, 128u),
+                                                        umma_desc(sw + (uint32_t)j * 2u * rpc * 16u, rpc * 16u, 128u), idf, accq[q]);
+                                        accq[q] = 1;
+                                    }
+                                    umma_commit<false>(bar(B_WEMPTY + ws));
+                                    if (++ws == NST) { ws = 0; wph ^= 1; }
+                                }
+                            }
+                        }
+                    }
+                    for (int j = 0; k >= 10 && j < nh; ++j) {
                         mbar_wait(bar(B_WFULL + ws), wph);
                         tc_fence_after();
                         const uint32_t sw = s_wring + ws * WSTAGE;
-                        if (k < 10) {
-                            const bool pe = j < npe;
-                            const uint32_t abase = pe ? (k == 9 ? s_pedir : s_pexyz) : s_hidden;
-                            const uint64_t ad = umma_desc(abase + (uint32_t)(pe ? j : j - npe) * 4096u, 2048u, 128u);
-                            const uint32_t nhalf = (k == 9) ? 64u : 128u;
-#pragma unroll
-                            for (uint32_t h = 0; h < 2; ++h)      // the forward pack keeps the two CTA-pair halves of a slab apart
-                                umma_f16<false>(tmem_base + TM_H + h * nhalf, ad, umma_desc(sw + h * (uint32_t)(slab >> 1), (uint32_t)(slab >> 2), 128u),
-                                                k == 9 ? idf64 : idf128, acc);
-                            acc = 1;
-                            umma_commit<false>(bar(B_WEMPTY + ws));
-                            if (++ws == NST) { ws = 0; wph ^= 1; }
-                        } else {
+                        {
                             // gradient tile = hi + lo (two bf16 tiles), weights = hi + lo (two slabs): hi*hi + lo*hi + hi*lo
                             const uint32_t ws_hi = ws;
                             if (++ws == NST) { ws = 0; wph ^= 1; }

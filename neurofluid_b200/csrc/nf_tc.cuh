@@ -70,6 +70,12 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// bulk copy global -> the same shared-memory offset of every CTA in `mask`; each destination's mbarrier (same offset) gets the bytes
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+                 : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -114,13 +120,14 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
             "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
             : "memory");
 }
-// PAIR: the arrive is multicast to the barrier at the same offset in both CTAs.
+// PAIR: the arrive is multicast to the barrier at the same offset in the CTAs of `mask` (cluster ranks; default: the
+// two CTAs of a cluster of 2).
 template <bool PAIR>
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
+__device__ __forceinline__ void umma_commit(uint32_t bar, uint16_t mask = 3) {
     if constexpr (PAIR)
         asm volatile(
             "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-            "h"((uint16_t)3)
+            "h"(mask)
             : "memory");
     else
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
