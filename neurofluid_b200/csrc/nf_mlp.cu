@@ -79,7 +79,7 @@ constexpr int NUM_THREADS = 14 * 32;
 // number of weight units (ring stages) one tile consumes
 __device__ __forceinline__ int weight_units(int nl) {
     int n = 0;
-    for (int l = 0; l < nl; ++l) n += 2 * ((layer_pe_steps(l) + WU_KSTEPS - 1) / WU_KSTEPS + (l > 0 ? KH_STEPS / WU_KSTEPS : 0));
+    for (int l = 0; l < nl; ++l) n += 2 * ((layer_pe_steps(l) + wu_ksteps(0) - 1) / wu_ksteps(0) + (l > 0 ? KH_STEPS / wu_ksteps(1) : 0));
     return n;
 }
 
@@ -203,15 +203,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp(const KernelArgs a)
                             }
                         }
                         const bool last_seg = (seg == 1) || (l == 0);
-                        for (int k0 = 0; k0 < nsteps; k0 += WU_KSTEPS) {
-                            const int g = min(WU_KSTEPS, nsteps - k0);
+                        const int kb = wu_ksteps(seg);
+                        for (int k0 = 0; k0 < nsteps; k0 += kb) {
+                            const int g = min(kb, nsteps - k0);
                             if (seg == 1) {      // the 8 K-steps of this block read activation chunks k0/4 and k0/4 + 1
                                 mbar_wait(bar(B_ACT_READY + (k0 >> 2)), hidw & 1);
                                 NF_TRACE(100 + l * 8 + 1 + (k0 >> 2));
                                 mbar_wait(bar(B_ACT_READY + (k0 >> 2) + 1), hidw & 1);
                                 NF_TRACE(100 + l * 8 + 2 + (k0 >> 2));
                             }
-                            const bool last_blk = last_seg && (k0 + WU_KSTEPS >= nsteps);
+                            const bool last_blk = last_seg && (k0 + kb >= nsteps);
 #pragma unroll
                             for (uint32_t nh = 0; nh < 2; ++nh) {
                                 if (!no_weights) mbar_wait(bar(B_WFULL + ws), wph);
@@ -273,8 +274,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp(const KernelArgs a)
                     const int npe = layer_pe_steps(l);
                     for (int seg = 0; seg < 2; ++seg) {
                         const int nsteps = seg == 0 ? npe : (l > 0 ? KH_STEPS : 0);
-                        for (int k0 = 0; k0 < nsteps; k0 += WU_KSTEPS) {
-                            const uint32_t mine = (uint32_t)min(WU_KSTEPS, nsteps - k0) * 2u * rpc * 16u;   // this CTA's rows of the unit
+                        const int kb = wu_ksteps(seg);
+                        for (int k0 = 0; k0 < nsteps; k0 += kb) {
+                            const uint32_t mine = (uint32_t)min(kb, nsteps - k0) * 2u * rpc * 16u;   // this CTA's rows of the unit
                             for (int nh = 0; nh < 2; ++nh) {
                                 mbar_wait(bar(B_WEMPTY + ws), wph ^ 1);
                                 mbar_arrive_expect_tx(bar(B_WFULL + ws), mine);
@@ -510,8 +512,8 @@ __device__ __forceinline__ size_t unit_offset(int layer, int seg, int k0, int nh
         const int rpc = (l == 9) ? 32 : 64;
         for (int sg = 0; sg < 2; ++sg) {
             const int nsteps = sg == 0 ? layer_pe_steps(l) : (l > 0 ? KH_STEPS : 0);
-            for (int kb = 0; kb < nsteps; kb += WU_KSTEPS) {
-                const int g = min(WU_KSTEPS, nsteps - kb);
+            for (int kb = 0; kb < nsteps; kb += wu_ksteps(sg)) {
+                const int g = min(wu_ksteps(sg), nsteps - kb);
                 for (int h = 0; h < 2; ++h) {
                     if (l == layer && sg == seg && kb == k0 && h == nh) return off;
                     off += (size_t)2 * g * 2 * rpc * 16;
@@ -550,9 +552,9 @@ __global__ void k_pack_weights(PackArgs p, uint8_t* out) {
         const int seg = (layer_pe_steps(layer) > 0 && src_valid != 256) ? 0 : 1;      // encoded-feature segments are 198 / 54 wide
         const int kseg = k0c / 16;
         const int rpc = (layer == 9) ? 32 : 64;
-        const int kblk = (kseg / WU_KSTEPS) * WU_KSTEPS;
+        const int kblk = (kseg / wu_ksteps(seg)) * wu_ksteps(seg);
         const int nsteps = seg == 0 ? layer_pe_steps(layer) : KH_STEPS;
-        const int g = min(WU_KSTEPS, nsteps - kblk);
+        const int g = min(wu_ksteps(seg), nsteps - kblk);
         const int nh = n / (2 * rpc), r = (n / rpc) % 2, row = n % rpc;
         const size_t off = unit_offset(layer, seg, kblk, nh) + ((((size_t)r * g + (kseg - kblk)) * 2 + kc) * rpc + row) * 16;
         *reinterpret_cast<uint4*>(out + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -620,16 +622,26 @@ static int max_clusters4() {
     return cached[dev] > 0 ? cached[dev] : 0;
 }
 
-// Clusters of two CTA pairs when (nearly) every SM fits into one, else plain CTA pairs (cluster of 2)
+// The one-tile kernel below is the production path.  The two-tile kernel (nf_mlp2.cu) measures the same today (both sit
+// on the accumulator-drain / dependency-ring bound, profiles/r02_notes.md) and stays an experiment of the tuning build.
 int launch(const KernelArgs& a, int dtype, cudaStream_t st) {
+#ifdef NF_TUNING
+    const char* e = getenv("NF_MLP_IMPL");
+    if (e && atoi(e) == 2) return launch2(a, dtype, st);
+#endif
+    return launch1(a, dtype, st);
+}
+
+// Clusters of two CTA pairs when (nearly) every SM fits into one, else plain CTA pairs (cluster of 2)
+int launch1(const KernelArgs& a, int dtype, cudaStream_t st) {
     const bool bf = dtype == NF_DTYPE_BF16;
     const int c4 = bf ? max_clusters4<true>() : max_clusters4<false>();
     const int pairs_grid = num_sms() & ~1;
 #ifdef NF_TUNING
     const char* e = getenv("NF_MLP_CLUSTER");
-    const bool want4 = e ? atoi(e) == 4 : true;
+    const bool want4 = e ? atoi(e) == 4 : false;
 #else
-    const bool want4 = true;
+    const bool want4 = false;      // measured: no gain (the bound is per-SM ingest, not L2 reads), and GPCs strand a few SMs
 #endif
     if (want4 && c4 * 4 * 10 >= pairs_grid * 9) {       // at most 10 % of the SMs left without a cluster
         const int grid = 4 * (c4 < num_sms() / 4 ? c4 : num_sms() / 4);

@@ -29,10 +29,12 @@ static_assert(PACKED_BYTES == W_BYTES + SP_FLOATS * 4, "packed size");
 
 // Packed weight stream = a sequence of UNITS in consumption order:
 //   for layer l (0..9; 8 = xyz_encoding_final, 9 = dir_encoding), for segment (0: encoded-feature columns, 1: hidden columns),
-//   for K-block k0 = 0, 8, ... of the segment's K-steps (16 input columns each), for N-half nh = 0, 1 of the layer's outputs:
+//   for K-block k0 = 0, kb, 2 kb ... of the segment's K-steps (16 input columns each; kb = wu_ksteps(segment): 4 for the
+//   encoded-feature segments, 8 for the hidden ones), for N-half nh = 0, 1 of the layer's outputs:
 //   unit = [CTA r of the pair (2)][K-step j < g][8-column chunk kc (2)][row (rpc)][8 halves]
 //   with rpc = 64 (32 for the dir layer) rows per CTA: output feature nh * 2 rpc + r * rpc + row.
-constexpr int WU_KSTEPS = 8;
+constexpr int WU_KSTEPS = 8;      // the most K-steps a unit holds
+__host__ __device__ inline int wu_ksteps(int seg) { return seg == 0 ? 4 : 8; }
 __host__ __device__ inline int layer_pe_steps(int l) { return (l == 0 || l == 4) ? KX_STEPS : (l == 9 ? KD_STEPS : 0); }
 
 
@@ -50,7 +52,10 @@ struct KernelArgs {
 };
 
 
-int launch(const KernelArgs& a, int dtype, cudaStream_t st);
+int launch(const KernelArgs& a, int dtype, cudaStream_t st);        // dispatches to launch2 (nf_mlp2.cu) unless a tuning build says otherwise
+int launch1(const KernelArgs& a, int dtype, cudaStream_t st);       // one tile per CTA (nf_mlp.cu)
+int launch2(const KernelArgs& a, int dtype, cudaStream_t st);       // two tiles per CTA sharing the weight stream (nf_mlp2.cu)
+size_t pe_scratch_bytes();                                          // per-device scratch of launch2 (allocated once, kept)
 
 }  // namespace mlp
 }  // namespace nf

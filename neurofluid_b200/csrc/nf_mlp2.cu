@@ -1,0 +1,528 @@
+// nf_mlp2.cu -- the fused positional-encoding + NeRF MLP forward with TWO 128-row tiles per CTA (sm_100a, tcgen05).
+//
+// replaces: Embedding.forward x6 (models/nerf.py:21-38 via models/renderer.py:125-179) and NeRF.forward
+//           (models/nerf.py:83-124); same arithmetic, operands and packed weights as k_nerf_mlp (nf_mlp.cu).
+//
+// Why two tiles.  The one-tile kernel's timeline (profiles/r02_mlp_timeline.txt) shows ~3,400-3,800 cycles per layer
+// against 2,048 of MMA: (1) nothing overlaps a layer's accumulator drain + epilogue, because the next layer of the same
+// tile needs its result, and (2) every SM has to take in 64 KB of weights per tile-layer, and bulk copies land at
+// ~23.7 B/clk per SM (2,765 cycles per layer; halving the L2 reads with a 4-CTA multicast changed nothing: the bound is
+// the SM's ingest, not L2).  Here every weight unit that arrives in shared memory is used by BOTH tiles of the CTA (half
+// the ingest per row), and while one tile's accumulator is being drained the tensor pipe works on the other tile.
+//
+// Per CTA pair (cluster of 2, tcgen05 cta_group::2, M = 256): 4 tiles per pass, tile T of CTA r = rows of tile
+// 4 * pass + 2 r + T.  Shared memory: two in-place activation tiles (2 x 64 KB), a 5-stage x 16 KB ring, small params.
+// The ring carries, in consumption order (nf_mlp.cuh), the weight units AND -- for the layers that read encoded
+// features (0, 4: xyz-like; 9: dir-like) -- "A pieces": 4 K-steps of a tile's encoded features.  The encodings are
+// written by the 4 producer warps to a per-CTA scratch in global memory (L2) one pass ahead, as tile images, so that
+// they occupy no shared memory between the layers that use them.
+// TMEM: accumulators of tile T in columns [256 T, 256 T + 256), single-buffered: the issuer waits for "accumulator
+// half drained" before it overwrites one.
+//
+// Roles (14 warps): 0-7 epilogue (two groups of four: group g owns columns [64c + 32g, +32) of every 64-column chunk c;
+// order per layer: (half 0, tile 0) (half 0, tile 1) (half 1, tile 0) (half 1, tile 1)), 8 MMA issuer (rank 0) / weight relay (rank 1),
+// 9 loader, 10-13 encoding producers.
+#include "nf_common.cuh"
+#include "nf_mlp.cuh"
+#include "nf_tc.cuh"
+
+namespace nf {
+namespace mlp {
+namespace v2 {
+
+#ifdef NF_TUNING
+#define NF_TRACE2(cond, slot) do { if (a.trace && (cond)) a.trace[(slot)] = clock64(); } while (0)
+#else
+#define NF_TRACE2(cond, slot) do { } while (0)
+#endif
+
+constexpr int NST = 5;
+constexpr int STAGE = 16384;
+constexpr int SM_HID = 0;                               // 2 x (128 x 256 halves)
+constexpr int SM_RING = SM_HID + 2 * 65536;
+constexpr int SM_SPARAM = SM_RING + NST * STAGE;
+constexpr int SM_PART = SM_SPARAM + SP_FLOATS * 4;      // 128 x float4: head partial sums of epilogue group 1
+constexpr int SM_BAR = SM_PART + 128 * 16;
+enum Bar {
+    B_WFULL = 0,
+    B_WEMPTY = NST,
+    B_ACT_READY = 2 * NST,          // [tile 2][chunk 4]
+    B_ACC_FULL = B_ACT_READY + 8,   // [tile 2][half 2]
+    B_ACC_FREE = B_ACC_FULL + 4,    // [tile 2][half 2]
+    B_PE_READY = B_ACC_FREE + 4,    // [parity 2]
+    B_PE_FREE = B_PE_READY + 2,     // [parity 2]
+    NUM_BARS = B_PE_FREE + 2,
+};
+constexpr int SM_TMEM_SLOT = SM_BAR + NUM_BARS * 8;
+constexpr int SM_TOTAL = SM_TMEM_SLOT + 16;
+static_assert(SM_TOTAL <= 232448, "shared memory budget");
+static_assert(SM_BAR % 8 == 0, "barrier alignment");
+
+constexpr int W_ISSUE = 8, W_LOAD = 9, W_PE = 10;
+constexpr int NUM_THREADS = 14 * 32;
+constexpr int PE_TILE_BYTES = (26 + 8) * 2048;          // xyz-like image (26 chunks) + dir-like image (8 chunks)
+constexpr int PE_CTA_BYTES = 2 /*parity*/ * 2 /*tile*/ * PE_TILE_BYTES;
+constexpr int TPP = 4;                                  // tiles per pair per pass
+
+// encoded-feature row -> tile image in GLOBAL memory: byte(row r, column k) = (k / 8) * 2048 + r * 16 + (k % 8) * 2
+template <bool BF16>
+struct RowWriterG {
+    uint8_t* base;  // image + row * 16
+    float lo;
+    uint32_t pk[4];
+    template <int COL>
+    __device__ __forceinline__ void put(float v) {
+        if constexpr ((COL & 1) == 0) {
+            lo = v;
+        } else {
+            pk[(COL & 7) >> 1] = pack2<BF16>(lo, v);
+            if constexpr ((COL & 7) == 7) *reinterpret_cast<uint4*>(base + (COL >> 3) * 2048) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+    }
+};
+template <bool BF16, int BASE, int C, int L>
+__device__ __forceinline__ void emit_encoding_g(RowWriterG<BF16>& w, const float* v) {
+    static_for<0, C>([&](auto ci) { w.template put<BASE + decltype(ci)::value>(v[decltype(ci)::value]); });
+    float s[C], c[C];
+#pragma unroll
+    for (int i = 0; i < C; ++i) sincosf(v[i], &s[i], &c[i]);
+    static_for<0, L>([&](auto fi) {
+        constexpr int f = decltype(fi)::value;
+        if constexpr (f == 5) {
+#pragma unroll
+            for (int i = 0; i < C; ++i) sincosf(32.0f * v[i], &s[i], &c[i]);
+        } else if constexpr (f > 0) {
+#pragma unroll
+            for (int i = 0; i < C; ++i) {
+                const float s2 = 2.0f * s[i] * c[i];
+                const float c2 = 1.0f - 2.0f * s[i] * s[i];
+                s[i] = s2;
+                c[i] = c2;
+            }
+        }
+        static_for<0, C>([&](auto ci) {
+            constexpr int i = decltype(ci)::value;
+            w.template put<BASE + C + 2 * C * f + i>(s[i]);
+        });
+        static_for<0, C>([&](auto ci) {
+            constexpr int i = decltype(ci)::value;
+            w.template put<BASE + C + 2 * C * f + C + i>(c[i]);
+        });
+    });
+}
+
+__device__ __forceinline__ int stages_per_pass(int nl) {
+    int n = 0;
+    for (int l = 0; l < nl; ++l) {
+        const int npe = layer_pe_steps(l);
+        n += 4 * ((npe + wu_ksteps(0) - 1) / wu_ksteps(0)) + (l > 0 ? 2 * (KH_STEPS / wu_ksteps(1)) : 0);
+    }
+    return n;
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp2(const KernelArgs a, uint8_t* __restrict__ pe_scratch) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr bool PAIR = true;
+    const int warp = uniform((int)(threadIdx.x >> 5)), lane = threadIdx.x & 31;
+    const uint32_t prank = uniform(cluster_ctarank());
+    const int unit = (int)(blockIdx.x >> 1), nunits = (int)(gridDim.x >> 1);
+    const int n_rows = uniform(a.n_rows_dev ? min(*a.n_rows_dev, a.n_rows_cap) : a.n_rows_host);
+    const int ntiles = (n_rows + TILE_M - 1) / TILE_M;
+    const int npass = (ntiles + TPP - 1) / TPP;
+    if (unit >= npass) return;          // both CTAs of a pair leave together
+    const int nl = a.n_layers;
+
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t s_ring = s_base + SM_RING, s_bar = s_base + SM_BAR;
+    float* sp = reinterpret_cast<float*>(smem + SM_SPARAM);
+    float4* part = reinterpret_cast<float4*>(smem + SM_PART);
+    auto bar = [&](int i) { return s_bar + 8u * (uint32_t)i; };
+    auto bar0 = [&](int i) { return mapa_rank(bar(i), 0); };       // the same barrier in the issuer's CTA (rank 0)
+    uint8_t* my_scratch = pe_scratch + (size_t)blockIdx.x * PE_CTA_BYTES;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NST; ++i) {
+            mbar_init(bar(B_WFULL + i), prank == 0 ? 2 : 1);    // own expect_tx arrive (+ the peer's relay)
+            mbar_init(bar(B_WEMPTY + i), 1);
+        }
+        for (int i = 0; i < 8; ++i) mbar_init(bar(B_ACT_READY + i), 16);     // 8 epilogue warps x 2 CTAs
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(bar(B_ACC_FULL + i), 1);
+            mbar_init(bar(B_ACC_FREE + i), 16);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar(B_PE_READY + i), 4);                  // the 4 producer warps of this CTA
+            mbar_init(bar(B_PE_FREE + i), 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {
+        const float4* src = reinterpret_cast<const float4*>(a.packed + W_BYTES);
+        float4* dst = reinterpret_cast<float4*>(sp);
+        for (int i = threadIdx.x; i < SP_FLOATS / 4; i += NUM_THREADS) dst[i] = __ldg(src + i);
+    }
+    if (warp == W_ISSUE) tmem_alloc<PAIR>(s_base + SM_TMEM_SLOT, 512);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = uniform(*reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM_SLOT));
+
+    if (warp == W_ISSUE) {
+        if (prank == 0) {
+            // ================================================================ MMA issuer (converged warp, one elected lane issues)
+            const uint32_t idesc128 = umma_idesc(128, BF16, 2 * TILE_M), idesc64 = umma_idesc(64, BF16, 2 * TILE_M);
+            const uint32_t pe_free_remote = mapa_rank(bar(B_PE_FREE), 1);
+            uint32_t ws = 0, wph = 0, hidw = 0, lcount = 0;
+            int ti = 0;
+            auto advance = [&]() { if (++ws == NST) { ws = 0; wph ^= 1; } };
+            for (int pass = unit; pass < npass; pass += nunits, ++ti) {
+                for (int l = 0; l < nl; ++l, ++lcount) {
+                    const bool n128 = (l == 9);
+                    int tslot = 100 + l * 12;
+                    NF_TRACE2(blockIdx.x == 0 && ti == 2 && lane == 0, tslot++);
+                    const uint32_t nhalf = n128 ? 64u : 128u, rpc = nhalf >> 1;
+                    const uint32_t idesc = n128 ? idesc64 : idesc128;
+                    const uint32_t bstep = (2u * rpc * 16u) >> 4;
+                    uint32_t accf = 0;                                  // bit (T * 2 + nh): that accumulator half has been started
+                    const int npe = layer_pe_steps(l);
+                    for (int seg = 0; seg < 2; ++seg) {
+                        const int nsteps = seg == 0 ? npe : (l > 0 ? KH_STEPS : 0);
+                        const int kb = wu_ksteps(seg);
+                        const bool last_seg = (seg == 1) || (l == 0);
+                        for (int k0 = 0; k0 < nsteps; k0 += kb) {
+                            const int g = min(kb, nsteps - k0);
+                            const bool last_blk = last_seg && (k0 + kb >= nsteps);
+                            uint32_t sa[2] = {0u, 0u};
+                            if (seg == 0) {                             // the two tiles' encoded-feature pieces of this K-block
+#pragma unroll
+                                for (int T = 0; T < 2; ++T) {
+                                    mbar_wait(bar(B_WFULL + ws), wph);
+                                    sa[T] = ws;
+                                    advance();
+                                }
+                            }
+#pragma unroll
+                            for (uint32_t nh = 0; nh < 2; ++nh) {
+                                mbar_wait(bar(B_WFULL + ws), wph);
+                                const uint64_t bd = umma_desc(s_ring + ws * STAGE, rpc * 16u, 128u);
+#pragma unroll
+                                for (uint32_t T = 0; T < 2; ++T) {
+                                    if (seg == 1 && nh == 0) {          // this block's K-steps read activation chunks k0/4, k0/4 + 1
+                                        mbar_wait(bar(B_ACT_READY + T * 4 + (k0 >> 2)), hidw & 1);
+                                        mbar_wait(bar(B_ACT_READY + T * 4 + (k0 >> 2) + 1), hidw & 1);
+                                    }
+                                    const uint32_t abit = 1u << (T * 2 + nh);
+                                    if (!(accf & abit)) {      // the previous layer's epilogue has drained what these MMAs overwrite
+                                        mbar_wait(bar(B_ACC_FREE + T * 2 + nh), (lcount & 1) ^ 1);
+                                        // the dir layer's halves are 64 columns wide: both lie inside layer 0's half 0
+                                        if (l == 0 && nh == 0) mbar_wait(bar(B_ACC_FREE + T * 2 + 1), (lcount & 1) ^ 1);
+                                    }
+                                    tc_fence_after();
+                                    if (elect_one()) {
+                                        const uint64_t ad = seg == 0 ? umma_desc(s_ring + sa[T] * STAGE, 2048u, 128u)
+                                                                     : umma_desc(s_base + SM_HID + T * 65536 + (uint32_t)k0 * 4096u, 2048u, 128u);
+                                        uint32_t acc = (accf & abit) ? 1u : 0u;
+#pragma unroll
+                                        for (int j = 0; j < WU_KSTEPS; ++j) {
+                                            if (j < g) {
+                                                umma_f16<PAIR>(tmem_base + T * 256 + nh * nhalf, ad + (uint64_t)(j * (4096 >> 4)), bd + (uint64_t)(j * bstep),
+                                                               idesc, acc);
+                                                acc = 1;
+                                            }
+                                        }
+                                        if (last_blk) umma_commit<PAIR>(bar(B_ACC_FULL + T * 2 + nh));
+                                        if (seg == 0 && nh == 1) umma_commit<PAIR>(bar(B_WEMPTY + sa[T]));
+                                        if (T == 1) umma_commit<PAIR>(bar(B_WEMPTY + ws));
+                                    }
+                                    __syncwarp();
+                                    accf |= abit;
+                                }
+                                if (seg == 1) NF_TRACE2(blockIdx.x == 0 && ti == 2 && lane == 0, tslot++);
+                                advance();
+                            }
+                        }
+                    }
+                    if (l > 0) ++hidw;
+                }
+                // every stage of this pass has landed: the encoding scratch of this parity may be rewritten
+                if (lane == 0) {
+                    mbar_arrive(bar(B_PE_FREE + (ti & 1)));
+                    mbar_arrive_cluster(pe_free_remote + 8u * (ti & 1));
+                }
+                __syncwarp();
+            }
+        } else if (lane == 0) {
+            // ================================================================ relay (rank 1): "my share of stage s has landed"
+            uint32_t ws = 0, wph = 0;
+            const int nstages = stages_per_pass(nl);
+            const uint32_t remote0 = bar0(B_WFULL);
+            for (int pass = unit; pass < npass; pass += nunits) {
+                for (int s = 0; s < nstages; ++s) {
+                    mbar_wait(bar(B_WFULL + ws), wph);
+                    mbar_arrive_cluster(remote0 + 8u * ws);
+                    if (++ws == NST) { ws = 0; wph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == W_LOAD) {
+        // ================================================================ loader: weight units + encoded-feature pieces
+        if (lane == 0) {
+            uint32_t ws = 0, wph = 0;
+            int ti = 0;
+            auto fill = [&](const void* src, uint32_t bytes) {
+                mbar_wait(bar(B_WEMPTY + ws), wph ^ 1);
+                mbar_arrive_expect_tx(bar(B_WFULL + ws), bytes);
+                bulk_g2s(s_ring + ws * STAGE, src, bytes, bar(B_WFULL + ws));
+                if (++ws == NST) { ws = 0; wph ^= 1; }
+            };
+            for (int pass = unit; pass < npass; pass += nunits, ++ti) {
+                const uint8_t* src = a.packed;
+                const uint8_t* pe = my_scratch + (size_t)(ti & 1) * 2 * PE_TILE_BYTES;
+                mbar_wait(bar(B_PE_READY + (ti & 1)), (ti >> 1) & 1);
+                for (int l = 0; l < nl; ++l) {
+                    const uint32_t rpc = (l == 9) ? 32u : 64u;
+                    const int npe = layer_pe_steps(l);
+                    for (int seg = 0; seg < 2; ++seg) {
+                        const int nsteps = seg == 0 ? npe : (l > 0 ? KH_STEPS : 0);
+                        const int kb = wu_ksteps(seg);
+                        for (int k0 = 0; k0 < nsteps; k0 += kb) {
+                            const int g = min(kb, nsteps - k0);
+                            if (seg == 0)
+                                for (int T = 0; T < 2; ++T)
+                                    fill(pe + (size_t)T * PE_TILE_BYTES + (l == 9 ? 26 * 2048 : 0) + (size_t)k0 * 4096, (uint32_t)g * 4096u);
+                            const uint32_t mine = (uint32_t)g * 2u * rpc * 16u;
+                            for (int nh = 0; nh < 2; ++nh) {
+                                fill(src + prank * mine, mine);
+                                src += 2 * mine;
+                            }
+                        }
+                    }
+                }
+            }
+            for (int i = 0; i < NST; ++i) {      // every multicast "slot free" arrive has landed before this CTA may exit
+                mbar_wait(bar(B_WEMPTY + ws), wph ^ 1);
+                if (++ws == NST) { ws = 0; wph ^= 1; }
+            }
+        }
+    } else if (warp < W_ISSUE) {
+        // ================================================================ epilogue
+        const int grp = warp >> 2;
+        const int tr = (warp & 3) * 32 + lane;           // row of the tile = TMEM lane
+        const uint32_t tlane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + grp * 32;
+        const uint32_t act_ready0 = bar0(B_ACT_READY), acc_free0 = bar0(B_ACC_FREE);
+        uint32_t lcount = 0;
+        int ti = 0;
+        for (int pass = unit; pass < npass; pass += nunits, ++ti) {
+            float sigma[2] = {0.f, 0.f};
+            float rgb[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+            for (int l = 0; l < nl; ++l, ++lcount) {
+                const bool writes = (l + 1 < nl);
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                    for (int T = 0; T < 2; ++T) {
+                        const int row = ((pass * TPP) + (int)prank * 2 + T) * TILE_M + tr;
+                        mbar_wait(bar(B_ACC_FULL + T * 2 + h), lcount & 1);
+                        tc_fence_after();
+                        NF_TRACE2(blockIdx.x == 0 && ti == 2 && threadIdx.x == 0, l * 8 + (h * 2 + T) * 2);
+                        const uint32_t taddr = tlane + T * 256;
+                        if (l < 9) {
+                            const float* bias = sp + SP_BIAS + l * 256 + grp * 32;
+                            uint32_t v[2][32];
+                            tmem_ld32(taddr + (2 * h) * 64, v[0]);
+                            tmem_ld32(taddr + (2 * h + 1) * 64, v[1]);
+                            tmem_ld_wait();
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_cluster(acc_free0 + 8u * (T * 2 + h));       // this warp's part of the half is in registers
+#pragma unroll
+                            for (int cc = 0; cc < 2; ++cc) {
+                                const int c = 2 * h + cc;
+                                float f[32];
+#pragma unroll
+                                for (int i = 0; i < 32; i += 4) {
+                                    const float4 b4 = *reinterpret_cast<const float4*>(bias + c * 64 + i);
+                                    f[i] = __uint_as_float(v[cc][i]) + b4.x;
+                                    f[i + 1] = __uint_as_float(v[cc][i + 1]) + b4.y;
+                                    f[i + 2] = __uint_as_float(v[cc][i + 2]) + b4.z;
+                                    f[i + 3] = __uint_as_float(v[cc][i + 3]) + b4.w;
+                                }
+                                if (l != 8) {
+#pragma unroll
+                                    for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+                                }
+                                if (l == 7) {
+                                    const float* wsig = sp + SP_WSIG + c * 64 + grp * 32;
+                                    float sg = sigma[T];
+#pragma unroll
+                                    for (int i = 0; i < 32; i += 4) {
+                                        const float4 w4 = *reinterpret_cast<const float4*>(wsig + i);
+                                        sg = fmaf(f[i], w4.x, sg);
+                                        sg = fmaf(f[i + 1], w4.y, sg);
+                                        sg = fmaf(f[i + 2], w4.z, sg);
+                                        sg = fmaf(f[i + 3], w4.w, sg);
+                                    }
+                                    sigma[T] = sg;
+                                }
+                                if (writes) {
+                                    const uint32_t dst = s_base + SM_HID + T * 65536 + (uint32_t)(c * 8 + grp * 4) * 2048 + (uint32_t)tr * 16;
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q)
+                                        st_shared_v4(dst + q * 2048, pack2<BF16>(f[8 * q], f[8 * q + 1]), pack2<BF16>(f[8 * q + 2], f[8 * q + 3]),
+                                                     pack2<BF16>(f[8 * q + 4], f[8 * q + 5]), pack2<BF16>(f[8 * q + 6], f[8 * q + 7]));
+                                    fence_proxy_async();
+                                    __syncwarp();
+                                    if (lane == 0) mbar_arrive_cluster(act_ready0 + 8u * (T * 4 + c));
+                                }
+                            }
+                            NF_TRACE2(blockIdx.x == 0 && ti == 2 && threadIdx.x == 0, l * 8 + (h * 2 + T) * 2 + 1);
+                            if (l == 7 && !writes && h == 1) {   // sigma-only network: combine the two column halves and emit
+                                if (grp == 1) part[tr] = make_float4(0.f, 0.f, 0.f, sigma[T]);
+                                named_bar_sync(1, 256);
+                                if (grp == 0 && row < n_rows) {
+                                    const int dst = a.rowid ? a.rowid[row] : row;
+                                    if (dst >= 0) a.out4[dst] = make_float4(0.f, 0.f, 0.f, sigma[T] + part[tr].w + sp[SP_BSIG]);
+                                }
+                                named_bar_sync(2, 256);
+                            }
+                        } else {
+                            // rgb head on the 128-wide dir layer: N-half h = columns [64h, 64h + 64); group g owns [64h + 32g, +32)
+                            const float* bias = sp + SP_BIAS + 9 * 256 + grp * 32;
+                            const float* wrgb = sp + SP_WRGB + grp * 32;
+                            uint32_t v[32];
+                            tmem_ld32(taddr + h * 64, v);
+                            tmem_ld_wait();
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_cluster(acc_free0 + 8u * (T * 2 + h));
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                const float f = fmaxf(__uint_as_float(v[i]) + bias[h * 64 + i], 0.f);
+                                rgb[T][0] = fmaf(f, wrgb[h * 64 + i], rgb[T][0]);
+                                rgb[T][1] = fmaf(f, wrgb[128 + h * 64 + i], rgb[T][1]);
+                                rgb[T][2] = fmaf(f, wrgb[256 + h * 64 + i], rgb[T][2]);
+                            }
+                            if (h == 1) {
+                                if (grp == 1) part[tr] = make_float4(rgb[T][0], rgb[T][1], rgb[T][2], sigma[T]);
+                                named_bar_sync(1, 256);
+                                if (grp == 0 && row < n_rows) {
+                                    const int dst = a.rowid ? a.rowid[row] : row;
+                                    if (dst >= 0) {
+                                        const float4 pb = part[tr];
+                                        float4 o;
+                                        o.x = 1.0f / (1.0f + expf(-(rgb[T][0] + pb.x + sp[SP_BRGB])));
+                                        o.y = 1.0f / (1.0f + expf(-(rgb[T][1] + pb.y + sp[SP_BRGB + 1])));
+                                        o.z = 1.0f / (1.0f + expf(-(rgb[T][2] + pb.z + sp[SP_BRGB + 2])));
+                                        o.w = sigma[T] + pb.w + sp[SP_BSIG];
+                                        a.out4[dst] = o;
+                                    }
+                                }
+                                named_bar_sync(2, 256);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+        // ================================================================ encoding producers (warps 10-13): one pass ahead, to global scratch
+        const int tp = threadIdx.x - W_PE * 32;  // 0..127
+        int ti = 0;
+        for (int pass = unit; pass < npass; pass += nunits, ++ti) {
+            mbar_wait(bar(B_PE_FREE + (ti & 1)), ((ti >> 1) & 1) ^ 1);
+            uint8_t* base = my_scratch + (size_t)(ti & 1) * 2 * PE_TILE_BYTES + (size_t)tp * 16;
+#pragma unroll 1
+            for (int T = 0; T < 2; ++T) {
+                const int row = ((pass * TPP) + (int)prank * 2 + T) * TILE_M + tp;
+                float r[16];
+                if (row < n_rows) {
+                    const float4* src = reinterpret_cast<const float4*>(a.records + (size_t)row * 16);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 t = __ldg(src + i);
+                        r[4 * i] = t.x; r[4 * i + 1] = t.y; r[4 * i + 2] = t.z; r[4 * i + 3] = t.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) r[i] = 0.f;
+                }
+                // xyz-like block: [PE10(x) 63 | PE4(density) 9 | PE10(smoothed) 63 | PE10(variance) 63 | 0 x10]
+                RowWriterG<BF16> w;
+                w.base = base + (size_t)T * PE_TILE_BYTES;
+                emit_encoding_g<BF16, 0, 3, 10>(w, r + 0);
+                emit_encoding_g<BF16, 63, 1, 4>(w, r + 3);
+                emit_encoding_g<BF16, 72, 3, 10>(w, r + 4);
+                emit_encoding_g<BF16, 135, 3, 10>(w, r + 7);
+                static_for<198, 208>([&](auto ci) { w.template put<decltype(ci)::value>(0.f); });
+                if (nl == 10) {
+                    // dir-like block: [PE4(ray dir) 27 | PE4(smoothed dir) 27 | 0 x10]
+                    RowWriterG<BF16> wd;
+                    wd.base = base + (size_t)T * PE_TILE_BYTES + 26 * 2048;
+                    emit_encoding_g<BF16, 0, 3, 4>(wd, r + 10);
+                    emit_encoding_g<BF16, 27, 3, 4>(wd, r + 13);
+                    static_for<54, 64>([&](auto ci) { wd.template put<decltype(ci)::value>(0.f); });
+                }
+            }
+            __threadfence();                                               // the images are read back by bulk copies (async proxy)
+            asm volatile("fence.proxy.async;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(B_PE_READY + (ti & 1)));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == W_ISSUE) tmem_dealloc<PAIR>(tmem_base, 512);
+}
+
+// per-device scratch for the encoded features (one block of PE_CTA_BYTES per CTA of the grid): allocated on first use and
+// kept for the life of the process -- like the kernel image itself, it is part of the library's device state, not per-call
+// memory (40 MB, all of it L2-resident while a launch runs)
+static uint8_t* pe_scratch_for_device() {
+    static uint8_t* cached[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!cached[dev]) {
+        void* p = nullptr;
+        if (cudaMalloc(&p, (size_t)num_sms() * PE_CTA_BYTES) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        cached[dev] = (uint8_t*)p;
+    }
+    return cached[dev];
+}
+
+template <bool BF16>
+static int launch_t(const KernelArgs& a, cudaStream_t st) {
+    auto* kern = k_nerf_mlp2<BF16>;
+    uint8_t* scratch = pe_scratch_for_device();
+    NF_REQUIRE(scratch != nullptr, NF_E_CUDA, "nf_mlp: could not allocate the encoding scratch (%zu bytes)", (size_t)num_sms() * PE_CTA_BYTES);
+    NF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(num_sms() & ~1), 1, 1);
+    cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = SM_TOTAL;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    NF_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, a, scratch));
+    count_launch();
+    return NF_OK;
+}
+
+}  // namespace v2
+
+size_t pe_scratch_bytes() { return (size_t)num_sms() * v2::PE_CTA_BYTES; }
+
+int launch2(const KernelArgs& a, int dtype, cudaStream_t st) {
+    return dtype == NF_DTYPE_BF16 ? v2::launch_t<true>(a, st) : v2::launch_t<false>(a, st);
+}
+
+}  // namespace mlp
+}  // namespace nf

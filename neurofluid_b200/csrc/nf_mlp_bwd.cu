@@ -226,8 +226,8 @@ __global__ void __launch_bounds__(DG_THREADS, 1) k_mlp_bwd_dgrad(const DgradArgs
                         const uint32_t rpc = (k == 9) ? 32u : 64u;
                         for (int seg = 0; seg < 2; ++seg) {
                             const int nsteps = seg == 0 ? npe : nh;
-                            for (int k0 = 0; k0 < nsteps; k0 += WU_KSTEPS) {
-                                const uint32_t piece = (uint32_t)min(WU_KSTEPS, nsteps - k0) * 2u * rpc * 16u;
+                            for (int k0 = 0; k0 < nsteps; k0 += wu_ksteps(seg)) {
+                                const uint32_t piece = (uint32_t)min(wu_ksteps(seg), nsteps - k0) * 2u * rpc * 16u;
                                 for (int q = 0; q < 4; ++q) {          // (N-half, CTA half) = 4 pieces per K-block
                                     mbar_wait(bar(B_WEMPTY + ws), wph ^ 1);
                                     mbar_arrive_expect_tx(bar(B_WFULL + ws), piece);
@@ -269,8 +269,8 @@ __global__ void __launch_bounds__(DG_THREADS, 1) k_mlp_bwd_dgrad(const DgradArgs
                         for (int seg = 0; seg < 2; ++seg) {
                             const int nsteps = seg == 0 ? npe : nh;
                             const uint32_t abase = seg == 0 ? (k == 9 ? s_pedir : s_pexyz) : s_hidden;
-                            for (int k0 = 0; k0 < nsteps; k0 += WU_KSTEPS) {
-                                const int g = min(WU_KSTEPS, nsteps - k0);
+                            for (int k0 = 0; k0 < nsteps; k0 += wu_ksteps(seg)) {
+                                const int g = min(wu_ksteps(seg), nsteps - k0);
                                 for (uint32_t q = 0; q < 4; ++q) {      // q = N-half * 2 + CTA half: output columns q * rpc ...
                                     mbar_wait(bar(B_WFULL + ws), wph);
                                     tc_fence_after();
