@@ -264,11 +264,17 @@ typedef struct nf_transition_args {
     int32_t* overflow_out; /* optional device int32[2]: += number of particles of this call whose fluid / box neighbour
                               list exceeded the 128 slots and was truncated (the reference has no cap): callers that
                               care poll it -- results are only reference-exact while it stays 0 */
-    int32_t phase; /* -1: whole step on all particles;  0..4: run only that phase on [shard_begin, shard_end):
+    int32_t phase; /* -1: whole step on all particles;  NF_PHASE_SHARDED (-2): whole step with the particles block-sharded over
+                      the ranks of nf_comm_init -- each rank computes rows [rank * per, (rank + 1) * per), per =
+                      ceil(n_fluid / world), and the library all-gathers the three activation matrices and the packed
+                      (pos, vel, count, delta) rows in place on `stream` (4 NCCL calls, no host work in between): every
+                      rank ends up with the full outputs, bit-identical to the single-GPU step;
+                      0..4: run only that phase on [shard_begin, shard_end):
                       0 integrate + grids + neighbour lists + layer 0,  1..3 conv layers,  4 position update.
                       Between phases the caller all-gathers the layer outputs (nf_transition_layer_buffer). */
 } nf_transition_args;
 
+#define NF_PHASE_SHARDED (-2)
 NF_API int nf_transition_num_phases(void);
 NF_API int nf_transition_step(const nf_transition_args* args, void* stream);
 /* Location of layer `layer`'s activation matrix (the ReLU'd fp16/bf16 rows the next layer gathers from)
@@ -302,6 +308,22 @@ typedef struct nf_transition_bwd_args {
     size_t workspace_bytes;
 } nf_transition_bwd_args;
 NF_API int nf_transition_backward(const nf_transition_bwd_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU exchange (one process per GPU): NCCL over NVLink / NVSwitch, on the caller's stream
+ * replaces: nothing -- the reference is single-GPU; this is the "position all-gather
+ *           per step" of the particle-block sharded transition step.
+ * Rank 0 creates an id (nf_comm_unique_id), the caller ships its NF_COMM_ID_BYTES bytes to every rank by whatever channel
+ * it has (torch.distributed broadcast, a file, MPI), every rank calls nf_comm_init.  One communicator per process.
+ * nf_allgather_rows: in-place all-gather of equal blocks -- rank g's bytes_per_rank bytes sit at buf + g * bytes_per_rank
+ * on every rank; enqueued on `stream` right behind whatever produced the block (no host synchronisation).
+ * ------------------------------------------------------------------------------------------- */
+#define NF_COMM_ID_BYTES 128
+NF_API int nf_comm_unique_id(void* id_out_host);
+NF_API int nf_comm_init(const void* id_host, int rank, int world);
+NF_API int nf_comm_finalize(void);
+NF_API int nf_comm_info(int* rank_host, int* world_host);
+NF_API int nf_allgather_rows(void* buf, size_t bytes_per_rank, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * One ContinuousConv (operator-level drop-in for a maintainer who keeps models/transmodel.py and swaps only the layer)

@@ -33,6 +33,8 @@ class RenderArgs(C.Structure):
 
 
 NF_RENDER_SAVE_NEIGHBORS = 1
+NF_PHASE_SHARDED = -2
+NF_COMM_ID_BYTES = 128
 
 
 class RenderWsView(C.Structure):
@@ -115,6 +117,11 @@ SIGNATURES = {
     "nf_transition_pack_weights_bwd": (C.c_int, [C.POINTER(_vp), _vp, _vp]),
     "nf_transition_backward_workspace_bytes": (_sz, [C.c_int]),
     "nf_transition_backward": (C.c_int, [C.POINTER(TransitionBwdArgs), _vp]),
+    "nf_comm_unique_id": (C.c_int, [_vp]),
+    "nf_comm_init": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "nf_comm_finalize": (C.c_int, []),
+    "nf_comm_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "nf_allgather_rows": (C.c_int, [_vp, _sz, _vp]),
     "nf_cconv_packed_weights_bytes": (_sz, [C.c_int, C.c_int]),
     "nf_cconv_pack_weights": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "nf_cconv_workspace_bytes": (_sz, [C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -56,7 +56,7 @@ def build(force: bool = False, verbose: bool = False, tuning: bool = False) -> s
             with open(obj + ".ptxas.log", "w") as f:
                 f.write(r.stderr)
             objs.append(obj)
-    subprocess.check_call([NVCC, "-shared", "-o", out, *objs, "-lcudart"])
+    subprocess.check_call([NVCC, "-shared", "-o", out, *objs, "-lcudart", "-ldl"])
     return out
 
 

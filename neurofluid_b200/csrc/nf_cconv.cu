@@ -941,13 +941,14 @@ inline PackedLayout packed_layout() {
 
 struct WsLayout {
     size_t pos_new, vel_new, grid_f, grid_b, pairs_ff, cnt_ff, pairs_fb, cnt_fb, slab_j, slab_w, slab_off, ans0, x0, ans1, x1, ans2, x2, ans3,
-        g3, flags, total;
+        g3, flags, out10, total;
 };
+constexpr int ROW_PAD = 8;      // row arrays that are all-gathered in place hold world * ceil(n / world) <= n + 7 rows (world <= 8)
 inline WsLayout ws_layout(int n, int m) {
     WsLayout L;
     size_t o = 0;
     auto take = [&](size_t b) { size_t r = o; o += align_up(b, 256); return r; };
-    const size_t N = (size_t)(n > 0 ? n : 1);
+    const size_t N = (size_t)(n > 0 ? n : 1) + ROW_PAD;
     L.pos_new = take(N * 12); L.vel_new = take(N * 12);
     L.grid_f = take(grid_layout(n).total);
     L.grid_b = take(grid_layout(m).total);
@@ -960,8 +961,31 @@ inline WsLayout ws_layout(int n, int m) {
     L.ans3 = take(N * 16 * 4);
     L.g3 = take(N * C3_G * 4);
     L.flags = take(256);
+    L.out10 = take(N * 10 * 4);
     L.total = o;
     return L;
+}
+
+// sharded step: a rank's rows of (pos_out, vel_out, count, delta) packed 10 floats wide for ONE all-gather, then unpacked
+__global__ void k_pack10(const float* __restrict__ pos, const float* __restrict__ vel, const float* __restrict__ nn,
+                         const float* __restrict__ delta, int begin, int end, float* __restrict__ out10) {
+    const int i = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= end) return;
+    float* o = out10 + (size_t)i * 10;
+    o[0] = pos[3 * i]; o[1] = pos[3 * i + 1]; o[2] = pos[3 * i + 2];
+    o[3] = vel[3 * i]; o[4] = vel[3 * i + 1]; o[5] = vel[3 * i + 2];
+    o[6] = nn ? nn[i] : 0.f;
+    o[7] = delta ? delta[3 * i] : 0.f; o[8] = delta ? delta[3 * i + 1] : 0.f; o[9] = delta ? delta[3 * i + 2] : 0.f;
+}
+__global__ void k_unpack10(const float* __restrict__ out10, int n, float* __restrict__ pos, float* __restrict__ vel, float* __restrict__ nn,
+                           float* __restrict__ delta) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* o = out10 + (size_t)i * 10;
+    pos[3 * i] = o[0]; pos[3 * i + 1] = o[1]; pos[3 * i + 2] = o[2];
+    vel[3 * i] = o[3]; vel[3 * i + 1] = o[4]; vel[3 * i + 2] = o[5];
+    if (nn) nn[i] = o[6];
+    if (delta) { delta[3 * i] = o[7]; delta[3 * i + 1] = o[8]; delta[3 * i + 2] = o[9]; }
 }
 
 template <int CIN, int COUT_PAD>
@@ -1805,9 +1829,14 @@ extern "C" int nf_transition_step(const nf_transition_args* a, void* stream_) {
     NF_REQUIRE(a->n_box == 0 || (a->box && a->box_normals), NF_E_INVALID, "nf_transition_step: null box");
     NF_REQUIRE(a->dtype == NF_DTYPE_F16 || a->dtype == NF_DTYPE_BF16, NF_E_UNSUPPORTED, "nf_transition_step: dtype");
     NF_REQUIRE(a->filter_extent > 2e-3f && a->dt > 0.f, NF_E_INVALID, "nf_transition_step: bad extent/dt");
-    NF_REQUIRE(a->phase >= -1 && a->phase < 5, NF_E_INVALID, "nf_transition_step: phase %d", a->phase);
+    NF_REQUIRE(a->phase >= NF_PHASE_SHARDED && a->phase < 5, NF_E_INVALID, "nf_transition_step: phase %d", a->phase);
     const int N = a->n_fluid, M = a->n_box;
-    const int begin = a->phase == -1 ? 0 : a->shard_begin, end = a->phase == -1 ? N : a->shard_end;
+    const bool sharded = a->phase == NF_PHASE_SHARDED;
+    const int world = sharded ? comm::world() : 1;
+    NF_REQUIRE(world <= ROW_PAD, NF_E_UNSUPPORTED, "nf_transition_step: at most %d ranks", ROW_PAD);
+    const int per = (N + world - 1) / world;
+    const int begin = a->phase == -1 ? 0 : (sharded ? min(comm::rank() * per, N) : a->shard_begin);
+    const int end = a->phase == -1 ? N : (sharded ? min(begin + per, N) : a->shard_end);
     NF_REQUIRE(begin >= 0 && end <= N && begin <= end, NF_E_INVALID, "nf_transition_step: bad shard [%d,%d)", begin, end);
     const WsLayout L = ws_layout(N, M);
     NF_REQUIRE(a->workspace_bytes >= L.total, NF_E_WORKSPACE, "nf_transition_step: workspace %zu < %zu",
@@ -1827,10 +1856,14 @@ extern "C" int nf_transition_step(const nf_transition_args* a, void* stream_) {
     float* ans3 = (float*)(b + L.ans3);
     int* flags = (int*)(b + L.flags);
     const float radius = 0.5f * a->filter_extent;
-    const bool all = a->phase == -1;
     const int nshard = end - begin;
-
-    if (all || a->phase == 0) {
+    const int ph_lo = a->phase < 0 ? 0 : a->phase, ph_hi = a->phase < 0 ? 4 : a->phase;
+    NF_REQUIRE(!sharded || a->nnbr_out, NF_E_INVALID, "nf_transition_step: the sharded step needs nnbr_out");
+    ConvArgs c;
+    c.slab_j = slab_j; c.slab_w = slab_w; c.slab_off = slab_off; c.n = N; c.begin = begin; c.end = end; c.dense = 1;
+    c.mask_src = nullptr; c.ld_mask = 0; c.relu_out = 1;
+    for (int ph = ph_lo; ph <= ph_hi; ++ph) {
+    if (ph == 0) {
         NF_CUDA_OK(cudaMemsetAsync(flags, 0, 256, st));
         k_integrate<<<(3 * N + 255) / 256, 256, 0, st>>>(a->pos, a->vel, N, a->gravity[0], a->gravity[1], a->gravity[2],
                                                         a->dt, pos_new, vel_new);
@@ -1867,20 +1900,17 @@ extern "C" int nf_transition_step(const nf_transition_args* a, void* stream_) {
                                            (size_t)nshard * 96 * 4, cudaMemcpyDeviceToDevice, st));
         }
     }
-    ConvArgs c;
-    c.slab_j = slab_j; c.slab_w = slab_w; c.slab_off = slab_off; c.n = N; c.begin = begin; c.end = end; c.dense = 1;
-    c.mask_src = nullptr; c.ld_mask = 0; c.relu_out = 1;
-    if (all || a->phase == 1) {     // conv1 + dense1 : 96 -> 64 (no residual: widths differ, :127-130)
+    if (ph == 1) {     // conv1 + dense1 : 96 -> 64 (no residual: widths differ, :127-130)
         c.x_in = x0; c.w_packed = w + PL.l1; c.residual = nullptr; c.ld_res = 0; c.ans = ans1; c.x_out = x1; c.cout = 64;
         int rc = launch_conv<96, 64>(c, a->dtype, st);
         if (rc != NF_OK) return rc;
     }
-    if (all || a->phase == 2) {     // conv2 + dense2 + residual : 64 -> 64
+    if (ph == 2) {     // conv2 + dense2 + residual : 64 -> 64
         c.x_in = x1; c.w_packed = w + PL.l2; c.residual = ans1; c.ld_res = 64; c.ans = ans2; c.x_out = x2; c.cout = 64;
         int rc = launch_conv<64, 64>(c, a->dtype, st);
         if (rc != NF_OK) return rc;
     }
-    if (all || a->phase == 3) {     // conv3 + dense3 : 64 -> 3  (project every particle, then gather per neighbour)
+    if (ph == 3) {     // conv3 + dense3 : 64 -> 3  (project every particle, then gather per neighbour)
         float* g3 = (float*)(b + L.g3);
         const bool bf = a->dtype == NF_DTYPE_BF16;
         const size_t smem = (size_t)NCELL * 64 * 3 * sizeof(float);
@@ -1902,10 +1932,30 @@ extern "C" int nf_transition_step(const nf_transition_args* a, void* stream_) {
             NF_LAUNCH_OK();
         }
     }
-    if ((all || a->phase == 4) && nshard > 0) {
+    if (ph == 4 && nshard > 0) {
         k_update<<<(3 * nshard + 255) / 256, 256, 0, st>>>(a->pos, pos_new, ans3, 16, begin, end, a->dt, a->pos_out,
                                                           a->vel_out, a->delta_out);
         NF_LAUNCH_OK();
     }
+    if (sharded && world > 1) {
+        // the exchange step: rows produced by this rank -> every rank, in place, on the same stream
+        int rc = NF_OK;
+        if (ph == 0) rc = comm::allgather_inplace(x0, (size_t)per * 96 * 2, st);
+        else if (ph == 1) rc = comm::allgather_inplace(x1, (size_t)per * 64 * 2, st);
+        else if (ph == 2) rc = comm::allgather_inplace(x2, (size_t)per * 64 * 2, st);
+        else if (ph == 4) {
+            float* out10 = (float*)(b + L.out10);
+            if (nshard > 0) {
+                k_pack10<<<(nshard + 255) / 256, 256, 0, st>>>(a->pos_out, a->vel_out, a->nnbr_out, a->delta_out, begin, end, out10);
+                NF_LAUNCH_OK();
+            }
+            rc = comm::allgather_inplace(out10, (size_t)per * 10 * 4, st);
+            if (rc != NF_OK) return rc;
+            k_unpack10<<<(N + 255) / 256, 256, 0, st>>>(out10, N, a->pos_out, a->vel_out, a->nnbr_out, a->delta_out);
+            NF_LAUNCH_OK();
+        }
+        if (rc != NF_OK) return rc;
+    }
+    }   // phase loop
     return NF_OK;
 }

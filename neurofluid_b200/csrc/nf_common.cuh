@@ -47,6 +47,13 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 int num_sms();
 
+// nf_comm.cu: the process's NCCL communicator (world 1 until nf_comm_init)
+namespace comm {
+int world();
+int rank();
+int allgather_inplace(void* buf, size_t bytes_per_rank, cudaStream_t st);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Spatial grid: dense, clamped, cell-sorted copy of the points.  Lives in a caller workspace.
 // ------------------------------------------------------------------------------------------------

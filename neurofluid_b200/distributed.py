@@ -86,38 +86,50 @@ def allgather_rows(buf: torch.Tensor, n: int, group=None) -> None:
     buf[:n] = out[:n]
 
 
+_comm_ready = {}
+
+
+def init_comm(group=None) -> None:
+    """Create the library's NCCL communicator for the ranks of `group` (idempotent): rank 0 makes the id
+    (nf_comm_unique_id), torch.distributed ships its 128 bytes (plumbing), every rank calls nf_comm_init."""
+    import ctypes as C
+    from . import _lib
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    key = (id(group), world, rank, torch.cuda.current_device())
+    if _comm_ready.get("key") == key:
+        return
+    L = _lib.lib()
+    idbuf = (C.c_ubyte * _lib.NF_COMM_ID_BYTES)()
+    if rank == 0:
+        _lib.check(L.nf_comm_unique_id(idbuf), "nf_comm_unique_id")
+    t = torch.tensor(list(idbuf), dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
+    src = dist.get_global_rank(group, 0) if group is not None else 0
+    dist.broadcast(t, src=src, group=group)
+    idbuf = (C.c_ubyte * _lib.NF_COMM_ID_BYTES)(*t.cpu().tolist())
+    _lib.check(L.nf_comm_init(idbuf, rank, world), "nf_comm_init")
+    _comm_ready["key"] = key
+
+
 def transition_step_sharded(net, pos, vel, box, box_feats, group=None):
     """`ParticleNet.forward` with the particles block-sharded over the ranks of `group`.
 
-    Every rank holds the full state (pos, vel).  Per phase each rank computes only its own rows; the
-    ReLU'd fp16 activation rows a layer produces are all-gathered (NCCL over NVLink) before the next layer
-    gathers neighbours from them, and the corrected positions / velocities are all-gathered at the end
-    -- the "position all-gather per step" of BASELINE.json's north_star.  4 small collectives per step."""
+    Every rank holds the full state (pos, vel) and ends up with the full result.  ONE call into the library
+    (nf_transition_step, phase NF_PHASE_SHARDED): each rank computes its own rows of every phase, and the library
+    all-gathers, in place on the compute stream and with no host work in between, the fp16 activation rows after layers
+    0-2 and the packed (pos, vel, neighbour count, delta) rows at the end -- the "position all-gather per step" of
+    BASELINE.json's north_star.  4 NCCL calls per step; bit-identical to the single-GPU step."""
     import ctypes as C
     from . import _lib
     world = dist.get_world_size(group) if dist.is_initialized() else 1
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
     if world == 1:
         return net(pos, vel, box, box_feats)
+    init_comm(group)
+    net._poll_overflow()
     p, v, b, bf, outs, ws = net._prepare(pos, vel, box, box_feats, None)
-    n, m = p.shape[0], b.shape[0]
-    lo, hi = shard_bounds(n, rank, world)
-    L = _lib.lib()
-
-    def layer_rows(layer):
-        off, rb = C.c_size_t(0), C.c_size_t(0)
-        _lib.check(L.nf_transition_layer_buffer(n, m, layer, C.byref(off), C.byref(rb)), "nf_transition_layer_buffer")
-        return ws[off.value: off.value + n * rb.value].view(torch.float16).view(n, rb.value // 2)
-
-    for phase in range(5):
-        a = net._args(p, v, b, bf, outs, ws, phase=phase, shard=(lo, hi))
-        _lib.check(L.nf_transition_step(C.byref(a), _lib.stream_ptr()), "nf_transition_step")
-        if phase <= 2:
-            allgather_rows(layer_rows(phase), n, group)       # bit patterns only; dtype view is irrelevant
-    for t in outs[:2]:
-        allgather_rows(t, n, group)
-    allgather_rows(outs[2].view(n, 1), n, group)
-    allgather_rows(outs[3], n, group)
+    a = net._args(p, v, b, bf, outs, ws, phase=_lib.NF_PHASE_SHARDED)
+    _lib.check(_lib.lib().nf_transition_step(C.byref(a), _lib.stream_ptr()), "nf_transition_step")
+    net._post_overflow()
     net.num_fluid_neighbors, net.pos_correction = outs[2], outs[3]
     net._keep = (p, v, b, bf)
     return outs[0], outs[1], outs[2]

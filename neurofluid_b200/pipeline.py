@@ -199,7 +199,7 @@ def rollout_and_render(transition_model, renderer, pos, vel, box, box_normals, c
         pos_hist.append(pos)
     renderer.return_num_nn = want_nn
     if hasattr(transition_model, "check_neighbor_overflow"):
-        transition_model.check_neighbor_overflow()               # the one host sync of the rollout
+        transition_model.check_neighbor_overflow(group)          # the one host sync of the rollout (all ranks decide together)
     out = {"positions": pos_hist, "images": frames, "fluid_errors": fe}
     if gt_images is not None:
         mse = torch.stack(psnr).view(n_frames, len(cams))
