@@ -223,10 +223,13 @@ __global__ void __launch_bounds__(256) k_nbr_build(GridView g, const float* __re
                                                    Pair* __restrict__ pairs, int* __restrict__ counts,
                                                    float* __restrict__ counts_f, int* __restrict__ overflow,
                                                    int* __restrict__ slab_j, float4* __restrict__ slab_w,
-                                                   unsigned short* __restrict__ slab_off) {
+                                                   unsigned short* __restrict__ slab_off,
+                                                   const float4* __restrict__ order /*NULL or cell-sorted copy: .w = particle index*/) {
     const int lane = threadIdx.x & 31;
-    const int i = begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (i >= end) return;
+    const int pos_i = begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (pos_i >= end) return;
+    // neighbouring warps work on spatially neighbouring particles (cell order): their cell rows and records share L1 lines
+    const int i = order ? __float_as_int(__ldg(&order[pos_i].w)) : pos_i;
     const GridHeader* h = g.hdr;
     const float qx = out_pos[3 * i], qy = out_pos[3 * i + 1], qz = out_pos[3 * i + 2];
     const float r2 = __fmul_rn(radius, radius);
@@ -416,13 +419,15 @@ struct Layer0Args {
     void* x0;                    // (N,96) half/bf16
     int begin, end;
     int bf16;
+    const float4* order;         // NULL or the fluid grid's cell-sorted copy (.w = particle index): work in cell order
 };
 
 __global__ void __launch_bounds__(256) k_layer0(const Layer0Args a) {
     __shared__ __align__(16) float sm_patch[8][NCELL * 4 + NCELL * 3];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int i = a.begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (i >= a.end) return;
+    const int pos_i = a.begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (pos_i >= a.end) return;
+    const int i = a.order ? __float_as_int(__ldg(&a.order[pos_i].w)) : pos_i;
     float* pf = sm_patch[wib];
     float* po = pf + NCELL * 4;
     // scatter: one lane per neighbour (records and features are fetched in parallel), shared-memory atomics
@@ -526,6 +531,9 @@ struct ConvArgs {
     const float* mask_src;                 // backward: (N, ld_mask) fp32 pre-activations; the result is zeroed where <= 0
     int ld_mask;                           //           (ReLU backward), BEFORE the residual is added.  NULL: no mask
     int relu_out;                          // 1: x_out = relu(ans) (forward);  0: x_out = ans (backward: next gradient)
+    const float4* order;                   // NULL, or the fluid grid's cell-sorted copy (.w = particle index): tile row t of the
+                                           // launch is particle order[begin + t] -- a tile then holds 128 spatial neighbours whose
+                                           // neighbour rows overlap (~300 distinct rows per tile: the gathers hit L1, not L2)
 };
 
 template <int CIN, int COUT_PAD>
@@ -543,7 +551,8 @@ struct ConvCfg {
     static constexpr int SM_W = SM_A + 128 * KSLAB * 2;
     static constexpr int SM_BIAS = SM_W + SLAB_BYTES;
     static constexpr int SM_OFFS = SM_BIAS + COUT_PAD * 4;           // 16 warps x 8 rows x 32 u16: slab list row starts
-    static constexpr int SM_BAR = SM_OFFS + 16 * 8 * 32 * 2;
+    static constexpr int SM_ROWMAP = SM_OFFS + 16 * 8 * 32 * 2;       // 128 ints: tile row -> particle
+    static constexpr int SM_BAR = SM_ROWMAP + 128 * 4;
     static constexpr int SM_TOTAL = SM_BAR + 64;
     static_assert(SM_TOTAL <= 232448, "smem budget");
 };
@@ -604,168 +613,148 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_cconv_tc(const ConvArgs a) 
         }
     } else {
         // ============================================================ workers: slab construction
-        // warp = 8 particles (rows of the tile), lane = channels {lane, lane+32, ...}.  For filter row s and
-        // particle r the slab list gives the neighbours that touch the row, already reduced to {j, weight per
-        // x cell}: lanes fetch the entries in parallel (one coalesced load, issued two units ahead), broadcast them
-        // by shuffle and gather 8 neighbour feature rows at a time.
+        // A warp owns 8 particles (rows of the tile).  Its lanes split into NG groups of GL lanes; a group works on ONE
+        // particle at a time and each of its lanes owns CPL consecutive input channels (CIN = 64: 4 groups x 8 lanes x 8
+        // channels, one 16-byte feature load per entry; CIN = 96: 2 groups x 16 lanes x 6 channels, three 4-byte loads).
+        // For filter row s the group walks the particle's slab-list entries {j, weight per x cell}: every lane of the
+        // group reads the same entry (a broadcast load, no shuffles), gathers its channels of neighbour j and adds
+        // w[x] * f into acc[x][channel].  NG particles advance per warp instruction: ~10 (CIN 64) / ~18 (CIN 96) warp
+        // instructions per entry instead of the ~40 of the lane-per-channel-pair version it replaces.
+        constexpr int GL = (CIN == 64) ? 8 : 16;
+        constexpr int CPL = CIN / GL;                      // 8 or 6 channels per lane
+        constexpr int NG = 32 / GL;
+        static_assert(CIN == 64 || CIN == 96, "channel mapping");
         const int rbase = warp * ROWS_PER_WARP;
+        const int gq = lane / GL, cl = lane % GL;
         // row starts of this warp's 8 slab lists: smem [r][32] u16 (17 used)
         unsigned short* offs = reinterpret_cast<unsigned short*>(smem + C::SM_OFFS) + warp * ROWS_PER_WARP * 32;
+        int* rowmap = reinterpret_cast<int*>(smem + C::SM_ROWMAP);      // tile row -> particle index (or -1)
         for (int r = 0; r < ROWS_PER_WARP; ++r) {
-            const int row = row0 + rbase + r;
-            offs[r * 32 + lane] = (row < a.end && lane < 17) ? __ldg(a.slab_off + (size_t)row * SLABOFF + lane) : (unsigned short)0;
+            const int tpos = row0 + rbase + r;
+            int row = -1;
+            if (tpos < a.end) row = a.order ? __float_as_int(__ldg(&a.order[tpos].w)) : tpos;
+            if (lane == 0) rowmap[rbase + r] = row;
+            offs[r * 32 + lane] = (row >= 0 && lane < 17) ? __ldg(a.slab_off + (size_t)row * SLABOFF + lane) : (unsigned short)0;
         }
         __syncwarp();
-        // unit u = s * 8 + r: filter row s of particle r.  Entry prefetch runs two units ahead of the gathers.
-        auto fetch_entries = [&](int unit, int& ne, int& ej, float4& ew) {
-            ne = 0; ej = 0;
-            ew = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (unit >= 16 * ROWS_PER_WARP) return;
-            const int r = unit & (ROWS_PER_WARP - 1), sr = unit >> 3;
-            const int beg = offs[r * 32 + sr];
-            ne = (int)offs[r * 32 + sr + 1] - beg;
-            if (lane < ne) {
-                const size_t base = (size_t)(row0 + rbase + r) * SLABCAP + beg + lane;
-                ej = __ldg(a.slab_j + base);
-                ew = __ldg(a.slab_w + base);
-            }
-        };
-        int ne_a, ej_a, ne_b, ej_b;
-        float4 ew_a, ew_b;
-        fetch_entries(0, ne_a, ej_a, ew_a);
-        fetch_entries(1, ne_b, ej_b, ew_b);
-        // channel ownership: lane l holds channels 2l, 2l+1 (one 32-bit load / store) and, for CIN = 96, 64 + l
-        constexpr bool THIRD = (CIN == 96);
-        static_assert(CIN == 64 || CIN == 96, "channel mapping");
-        const uint32_t* xin32 = reinterpret_cast<const uint32_t*>(a.x_in);
-        const unsigned short* xin16 = reinterpret_cast<const unsigned short*>(a.x_in);
+        const uint8_t* xin = reinterpret_cast<const uint8_t*>(a.x_in);
         auto cvt2 = [](uint32_t v, float& lo, float& hi) {
             if (BF16) { lo = __uint_as_float(v << 16); hi = __uint_as_float(v & 0xffff0000u); }
             else { const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&v)); lo = t.x; hi = t.y; }
         };
-        auto cvt1 = [](unsigned short v) {
-            if (BF16) return __uint_as_float((uint32_t)v << 16);
-            return __half2float(*reinterpret_cast<const __half*>(&v));
+        auto pack = [](float lo, float hi) -> uint32_t {
+            if (BF16) { __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi); return *reinterpret_cast<uint32_t*>(&h); }
+            __half2 h = __floats2half2_rn(lo, hi);
+            return *reinterpret_cast<uint32_t*>(&h);
         };
-        constexpr int GB = 8;                    // neighbour rows gathered per round trip (4 .. 16 measured alike)
-        // Lanes >= ne hold j = 0, w = 0, so every batch of GB gathers runs unconditionally: gathers beyond the list
-        // read row 0 (an L1 hit) and add nothing.  The batch loop is deliberately rolled: with the 16-deep, software-
-        // pipelined variant the hot loop outgrew the instruction cache (13 % no-instruction stalls) and was slower.
-        auto load_feats = [&](auto nb, int ej, int u0, uint32_t* fp, unsigned short* fs) {
+        // CPL halves of neighbour j's feature row, as CPL/2 packed words
+        auto load_feat = [&](int j, uint32_t (&f)[CPL / 2]) {
+            const uint8_t* p = xin + (size_t)j * (CIN * 2) + cl * (CPL * 2);
+            if constexpr (CPL == 8) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+                f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+            } else {
 #pragma unroll
-            for (int u = 0; u < decltype(nb)::value; ++u) {
-                const int j = __shfl_sync(NF_FULL, ej, (u0 + u) & 31);
-                fp[u] = __ldg(xin32 + (((size_t)j * CIN) >> 1) + lane);
-                if (THIRD) fs[u] = __ldg(xin16 + (size_t)j * CIN + 64 + lane);
+                for (int i = 0; i < CPL / 2; ++i) f[i] = __ldg(reinterpret_cast<const uint32_t*>(p) + i);
             }
         };
-        auto fma_feats = [&](auto nb, const float4& ew, int u0, const uint32_t* fp, const unsigned short* fs, float (&acc)[4][3]) {
+        auto fma_feat = [&](const float4& w, const uint32_t (&f)[CPL / 2], float (&acc)[4][CPL]) {
 #pragma unroll
-            for (int u = 0; u < decltype(nb)::value; ++u) {
-                const int src = (u0 + u) & 31;
-                const float wx = __shfl_sync(NF_FULL, ew.x, src), wy = __shfl_sync(NF_FULL, ew.y, src);
-                const float wz = __shfl_sync(NF_FULL, ew.z, src), ww = __shfl_sync(NF_FULL, ew.w, src);
+            for (int i = 0; i < CPL / 2; ++i) {
                 float f0, f1;
-                cvt2(fp[u], f0, f1);
-                acc[0][0] += wx * f0; acc[1][0] += wy * f0; acc[2][0] += wz * f0; acc[3][0] += ww * f0;
-                acc[0][1] += wx * f1; acc[1][1] += wy * f1; acc[2][1] += wz * f1; acc[3][1] += ww * f1;
-                if (THIRD) {
-                    const float f2 = cvt1(fs[u]);
-                    acc[0][2] += wx * f2; acc[1][2] += wy * f2; acc[2][2] += wz * f2; acc[3][2] += ww * f2;
-                }
+                cvt2(f[i], f0, f1);
+                acc[0][2 * i] += w.x * f0; acc[1][2 * i] += w.y * f0; acc[2][2 * i] += w.z * f0; acc[3][2 * i] += w.w * f0;
+                acc[0][2 * i + 1] += w.x * f1; acc[1][2 * i + 1] += w.y * f1; acc[2][2 * i + 1] += w.z * f1; acc[3][2 * i + 1] += w.w * f1;
             }
         };
-        // prologue: unit 0's entries become "current"
-        int ne_c = ne_a, ej_c = ej_a;
-        float4 ew_c = ew_a;
-        ne_a = ne_b; ej_a = ej_b; ew_a = ew_b;
-        fetch_entries(2, ne_b, ej_b, ew_b);
 #pragma unroll 1
-        for (int unit = 0; unit < 17 * ROWS_PER_WARP; ++unit) {
-            {
-                const int s = unit >> 3, r = unit & (ROWS_PER_WARP - 1);
-                const int rl = rbase + r;
-                const int row = row0 + rl;
-                float acc[4][3];
+        for (int s = 0; s <= 16; ++s) {
+#pragma unroll 1
+            for (int R = 0; R < ROWS_PER_WARP / NG; ++R) {
+                const int r = R * NG + gq;
+                const int rl = rbase + r, row = rowmap[rl];
+                float acc[4][CPL];
 #pragma unroll
-                for (int x = 0; x < 4; ++x) acc[x][0] = acc[x][1] = acc[x][2] = 0.f;
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int i = 0; i < CPL; ++i) acc[x][i] = 0.f;
                 if (s < 16) {
-                    // this unit's entries were fetched two units ago; gather and accumulate 8 neighbour rows per round
-                    // (rolled: the hot loop stays small enough for the instruction cache)
-                    {
-                        int ej = ej_c;
-                        float4 ew = ew_c;
-#pragma unroll 1
-                        for (int e0 = 0; e0 < ne_c; e0 += 32) {
-                            if (e0 > 0) {
-                                const size_t base = (size_t)row * SLABCAP + offs[r * 32 + s] + e0 + lane;
-                                ej = 0; ew = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (e0 + lane < ne_c) {
-                                    ej = __ldg(a.slab_j + base);
-                                    ew = __ldg(a.slab_w + base);
-                                }
-                            }
-                            const int cnt = min(32, ne_c - e0);
-#pragma unroll 1
-                            for (int u0 = 0; u0 < cnt; u0 += GB) {
-                                uint32_t fp[GB];
-                                unsigned short fs[GB];
-                                load_feats(std::integral_constant<int, GB>{}, ej, u0, fp, fs);
-                                fma_feats(std::integral_constant<int, GB>{}, ew, u0, fp, fs, acc);
-                            }
+                    const int beg = offs[r * 32 + s];
+                    const int n = (int)offs[r * 32 + s + 1] - beg;
+                    const int nmax = __reduce_max_sync(NF_FULL, n);
+                    const size_t ebase = (size_t)max(row, 0) * SLABCAP + beg;       // no particle: n = 0, never dereferenced
+                    // EB entries per iteration, the next iteration's {j, w} already in flight while this one's feature rows
+                    // are gathered (the lists stream from L2 / HBM: one exposed round trip per iteration, not two).
+                    // Entries past the group's own list read {j = 0, w = 0}: row 0 is an L1 hit.
+                    constexpr int EB = 4;
+                    int jn[EB];
+                    float4 wn[EB];
+                    auto fetch = [&](int e) {
+#pragma unroll
+                        for (int u = 0; u < EB; ++u) {
+                            jn[u] = 0; wn[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (e + u < n) { jn[u] = __ldg(a.slab_j + ebase + e + u); wn[u] = __ldg(a.slab_w + ebase + e + u); }
                         }
+                    };
+                    fetch(0);
+#pragma unroll 1
+                    for (int e = 0; e < nmax; e += EB) {
+                        int jc[EB];
+                        float4 wc[EB];
+                        uint32_t f[EB][CPL / 2];
+#pragma unroll
+                        for (int u = 0; u < EB; ++u) { jc[u] = jn[u]; wc[u] = wn[u]; }
+#pragma unroll
+                        for (int u = 0; u < EB; ++u) load_feat(jc[u], f[u]);
+                        fetch(e + EB);
+#pragma unroll
+                        for (int u = 0; u < EB; ++u) fma_feat(wc[u], f[u], acc);
                     }
-                    // rotate: next -> current, prefetch entries three units ahead
-                    ne_c = ne_a; ej_c = ej_a; ew_c = ew_a;
-                    ne_a = ne_b; ej_a = ej_b; ew_a = ew_b;
-                    fetch_entries(unit + 3, ne_b, ej_b, ew_b);
-                } else if (row < a.end && a.dense) {
+                } else if (row >= 0 && a.dense) {
                     // dense branch: the particle's own (ReLU'd) features, K = CIN
-                    cvt2(__ldg(xin32 + (((size_t)row * CIN) >> 1) + lane), acc[0][0], acc[0][1]);
-                    if (THIRD) acc[0][2] = cvt1(__ldg(xin16 + (size_t)row * CIN + 64 + lane));
+                    uint32_t f[CPL / 2];
+                    load_feat(row, f);
+#pragma unroll
+                    for (int i = 0; i < CPL / 2; ++i) cvt2(f[i], acc[0][2 * i], acc[0][2 * i + 1]);
                 }
-                if (r == 0 && s > 0) mbar_wait(bar_mma_done, (s - 1) & 1);   // previous slab consumed
+                if (R == 0 && s > 0) mbar_wait(bar_mma_done, (s - 1) & 1);   // previous slab consumed
                 const int nx = (s < 16) ? 4 : 1;
 #pragma unroll
                 for (int x = 0; x < 4; ++x) {
                     if (x < nx) {
-                        auto pack = [](float lo, float hi) -> uint32_t {
-                            if (BF16) { __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi); return *reinterpret_cast<uint32_t*>(&h); }
-                            __half2 h = __floats2half2_rn(lo, hi);
-                            return *reinterpret_cast<uint32_t*>(&h);
-                        };
-                        {
-                            const int k = x * CIN + 2 * lane;
-                            const uint32_t addr = s_a + (uint32_t)(k >> 3) * 2048 + (uint32_t)rl * 16 + (uint32_t)(k & 7) * 2;
-                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(pack(acc[x][0], acc[x][1])) : "memory");
-                        }
-                        if (THIRD) {
-                            const int k = x * CIN + 64 + lane;
-                            const uint32_t addr = s_a + (uint32_t)(k >> 3) * 2048 + (uint32_t)rl * 16 + (uint32_t)(k & 7) * 2;
-                            const uint32_t bits = pack(acc[x][2], 0.f);
-                            asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)(bits & 0xffffu)) : "memory");
+                        const int k = x * CIN + cl * CPL;                     // first of this lane's CPL slab columns
+                        if constexpr (CPL == 8) {
+                            const uint32_t addr = s_a + (uint32_t)(k >> 3) * 2048 + (uint32_t)rl * 16;
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack(acc[x][0], acc[x][1])),
+                                         "r"(pack(acc[x][2], acc[x][3])), "r"(pack(acc[x][4], acc[x][5])), "r"(pack(acc[x][6], acc[x][7]))
+                                         : "memory");
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < CPL / 2; ++i) {
+                                const int kk = k + 2 * i;
+                                const uint32_t addr = s_a + (uint32_t)(kk >> 3) * 2048 + (uint32_t)rl * 16 + (uint32_t)(kk & 7) * 2;
+                                asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(pack(acc[x][2 * i], acc[x][2 * i + 1])) : "memory");
+                            }
                         }
                     }
                 }
-                if (r == ROWS_PER_WARP - 1) {
-                    fence_proxy_async();
-                    mbar_arrive(bar_a_ready);
-                }
             }
+            fence_proxy_async();
+            mbar_arrive(bar_a_ready);
         }
         // ============================================================ epilogue (warps 0-3, thread = row)
         if (warp < 4) {
             mbar_wait(bar_mma_done, 0);     // 17 commits: the last one completes phase index 16 -> parity 0
             tc_fence_after();
             const int rl = warp * 32 + lane;
-            const int row = row0 + rl;
+            const int row = rowmap[rl];
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
 #pragma unroll
             for (int c0 = 0; c0 < COUT_PAD; c0 += 16) {
                 uint32_t v[16];
                 tmem_ld16(taddr + c0, v);
                 tmem_ld_wait();
-                if (row < a.end) {
+                if (row >= 0) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const int c = c0 + i;
@@ -842,10 +831,11 @@ __global__ void __launch_bounds__(256) k_conv3_gather(const Pair* __restrict__ p
                                                       const float* __restrict__ g, const void* __restrict__ x_in,
                                                       const float* __restrict__ b_conv, const float* __restrict__ w_dense,
                                                       const float* __restrict__ b_dense, int begin, int end,
-                                                      float* __restrict__ ans3 /*(N,16)*/) {
+                                                      float* __restrict__ ans3 /*(N,16)*/, const float4* __restrict__ order) {
     const int lane = threadIdx.x & 31;
-    const int i = begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (i >= end) return;
+    const int pos_i = begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (pos_i >= end) return;
+    const int i = order ? __float_as_int(__ldg(&order[pos_i].w)) : pos_i;
     float acc[C3_OUT] = {0.f, 0.f, 0.f};
     const int n = cnt[i];
     const Pair* pr = pairs + (size_t)i * MAXNBR;
@@ -1657,7 +1647,7 @@ extern "C" int nf_cconv_forward(const nf_cconv_args* a, void* stream_) {
     k_nbr_build<<<blocks, 256, 0, st>>>(grid_view(a->grid_in, a->n_in), a->out_pos, 0, a->n_out, radius, a->ignore_same != 0,
                                        a->use_window != 0, pairs, cnt, a->count_out, flags,
                                        tc ? (int*)(b + L.slab_j) : nullptr, tc ? (float4*)(b + L.slab_w) : nullptr,
-                                       tc ? (unsigned short*)(b + L.slab_off) : nullptr);
+                                       tc ? (unsigned short*)(b + L.slab_off) : nullptr, nullptr);
     NF_LAUNCH_OK();
     if (a->overflow_out) {
         k_add_overflow<<<1, 32, 0, st>>>(flags, a->overflow_out);
@@ -1679,7 +1669,7 @@ extern "C" int nf_cconv_forward(const nf_cconv_args* a, void* stream_) {
         c.slab_off = (const unsigned short*)(b + L.slab_off);
         c.x_in = b + L.x16; c.w_packed = (const uint8_t*)a->weights; c.residual = nullptr; c.ld_res = 0;
         c.ans = a->out; c.x_out = nullptr; c.n = a->n_in; c.begin = 0; c.end = a->n_out; c.cout = 64; c.dense = 0;
-        c.mask_src = nullptr; c.ld_mask = 0; c.relu_out = 1;
+        c.mask_src = nullptr; c.ld_mask = 0; c.relu_out = 1; c.order = nullptr;
         return a->cin == 96 ? launch_conv<96, 64>(c, a->dtype, st) : launch_conv<64, 64>(c, a->dtype, st);
     }
     const size_t kb = (size_t)NCELL * a->cin * a->cout * 4;
@@ -1785,6 +1775,7 @@ extern "C" int nf_transition_backward(const nf_transition_bwd_args* b, void* str
     if ((rc = launch_dense_wgrad(g_ans2, 64, 64, x1, 64, xkind, 0, N, dP /*unused: cin = 0*/, dP + PO.off[11], dP + PO.off[13], st)) != NF_OK) return rc;
     ConvArgs c;
     c.slab_j = wg.slab_j; c.slab_w = wg.slab_w; c.slab_off = wg.slab_off; c.n = N; c.begin = 0; c.end = N; c.dense = 1; c.relu_out = 0;
+    c.order = grid_view(ws + L.grid_f, N).sorted;     // the forward's fluid grid is still in its workspace
     c.x_in = g_ans2_h; c.w_packed = wb + BL.l2; c.residual = g_ans2; c.ld_res = 64; c.ans = g_ans1; c.x_out = g_ans1_h; c.cout = 64;
     c.mask_src = ans1; c.ld_mask = 64;
     if ((rc = launch_conv<64, 64>(c, NF_DTYPE_BF16, st)) != NF_OK) return rc;
@@ -1860,8 +1851,12 @@ extern "C" int nf_transition_step(const nf_transition_args* a, void* stream_) {
     const int ph_lo = a->phase < 0 ? 0 : a->phase, ph_hi = a->phase < 0 ? 4 : a->phase;
     NF_REQUIRE(!sharded || a->nnbr_out, NF_E_INVALID, "nf_transition_step: the sharded step needs nnbr_out");
     ConvArgs c;
+    // Whole-step, single-GPU: every per-particle kernel walks the particles in the fluid grid's CELL ORDER (the grid is
+    // built in phase 0), so that a warp's / a tile's particles are spatial neighbours and their gathers share cache lines.
+    // Sharded / per-phase calls keep array order: a rank's rows must be a contiguous block for the in-place all-gather.
+    const float4* order = a->phase == -1 ? grid_view(b + L.grid_f, N).sorted : nullptr;
     c.slab_j = slab_j; c.slab_w = slab_w; c.slab_off = slab_off; c.n = N; c.begin = begin; c.end = end; c.dense = 1;
-    c.mask_src = nullptr; c.ld_mask = 0; c.relu_out = 1;
+    c.mask_src = nullptr; c.ld_mask = 0; c.relu_out = 1; c.order = order;
     for (int ph = ph_lo; ph <= ph_hi; ++ph) {
     if (ph == 0) {
         NF_CUDA_OK(cudaMemsetAsync(flags, 0, 256, st));
@@ -1877,10 +1872,10 @@ extern "C" int nf_transition_step(const nf_transition_args* a, void* stream_) {
         if (nshard > 0) {
             const int blocks = (nshard + 7) / 8;
             k_nbr_build<<<blocks, 256, 0, st>>>(grid_view(b + L.grid_f, N), pos_new, begin, end, radius, 1, 1, pairs_ff,
-                                               cnt_ff, a->nnbr_out, flags, slab_j, slab_w, slab_off);
+                                               cnt_ff, a->nnbr_out, flags, slab_j, slab_w, slab_off, order);
             NF_LAUNCH_OK();
             k_nbr_build<<<blocks, 256, 0, st>>>(grid_view(a->box_grid_ws ? a->box_grid_ws : b + L.grid_b, M), pos_new, begin, end, radius, 1, 1, pairs_fb,
-                                               cnt_fb, nullptr, flags + 1, nullptr, nullptr, nullptr);
+                                               cnt_fb, nullptr, flags + 1, nullptr, nullptr, nullptr, order);
             NF_LAUNCH_OK();
             if (a->overflow_out) {
                 k_add_overflow<<<1, 32, 0, st>>>(flags, a->overflow_out);
@@ -1893,6 +1888,7 @@ extern "C" int nf_transition_step(const nf_transition_args* a, void* stream_) {
             l0.k_obst = (const float*)(w + PL.k_obst); l0.b_obst = (const float*)(w + PL.b_obst);
             l0.w_dense = (const float*)(w + PL.w_dense0); l0.b_dense = (const float*)(w + PL.b_dense0);
             l0.ans0 = ans0; l0.x0 = x0; l0.begin = begin; l0.end = end; l0.bf16 = a->dtype == NF_DTYPE_BF16;
+            l0.order = order;
             k_layer0<<<blocks, 256, 0, st>>>(l0);
             NF_LAUNCH_OK();
             if (a->feats0_out)
@@ -1926,9 +1922,9 @@ extern "C" int nf_transition_step(const nf_transition_args* a, void* stream_) {
         if (nshard > 0) {
             const int blocks = (nshard + 7) / 8;
             if (bf) k_conv3_gather<true><<<blocks, 256, 0, st>>>(pairs_ff, cnt_ff, g3, x2, (const float*)(w + PL.b3), (const float*)(w + PL.w_dense3),
-                                                                (const float*)(w + PL.b_dense3), begin, end, ans3);
+                                                                (const float*)(w + PL.b_dense3), begin, end, ans3, order);
             else k_conv3_gather<false><<<blocks, 256, 0, st>>>(pairs_ff, cnt_ff, g3, x2, (const float*)(w + PL.b3), (const float*)(w + PL.w_dense3),
-                                                               (const float*)(w + PL.b_dense3), begin, end, ans3);
+                                                               (const float*)(w + PL.b_dense3), begin, end, ans3, order);
             NF_LAUNCH_OK();
         }
     }

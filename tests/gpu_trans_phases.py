@@ -22,3 +22,12 @@ for rep in range(2):
         e0.record(); _lib.check(_lib.lib().nf_transition_step(C.byref(a), _lib.stream_ptr()), "step"); e1.record()
         torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
     print("phase ms:", [round(t, 3) for t in ts], "sum", round(sum(ts), 3))
+# whole step (phase -1: cell-ordered kernels), CUDA events over 50 steps
+for rep in range(2):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pp, vv = pos, vel
+    e0.record()
+    for _ in range(50):
+        pp, vv, _ = net(pp, vv, box, box_n)
+    e1.record(); torch.cuda.synchronize()
+    print("whole step ms:", round(e0.elapsed_time(e1) / 50, 4))
