@@ -156,6 +156,12 @@ typedef struct nf_render_args {
     int32_t* stats;
     int32_t flags; /* NF_RENDER_SAVE_NEIGHBORS: keep every record row's neighbour list in the workspace (parity tests,
                       backward pass); size the workspace with nf_render_workspace_bytes_ex(..., K, flags) */
+    /* training-time jitter (utils/ray_utils.py:245-253, 186-190; models/renderer.py:192-196): random numbers are the caller's */
+    int32_t z_stride;    /* 0: z_coarse is one table of n_coarse depths shared by all rays;  else z_coarse holds one row of
+                            z_stride floats per ray (perturb > 0: stratified depths, ascending within a ray) */
+    int32_t u_stride;    /* likewise for u_importance (perturb > 0: u ~ U[0,1) per ray and sample) */
+    const float* noise0; /* optional (n_rays, n_coarse): added to sigma before the ReLU in the coarse compositing */
+    const float* noise1; /* optional (n_rays, n_coarse + n_importance): the same for the fine pass */
 } nf_render_args;
 
 #define NF_RENDER_SAVE_NEIGHBORS 1

@@ -51,6 +51,9 @@ struct StageArgs {
     int solo_max_occ, peel_lanes, peel_from;   // stream: tuning, see search_stream
     const float* z_coarse;
     const float* u_imp;
+    int z_stride, u_stride;                    // 0: one table shared by all rays;  else per-ray rows (perturb > 0)
+    const float* noise0;                       // optional (R, S0): added to sigma before the ReLU (noise_std > 0)
+    const float* noise1;                       // optional (R, S1)
     int S0, n_imp, S1;
     // outputs
     float *rgb0, *depth0, *opac0, *mask0;
@@ -658,18 +661,25 @@ __host__ __device__ inline size_t q0_smem_per_warp(int fl, int K, int P) {
 template <int NS0, int FL>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, FL == 1 ? 3 : 2) k_stage_q0(const StageArgs p) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
-    __shared__ float sm_z[NS0 * 32];
+    __shared__ float sm_zw[WARPS_PER_BLOCK][NS0 * 32];     // this warp's ray's coarse depths (a shared table, or its perturbed row)
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int s = threadIdx.x; s < p.S0; s += blockDim.x) sm_z[s] = __ldg(p.z_coarse + s);
-    __syncthreads();
+    float* sm_z = sm_zw[wib];
+    for (int s = lane; s < p.S0; s += 32) sm_z[s] = __ldg(p.z_coarse + s);
+    __syncwarp();
     int* sel = reinterpret_cast<int*>(dyn_smem + wib * q0_smem_per_warp(FL, p.K, p.n_points));
     unsigned* scratch = reinterpret_cast<unsigned*>(sel + 32 * sel_stride(p.K));
     QueryStats qs;
     for (int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ray < p.n_rays; ray += nwarps) {
         float o[3], d[3];
         load_ray(p.rays, ray, o, d);
-        const bool miss = p.use_mask && ray_misses_points(p, o, d, sm_z[0], sm_z[p.S0 - 1]);
+        if (p.z_stride) {
+            __syncwarp();
+            for (int s = lane; s < p.S0; s += 32) sm_z[s] = __ldg(p.z_coarse + (size_t)ray * p.z_stride + s);
+            __syncwarp();
+        }
+        // with sigma noise an empty ray still composites relu(noise): no shortcut for rays that miss the particles
+        const bool miss = p.use_mask && !p.noise0 && !p.noise1 && ray_misses_points(p, o, d, sm_z[0], sm_z[p.S0 - 1]);
         if (lane == 0) p.miss[ray] = miss ? 1 : 0;
         if (miss) {
             for (int s = lane; s < p.S0; s += 32) {
@@ -740,11 +750,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, FL == 1 ? 3 : 2) k_stage
 #pragma unroll
         for (int slot = 0; slot < NS0; ++slot) {
             const int s = slot * 32 + lane;
-            z0[slot] = __ldg(p.z_coarse + min(s, S0 - 1));
+            z0[slot] = __ldg(p.z_coarse + (size_t)ray * p.z_stride + min(s, S0 - 1));
             const unsigned bits = p.act0[(size_t)ray * NS0 + slot];
             nfull += __popc(bits);
             const bool ev = s < S0 && (p.use_mask ? ((bits >> lane) & 1u) : true);
             c0[slot] = ev ? p.out0[(size_t)ray * S0 + s] : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.noise0 && s < S0) c0[slot].w += p.noise0[(size_t)ray * S0 + s];      // models/renderer.py:192-196
         }
         float rgb[3], depth, acc;
         ray_composite<NS0>(z0, c0, S0, dnorm, lane, p.white_bg != 0, w0, rgb, depth, acc);
@@ -794,7 +805,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, FL == 1 ? 3 : 2) k_stage
             const int j = j0 + lane;
             float sv = -3.0e38f;
             if (j < NI) {
-                const float u = __ldg(p.u_imp + j);
+                const float u = __ldg(p.u_imp + (size_t)ray * p.u_stride + j);
                 int lo = 0, hi = nb;            // count of cdf[k] <= u   (searchsorted right=True)
                 while (lo < hi) {
                     const int mid = (lo + hi) >> 1;
@@ -807,6 +818,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, FL == 1 ? 3 : 2) k_stage
                 const float t = (u - c_lo) / den;
                 sv = bins[below] + t * (bins[above] - bins[below]);
             }
+            if (p.u_stride) {          // random inverse-CDF arguments: the draws come in no order; sorted below
+                if (j < NI) smp[j] = sv;
+                continue;
+            }
             float M = sv;
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
@@ -818,6 +833,25 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, FL == 1 ? 3 : 2) k_stage
             runmax = __shfl_sync(NF_FULL, M, 31);
         }
         __syncwarp();
+        if (p.u_stride) {
+            // torch.sort(cat[z, z_samples]) (utils/ray_utils.py:225): bitonic sort of the draws in shared memory, then the
+            // same rank merge as the deterministic path
+            int n2 = 1;
+            while (n2 < NI) n2 <<= 1;
+            for (int i = NI + lane; i < n2; i += 32) smp[i] = 3.0e38f;
+            __syncwarp();
+            for (int k = 2; k <= n2; k <<= 1)
+                for (int jj = k >> 1; jj > 0; jj >>= 1) {
+                    for (int i = lane; i < n2; i += 32) {
+                        const int ixj = i ^ jj;
+                        if (ixj > i) {
+                            const float va = smp[i], vb = smp[ixj];
+                            if ((va > vb) == ((i & k) == 0)) { smp[i] = vb; smp[ixj] = va; }
+                        }
+                    }
+                    __syncwarp();
+                }
+        }
         // rank merge of the two sorted lists (ties: coarse depths first)
 #pragma unroll
         for (int slot = 0; slot < NS0; ++slot) {
@@ -887,11 +921,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_stage_fin(const StageA
 #pragma unroll
         for (int slot = 0; slot < NS; ++slot) {
             const int s = slot * 32 + lane;
-            z[slot] = FIRST ? __ldg(p.z_coarse + min(s, S - 1)) : p.z1[(size_t)ray * S + min(s, S - 1)];
+            z[slot] = FIRST ? __ldg(p.z_coarse + (size_t)ray * p.z_stride + min(s, S - 1)) : p.z1[(size_t)ray * S + min(s, S - 1)];
             const unsigned bits = act[(size_t)ray * NS + slot];
             nfull += __popc(bits);
             const bool ev = s < S && (p.use_mask ? ((bits >> lane) & 1u) : true);
             c[slot] = ev ? out[(size_t)ray * S + s] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float* noise = FIRST ? p.noise0 : p.noise1;
+            if (noise && s < S) c[slot].w += noise[(size_t)ray * S + s];
         }
         float rgb[3], depth, acc;
         ray_composite<NS>(z, c, S, dnorm, lane, p.white_bg != 0, w, rgb, depth, acc);
@@ -1123,6 +1159,10 @@ extern "C" int nf_render_forward(const nf_render_args* a, void* stream_) {
         p.search_mode = (a->search == NF_SEARCH_STREAM || a->n_particles > SCS_MAX_POINTS) ? 0 : 1;
     }
     p.z_coarse = a->z_coarse; p.u_imp = a->u_importance;
+    p.z_stride = a->z_stride; p.u_stride = a->u_stride;
+    NF_REQUIRE((a->z_stride == 0 || a->z_stride >= a->n_coarse) && (a->u_stride == 0 || a->u_stride >= NI), NF_E_INVALID,
+               "nf_render_forward: z_stride / u_stride must be 0 or at least a row");
+    p.noise0 = a->noise0; p.noise1 = fine ? a->noise1 : nullptr;
     p.S0 = a->n_coarse; p.n_imp = NI; p.S1 = a->n_coarse + NI;
     const bool want0 = a->mode != NF_RENDER_FINE;
     p.rgb0 = want0 ? a->rgb0 : nullptr; p.depth0 = want0 ? a->depth0 : nullptr;

@@ -31,7 +31,9 @@ constexpr int DFEAT_W = 272;
 struct CompArgs {
     const float* rays; int n_rays;
     const float* z_shared;      // (S) depths shared by all rays (coarse pass) or NULL
-    const float* z_per_ray;     // (n_rays, S) (fine pass) or NULL
+    const float* z_per_ray;     // (n_rays, z_stride) (fine pass; perturbed coarse pass) or NULL
+    int z_stride;
+    const float* noise;         // optional (n_rays, S): sigma noise of the forward
     int S;
     const unsigned* act; int act_stride;
     const unsigned char* miss;
@@ -66,7 +68,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_composite_bwd(const CompArgs p) 
         for (int slot = 0; slot < NS; ++slot) {
             const int s = slot * 32 + lane;
             const bool in = s < S;
-            z[slot] = p.z_shared ? __ldg(p.z_shared + min(s, S - 1)) : p.z_per_ray[(size_t)ray * S + min(s, S - 1)];
+            z[slot] = p.z_shared ? __ldg(p.z_shared + min(s, S - 1)) : p.z_per_ray[(size_t)ray * p.z_stride + min(s, S - 1)];
         }
 #pragma unroll
         for (int slot = 0; slot < NS; ++slot) {
@@ -75,6 +77,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_composite_bwd(const CompArgs p) 
             const unsigned bits = p.act[(size_t)ray * p.act_stride + slot];
             ev[slot] = in && (p.use_mask ? ((bits >> lane) & 1u) : true);
             c[slot] = ev[slot] ? p.out4[(size_t)ray * S + s] : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.noise && in) c[slot].w += p.noise[(size_t)ray * S + s];
             float zn = __shfl_down_sync(NF_FULL, z[slot], 1);
             float z_next0 = 0.f;
             if (slot + 1 < NS) z_next0 = __shfl_sync(NF_FULL, z[slot + 1], 0);
@@ -305,8 +308,10 @@ extern "C" int nf_render_backward(const nf_render_bwd_args* b, void* stream_) {
         NF_REQUIRE(wfw && wbw && dpar, NF_E_INVALID, "nf_render_backward: null weights / parameter-gradient buffer");
         CompArgs c;
         c.rays = a->rays; c.n_rays = a->n_rays;
-        c.z_shared = coarse ? a->z_coarse : nullptr;
-        c.z_per_ray = coarse ? nullptr : (const float*)(ws + v.z1);
+        c.z_shared = (coarse && a->z_stride == 0) ? a->z_coarse : nullptr;
+        c.z_per_ray = coarse ? (a->z_stride ? a->z_coarse : nullptr) : (const float*)(ws + v.z1);
+        c.z_stride = coarse ? a->z_stride : S1;
+        c.noise = coarse ? a->noise0 : a->noise1;
         c.S = coarse ? S0 : S1;
         c.act = (const unsigned*)(ws + (coarse ? v.act0 : v.act1));
         c.act_stride = coarse ? v.act_stride0 : v.act_stride1;

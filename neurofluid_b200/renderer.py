@@ -140,14 +140,36 @@ class RenderNet(nn.Module):
             self._packed[name + "/bwd"] = (key, out)
         return self._packed[name + "/bwd"][1]
 
+    def _draw_jitter(self, R, S0, NI, perturb, noise_std, fine, z_tab, dev, given=None):
+        """The reference's random numbers, drawn with torch's generator in the reference's order (coarse_sample_ray's
+        rand, render_image's randn, sample_pdf's rand, render_image's randn: utils/ray_utils.py:245-253,186-190,
+        models/renderer.py:192-194) -- under the same seed and default device the draws are the reference's own.
+        Returns (z (R,S0) or None, u (R,NI) or None, noise0, noise1).  `given` (tests): pre-drawn tensors by name."""
+        given = given or {}
+        z = u = n0 = n1 = None
+        if perturb > 0:
+            zv = z_tab.expand(R, S0)
+            mid = 0.5 * (zv[:, :-1] + zv[:, 1:])
+            upper, lower = torch.cat([mid, zv[:, -1:]], -1), torch.cat([zv[:, :1], mid], -1)
+            r = given.get("z_rand")
+            r = torch.rand((R, S0), device=dev) if r is None else r.to(dev)
+            z = (lower + (upper - lower) * (perturb * r)).contiguous()
+        if noise_std > 0:
+            r = given.get("noise0")
+            n0 = ((torch.randn((R, S0), device=dev) if r is None else r.to(dev)) * noise_std).contiguous()
+        if fine and perturb != 0:                   # det = (perturb == 0)
+            r = given.get("u")
+            u = (torch.rand((R, NI), device=dev) if r is None else r.to(dev)).contiguous()
+        if fine and noise_std > 0:
+            r = given.get("noise1")
+            n1 = ((torch.randn((R, S0 + NI), device=dev) if r is None else r.to(dev)) * noise_std).contiguous()
+        return z, u, n0, n1
+
     def _run(self, mode, physical_particles, ro, rays, use_disp, perturb, noise_std, white_background, _train=False):
         if not _train and torch.is_grad_enabled() and (
                 (isinstance(physical_particles, torch.Tensor) and physical_particles.requires_grad)
                 or any(p.requires_grad for p in self.parameters())):
             return _render_with_grad(self, mode, physical_particles, ro, rays, use_disp, perturb, noise_std, white_background)
-        if perturb != 0 or noise_std != 0:
-            raise NFError("perturb / noise_std are training-time jitter the reference's trainers never enable "
-                          "(trainer/basetrainer.py:284-289); only the deterministic path is implemented")
         require_cuda(physical_particles, rays)
         dev = rays.device
         particles = physical_particles.detach().to(torch.float32).contiguous()
@@ -165,6 +187,9 @@ class RenderNet(nn.Module):
             mode, fine, NI = _lib.NF_RENDER_COARSE, False, 0
         S1 = S0 + NI
         z_tab, u_tab = self._sample_tables(dev, use_disp)
+        jz, ju, jn0, jn1 = (None, None, None, None)
+        if perturb != 0 or noise_std != 0:
+            jz, ju, jn0, jn1 = self._draw_jitter(R, S0, NI, perturb, noise_std, fine, z_tab, dev, getattr(self, "_given_jitter", None))
         grid = self._grid(particles)
         wc = self._packed_weights("nerf_coarse")
         wf = self._packed_weights("nerf_fine") if fine else None
@@ -207,6 +232,12 @@ class RenderNet(nn.Module):
             a.ro_dev = ptr(ro_dev)
             a.flags = flags
             a.z_coarse, a.u_importance, a.n_coarse, a.n_importance = ptr(z_tab), ptr(u_tab), S0, NI
+            off = lambda t, per_ray: None if t is None else C.c_void_p(t.data_ptr() + r0 * per_ray * 4)
+            if jz is not None:
+                a.z_coarse, a.z_stride = off(jz, S0), S0
+            if ju is not None:
+                a.u_importance, a.u_stride = off(ju, NI), NI
+            a.noise0, a.noise1 = off(jn0, S0), off(jn1, S1)
             a.radius, a.K, a.search = float(self.raduis), int(self.num_neighbor), self.search
             a.mode, a.use_mask, a.white_background = int(mode), int(bool(self.cfg.use_mask)), int(bool(white_background))
             a.dtype = self.operand_dtype
@@ -227,7 +258,7 @@ class RenderNet(nn.Module):
         self._debug = (ws, R, NI) if flags and R > 0 else None
         if _train:
             saved = dict(args=a if R > 0 else None, ws=ws, R=R, NI=NI, S0=S0, n_particles=particles.shape[0],
-                         keep=(grid, particles, rays, ro_dev, z_tab, u_tab, wc, wf, stats))
+                         keep=(grid, particles, rays, ro_dev, z_tab, u_tab, wc, wf, stats, jz, ju, jn0, jn1))
             return out, saved
         return out
 
@@ -258,9 +289,9 @@ class _RenderFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, net, call, particles, *params):
-        mode, ro, rays, use_disp, white_background = call
+        mode, ro, rays, use_disp, perturb, noise_std, white_background = call
         with torch.no_grad():
-            out, saved = net._run(mode, particles, ro, rays, use_disp, 0, 0., white_background, _train=True)
+            out, saved = net._run(mode, particles, ro, rays, use_disp, perturb, noise_std, white_background, _train=True)
         keys = list(out.keys())
         ctx.net, ctx.saved, ctx.keys = net, saved, keys
         ctx.mark_non_differentiable(*[out[k] for k in keys if k.startswith(("num_nn", "mask"))])
@@ -303,11 +334,8 @@ class _RenderFunction(torch.autograd.Function):
 
 
 def _render_with_grad(net, mode, physical_particles, ro, rays, use_disp, perturb, noise_std, white_background):
-    if perturb != 0 or noise_std != 0:
-        raise NFError("perturb / noise_std are training-time jitter the reference's trainers never enable "
-                      "(trainer/basetrainer.py:284-289); only the deterministic path is implemented")
     params = list(net.nerf_coarse.ordered_params()) + list(net.nerf_fine.ordered_params())
-    outs = _RenderFunction.apply(net, (mode, ro, rays, use_disp, white_background), physical_particles, *params)
+    outs = _RenderFunction.apply(net, (mode, ro, rays, use_disp, perturb, noise_std, white_background), physical_particles, *params)
     return dict(zip(net._train_keys, outs))
 
 

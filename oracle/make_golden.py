@@ -85,6 +85,35 @@ def render_case(RenderNet, ray_utils, name, n_lat, H, crop, seed, sigma_boost, u
           f"rgb1 mean={float(full['rgb1'].mean()):.4f} min={float(full['rgb1'].min()):.4f}")
 
 
+def render_jitter_case(RenderNet, ray_utils, name, n_lat, H, crop, seed, sigma_boost, perturb, noise_std, rays_stride=1):
+    """Training-time jitter (perturb > 0: stratified depths + random inverse-CDF arguments; noise_std > 0: sigma noise) through
+    the reference's own forward under torch.manual_seed(seed); the same seed then replays the four draws in the reference's
+    call order, and they are stored with the outputs so that the oracle / CUDA path can be fed the identical numbers."""
+    from neurofluid_b200 import scenes
+    import math
+    cfg = scenes.render_cfg()
+    net = RenderNet(cfg, scenes.NEAR, scenes.FAR)
+    sd = scenes.init_render_state(seed, sigma_boost)
+    net.load_state_dict(sd, strict=True)
+    particles = torch.from_numpy(scenes.lattice_particles(n_lat, seed))
+    rays_full, focal, cw = scenes.camera_rays(H, H)
+    rays = scenes.center_crop_rays(rays_full, H, H, crop)[::rays_stride].contiguous()
+    R, S, SI = rays.shape[0], cfg.ray.N_samples, cfg.ray.N_importance
+    torch.manual_seed(1000 + seed)
+    with torch.no_grad():
+        full = net(particles, net.set_ro(cw), rays, focal, cw, perturb=perturb, noise_std=noise_std)
+    torch.manual_seed(1000 + seed)
+    draws = {"z_rand": torch.rand((R, S)), "noise0": torch.randn((R, S)), "u": torch.rand([R, SI]), "noise1": torch.randn((R, S + SI))}
+    out = {"n_lat": n_lat, "H": H, "crop": crop, "seed": seed, "sigma_boost": sigma_boost, "use_mask": True, "rays_stride": rays_stride,
+           "weight_gain": 1.0, "center": np.zeros(3, np.float32), "rays": rays.numpy(), "perturb": perturb, "noise_std": noise_std}
+    for k, v in draws.items():
+        out["draw." + k] = v.numpy()
+    for k, v in full.items():
+        out[f"forward.{k}"] = v.numpy().astype(np.int8) if k.startswith("num_nn") else v.numpy()
+    np.savez_compressed(os.path.join(GOLD, f"render_{name}.npz"), **out)
+    print(f"render_{name}: R={R} perturb={perturb} noise_std={noise_std} rgb1 mean={float(full['rgb1'].mean()):.4f}")
+
+
 def transition_case(ParticleNet, name, n_lat, seed, box_spacing, steps):
     from neurofluid_b200 import scenes
     net = ParticleNet(gravity=(0.0, 0.0, -9.81))
@@ -125,6 +154,7 @@ def main():
     render_case(RenderNet, ray_utils, "cfg0_sub", 18, 400, 64, 3, 5.0, rays_stride=16)
     # He-scaled weights: O(1) activations, sigma of both signs, structured rgb -> stresses MLP numerics
     render_case(RenderNet, ray_utils, "small_he", 9, 400, 16, 4, 1.0, weight_gain=2.45)
+    render_jitter_case(RenderNet, ray_utils, "small_jitter", 9, 400, 16, 5, 5.0, perturb=1.0, noise_std=0.5, rays_stride=4)
     transition_case(ParticleNet, "small", 8, 0, 0.1, 3)
     transition_case(ParticleNet, "medium", 14, 1, 0.05, 2)
 

@@ -58,8 +58,12 @@ def coarse_z_table(near: float, far: float, n_samples: int) -> torch.Tensor:
     return near * (1 - t) + far * t
 
 
-def coarse_samples(near, far, rays, n_samples):
+def coarse_samples(near, far, rays, n_samples, perturb=0.0, z_rand=None):
     z = coarse_z_table(near, far, n_samples).expand(rays.shape[0], n_samples)
+    if perturb > 0:                                     # utils/ray_utils.py:245-253; z_rand = the torch.rand draw
+        mid = 0.5 * (z[:, :-1] + z[:, 1:])
+        upper, lower = torch.cat([mid, z[:, -1:]], -1), torch.cat([z[:, :1], mid], -1)
+        z = lower + (upper - lower) * (perturb * z_rand)
     xyz = rays[:, None, 0:3] + rays[:, None, 3:6] * z[:, :, None]
     return z, xyz
 
@@ -107,8 +111,10 @@ def local_geometry_features(d2, nn, xyz, rays, ro, radius, enc, sigma_only=False
 
 
 # models/renderer.py:182-208
-def composite(rgbsigma, z, rays, white_background=True):
+def composite(rgbsigma, z, rays, white_background=True, noise=None):
     rgb, sigma = rgbsigma[..., :3], rgbsigma[..., 3]
+    if noise is not None:                               # models/renderer.py:192-196 (noise = randn * noise_std)
+        sigma = sigma + noise
     delta = torch.cat([z[:, 1:] - z[:, :-1], 1e10 * torch.ones_like(z[:, :1])], -1)
     delta = delta * torch.norm(rays[:, 3:6].unsqueeze(1), dim=-1)
     alpha = 1 - torch.exp(-delta * torch.relu(sigma))
@@ -123,12 +129,14 @@ def composite(rgbsigma, z, rays, white_background=True):
 
 
 # utils/ray_utils.py:178-229 (det=True)
-def importance_samples(z, weights, n_importance, rays):
+def importance_samples(z, weights, n_importance, rays, u=None):
     bins = 0.5 * (z[:, 1:] + z[:, :-1])
     w = weights[:, 1:-1] + 1e-5
     pdf = w / w.sum(-1, keepdim=True)
     cdf = torch.cat([torch.zeros_like(pdf[:, :1]), torch.cumsum(pdf, -1)], -1)
-    u = torch.linspace(0.0, 1.0, n_importance).expand(cdf.shape[0], n_importance).contiguous()
+    if u is None:                                       # det = True; else the torch.rand draw of sample_pdf
+        u = torch.linspace(0.0, 1.0, n_importance).expand(cdf.shape[0], n_importance)
+    u = u.contiguous()
     inds = torch.searchsorted(cdf, u, right=True)
     below = (inds - 1).clamp(min=0)
     above = inds.clamp(max=cdf.shape[-1] - 1)
@@ -183,47 +191,55 @@ def _pass(sd, net, cfg, radius, K, particles, ro, rays, xyz, z, sigma_only=False
 
 
 @torch.no_grad()
-def render_forward(sd, cfg, near, far, particles, ro, rays, mode="forward", white_background=True, debug=False):
+def render_forward(sd, cfg, near, far, particles, ro, rays, mode="forward", white_background=True, debug=False, perturb=0.0,
+                   noise_std=0.0, jitter=None):
     """mode: 'forward' (models/renderer.py:211-270), 'coarse' (:273-307), 'fine' (:310-369)."""
-    return _render_forward(sd, cfg, near, far, particles, ro, rays, mode, white_background, debug)
+    return _render_forward(sd, cfg, near, far, particles, ro, rays, mode, white_background, debug, None, None, perturb, noise_std,
+                           jitter)
 
 
 def render_forward_grad(sd, cfg, near, far, particles, ro, rays, mode="forward", white_background=True, z1_override=None,
-                        quant=None):
+                        quant=None, perturb=0.0, noise_std=0.0, jitter=None):
     """The same forward with autograd recording: gradients flow to `sd`'s tensors and to `particles` (through the
     gathered neighbour positions, as through pytorch3d's masked_gather); the importance samples are detached
     (utils/ray_utils.py:224).  `z1_override` (R, S0+S_imp): use these merged depths instead of resampling (parity tests
     feed the CUDA path's own depths, which depend on its fp16-operand coarse sigmas)."""
     with torch.enable_grad():
-        return _render_forward(sd, cfg, near, far, particles, ro, rays, mode, white_background, False, z1_override, quant)
+        return _render_forward(sd, cfg, near, far, particles, ro, rays, mode, white_background, False, z1_override, quant, perturb,
+                               noise_std, jitter)
 
 
 def _render_forward(sd, cfg, near, far, particles, ro, rays, mode="forward", white_background=True, debug=False, z1_override=None,
-                    quant=None):
+                    quant=None, perturb=0.0, noise_std=0.0, jitter=None):
+    """`jitter` (perturb / noise_std): the random draws of the reference, by name: z_rand (R,S) ~ U, noise0 (R,S) ~ N,
+    u (R,S_imp) ~ U, noise1 (R,S+S_imp) ~ N."""
+    jitter = jitter or {}
+    n0 = jitter["noise0"] * noise_std if noise_std > 0 else None
+    n1 = jitter["noise1"] * noise_std if noise_std > 0 else None
     particles, ro, rays = particles.float().cpu(), ro.float().cpu(), rays.float().cpu()
     radius = cfg.NN_search.search_raduis_scale * cfg.NN_search.particle_radius
     K = cfg.NN_search.N_neighbor
     S, S_imp = cfg.ray.N_samples, cfg.ray.N_importance
     res = {}
-    z0, xyz0 = coarse_samples(near, far, rays, S)
+    z0, xyz0 = coarse_samples(near, far, rays, S, perturb, jitter.get("z_rand"))
     if mode == "fine":
         sig, num0, mask0, idx0 = _pass(sd, "nerf_coarse", cfg, radius, K, particles, ro, rays, xyz0, z0, True, quant)
         fake = torch.cat([torch.zeros(sig.shape[0], S, 3), sig], -1)
-        _, _, w0 = composite(fake, z0, rays, white_background)
+        _, _, w0 = composite(fake, z0, rays, white_background, n0)
     else:
         out0, num0, mask0, idx0 = _pass(sd, "nerf_coarse", cfg, radius, K, particles, ro, rays, xyz0, z0, False, quant)
-        rgb0, depth0, w0 = composite(out0, z0, rays, white_background)
+        rgb0, depth0, w0 = composite(out0, z0, rays, white_background, n0)
         res.update(rgb0=rgb0, depth0=depth0, opacity0=w0.sum(1), num_nn_0=num0, mask_0=mask0.sum(1))
     if debug:
         res.update(dbg_idx0=idx0, dbg_w0=w0)
     if mode != "coarse" and S_imp > 0:
-        xyz1, z1 = importance_samples(z0, w0.detach(), S_imp, rays)
+        xyz1, z1 = importance_samples(z0, w0.detach(), S_imp, rays, jitter.get("u") if perturb != 0 else None)
         if z1_override is not None:
             z1 = z1_override.float().cpu()
             xyz1 = rays[:, None, 0:3] + rays[:, None, 3:6] * z1[:, :, None]
         xyz1, z1 = xyz1.detach(), z1.detach()                                  # utils/ray_utils.py:224
         out1, num1, mask1, idx1 = _pass(sd, "nerf_fine", cfg, radius, K, particles, ro, rays, xyz1, z1, False, quant)
-        rgb1, depth1, w1 = composite(out1, z1, rays, white_background)
+        rgb1, depth1, w1 = composite(out1, z1, rays, white_background, n1)
         res.update(rgb1=rgb1, depth1=depth1, opacity1=w1.sum(1), num_nn_1=num1, mask_1=mask1.sum(1))
         if debug:
             res.update(dbg_z1=z1, dbg_idx1=idx1)

@@ -148,6 +148,42 @@ def test_render_backward_vs_oracle_autograd(dev, name, mode, margin):
             assert rel_l2(p.grad.cpu(), gref) < TOL, (k, rel_l2(p.grad.cpu(), gref))
 
 
+def test_render_backward_with_jitter_vs_oracle_autograd(dev):
+    """perturb / noise_std are live in training: gradients with the reference's stored random draws."""
+    c = load_render_case("small_jitter")
+    c["sd"] = with_margin(c["sd"])
+    g = c["g"]
+    jit = {k: torch.from_numpy(g["draw." + k]) for k in ("z_rand", "noise0", "u", "noise1")}
+    rng = np.random.RandomState(2)
+    target = torch.from_numpy(rng.uniform(0, 1, (c["rays"].shape[0], 3)).astype(np.float32))
+    net = nb.RenderNet(c["cfg"], scenes.NEAR, scenes.FAR)
+    net.load_state_dict(c["sd"])
+    net = net.to(dev)
+    net._given_jitter = jit
+    part = c["particles"].to(dev).requires_grad_(True)
+    with torch.enable_grad():
+        out = net(part, c["ro"].to(dev), c["rays"].to(dev), 1.0, c["cw"].to(dev), perturb=1.0, noise_std=0.5)
+        loss = ((out["rgb0"] - target.to(dev)) ** 2).mean() + ((out["rgb1"] - target.to(dev)) ** 2).mean()
+        loss.backward()
+    z1 = net.debug_view()["z1"].cpu()
+    with torch.enable_grad():
+        sdg = {k: v.clone().requires_grad_(True) if v.is_floating_point() else v for k, v in c["sd"].items()}
+        pg = c["particles"].clone().requires_grad_(True)
+        ref = orender.render_forward_grad(sdg, c["cfg"], scenes.NEAR, scenes.FAR, pg, c["ro"], c["rays"], z1_override=z1,
+                                          quant=orender.operand_rounding(torch.float16), perturb=1.0, noise_std=0.5, jitter=jit)
+        lref = ((ref["rgb0"] - target) ** 2).mean() + ((ref["rgb1"] - target) ** 2).mean()
+        lref.backward()
+    assert abs(float(loss) - float(lref)) < 1e-4 * abs(float(lref))
+    assert rel_l2(part.grad.cpu(), pg.grad) < GRAD_TOL, rel_l2(part.grad.cpu(), pg.grad)
+    scale = max(float(sdg[k].grad.norm()) for k, _ in net.named_parameters())
+    for k, p in net.named_parameters():
+        gref = sdg[k].grad
+        if float(gref.norm()) < 1e-5 * scale:
+            assert float(p.grad.norm()) < 1e-4 * scale, k
+        else:
+            assert rel_l2(p.grad.cpu(), gref) < GRAD_TOL, (k, rel_l2(p.grad.cpu(), gref))
+
+
 def test_render_training_step_changes_the_loss(dev):
     """Several forwards before one backward (one per view, trainer/trainer_e2e.py:219-244), Adam on the renderer."""
     c = load_render_case("small_boost")

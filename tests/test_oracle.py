@@ -29,6 +29,24 @@ def test_render_oracle_matches_reference_golden(name):
     assert "rgb1" not in co
 
 
+def test_render_oracle_jitter_matches_reference_golden():
+    """perturb > 0 / noise_std > 0 (utils/ray_utils.py:245-253, 186-190; models/renderer.py:192-196): the golden is the
+    reference's own forward under a fixed seed; its four random draws, replayed in the reference's call order, are stored
+    with it -- the oracle fed those numbers must reproduce the reference's outputs."""
+    c = load_render_case("small_jitter")
+    g = c["g"]
+    jit = {k: torch.from_numpy(g["draw." + k]) for k in ("z_rand", "noise0", "u", "noise1")}
+    out = orender.render_forward(c["sd"], c["cfg"], scenes.NEAR, scenes.FAR, c["particles"], c["ro"], c["rays"],
+                                 perturb=float(g["perturb"]), noise_std=float(g["noise_std"]), jitter=jit)
+    for k in ("num_nn_0", "num_nn_1"):
+        assert np.array_equal(out[k].numpy().astype(np.int8), g[f"forward.{k}"]), k
+    for k in ("rgb0", "rgb1", "depth0", "depth1", "opacity0", "opacity1"):
+        assert rel_l2(out[k], g[f"forward.{k}"]) < 1e-6, k
+    # and the jitter matters: the deterministic forward is something else
+    det = orender.render_forward(c["sd"], c["cfg"], scenes.NEAR, scenes.FAR, c["particles"], c["ro"], c["rays"])
+    assert rel_l2(det["rgb1"], g["forward.rgb1"]) > 1e-2
+
+
 def test_render_oracle_fine_mode_self_consistent():
     # reference fine_rendering is broken on shipped configs (see make_golden.py); the restated intent
     # must equal the full forward when the coarse pass only contributes sigma (it always does).
