@@ -85,6 +85,16 @@ NF_API int nf_ballquery_firstk(const void* grid_ws, int n_points /* as passed to
 NF_API size_t nf_render_packed_weights_bytes(void);
 NF_API int nf_render_pack_weights(const float* const* params_host /*[24] device pointers*/, int dtype, void* packed_out,
                            void* stream);
+/* Encoding ablations (cfg.encoding.{density, smoothed_pos, var, smoothed_dir}, models/renderer.py:152-175): a network built
+ * without a feature block has narrower first / skip / direction layers (in_xyz = 63 + 9 d + 63 s + 63 v, in_dir = 27 + 27 sd).
+ * The kernels always produce all six encodings; the packer places the narrower weight matrices into the full column layout
+ * and leaves the columns of a disabled block zero, which is the same function.  enc_flags = OR of NF_ENC_*. */
+#define NF_ENC_DENSITY 1
+#define NF_ENC_SMOOTHED_POS 2
+#define NF_ENC_VAR 4
+#define NF_ENC_SMOOTHED_DIR 8
+#define NF_ENC_ALL 15
+NF_API int nf_render_pack_weights_ex(const float* const* params_host, int dtype, int enc_flags, void* packed_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused positional-encoding + NeRF MLP over compact geometry records (parity / debug entry point)
@@ -193,6 +203,7 @@ NF_API size_t nf_render_param_count(void);
 NF_API size_t nf_render_packed_weights_bwd_bytes(void);
 /* transposed bf16 weight slabs for the data-gradient GEMMs; params as for nf_render_pack_weights */
 NF_API int nf_render_pack_weights_bwd(const float* const* params_host /*[24] device pointers*/, void* packed_out, void* stream);
+NF_API int nf_render_pack_weights_bwd_ex(const float* const* params_host, int enc_flags, void* packed_out, void* stream);
 /* Backward of nf_nerf_mlp_forward (parity / debug entry point, and the MLP stage of nf_render_backward):
  * dout4 (n,4): gradient w.r.t. (pre-sigmoid r, g, b, sigma), read at index rowid[row] (rowid NULL: row);
  * dfeat (n_rows,272) out: gradient w.r.t. the encoded features [xyz-like 198 | 10 pad | dir-like 54 | 10 pad];

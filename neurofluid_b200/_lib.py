@@ -95,6 +95,7 @@ SIGNATURES = {
     "nf_ballquery_firstk": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _f32, C.c_int, _vp, _vp, _vp]),
     "nf_render_packed_weights_bytes": (_sz, []),
     "nf_render_pack_weights": (C.c_int, [C.POINTER(_vp), C.c_int, _vp, _vp]),
+    "nf_render_pack_weights_ex": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, _vp, _vp]),
     "nf_nerf_mlp_forward": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, _vp, _vp]),
     "nf_render_workspace_bytes": (_sz, [C.c_int, C.c_int, C.c_int]),
     "nf_render_workspace_bytes_ex": (_sz, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
@@ -103,6 +104,7 @@ SIGNATURES = {
     "nf_render_param_count": (_sz, []),
     "nf_render_packed_weights_bwd_bytes": (_sz, []),
     "nf_render_pack_weights_bwd": (C.c_int, [C.POINTER(_vp), _vp, _vp]),
+    "nf_render_pack_weights_bwd_ex": (C.c_int, [C.POINTER(_vp), C.c_int, _vp, _vp]),
     "nf_nerf_mlp_backward_workspace_bytes": (_sz, [C.c_int]),
     "nf_nerf_mlp_backward": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _sz, _vp]),
     "nf_render_backward_workspace_bytes": (_sz, [C.c_int] * 5),

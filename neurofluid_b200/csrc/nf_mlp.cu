@@ -525,7 +525,7 @@ __device__ __forceinline__ size_t unit_offset(int layer, int seg, int k0, int nh
 }
 
 template <bool BF16>
-__global__ void k_pack_weights(PackArgs p, uint8_t* out) {
+__global__ void k_pack_weights(PackArgs p, uint8_t* out, int enc) {
     // one thread per (K-step, kc, n): writes 8 halves (16 B)
     const int total = N256_STEPS * 2 * 256 + N128_STEPS * 2 * 128;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -540,12 +540,22 @@ __global__ void k_pack_weights(PackArgs p, uint8_t* out) {
         int layer, k0c, src_off, src_valid, ld;
         step_source(s, layer, k0c, src_off, src_valid, ld);
         const float* W = p.w[layer];
+        // source column of fixed-layout column k of this segment (encoding ablations narrow the network's own inputs)
+        const int in_xyz = enc_in_xyz(enc), in_dir = enc_in_dir(enc);
+        const bool seg_xyz = (src_valid == 198), seg_dir = (src_valid == 54);
+        const int ld_e = layer == 0 ? in_xyz : (layer == 4 ? in_xyz + 256 : (layer == 9 ? 256 + in_dir : ld));
+        const int off_e = (layer == 4 && !seg_xyz) ? in_xyz : src_off;       // skip layer: [input_xyz | h]; dir layer: [final | input_dir]
+        auto src_col = [&](int k) -> int {
+            if (seg_xyz) return enc_col_xyz(k, enc);
+            if (seg_dir) { const int c = enc_col_dir(k, enc); return c < 0 ? -1 : 256 + c; }
+            return k < src_valid ? off_e + k : -1;
+        };
         uint32_t pk[4];
 #pragma unroll
         for (int e = 0; e < 8; e += 2) {
-            const int ka = k0c + kc * 8 + e, kb = ka + 1;
-            const float va = ka < src_valid ? W[(size_t)n * ld + src_off + ka] : 0.f;
-            const float vb = kb < src_valid ? W[(size_t)n * ld + src_off + kb] : 0.f;
+            const int ca = src_col(k0c + kc * 8 + e), cb = src_col(k0c + kc * 8 + e + 1);
+            const float va = ca >= 0 ? W[(size_t)n * ld_e + ca] : 0.f;
+            const float vb = cb >= 0 ? W[(size_t)n * ld_e + cb] : 0.f;
             pk[e >> 1] = pack2<BF16>(va, vb);
         }
         // destination: the unit of (layer, segment, K-block, N-half) this (K-step, row) belongs to
@@ -596,6 +606,7 @@ static int launch_t(const KernelArgs& a, cudaStream_t st, int grid) {
     return NF_OK;
 }
 
+#ifdef NF_TUNING
 // How many clusters of four CTAs (one CTA per SM: 227 KB of shared memory each) the device can hold at once: a cluster
 // lives inside one GPC, so GPCs whose SM count is not a multiple of four leave SMs idle.  Queried once per device.
 template <bool BF16>
@@ -621,32 +632,26 @@ static int max_clusters4() {
     }
     return cached[dev] > 0 ? cached[dev] : 0;
 }
-
-// The one-tile kernel below is the production path.  The two-tile kernel (nf_mlp2.cu) measures the same today (both sit
-// on the accumulator-drain / dependency-ring bound, profiles/r02_notes.md) and stays an experiment of the tuning build.
-int launch(const KernelArgs& a, int dtype, cudaStream_t st) {
-#ifdef NF_TUNING
-    const char* e = getenv("NF_MLP_IMPL");
-    if (e && atoi(e) == 2) return launch2(a, dtype, st);
 #endif
-    return launch1(a, dtype, st);
-}
 
-// Clusters of two CTA pairs when (nearly) every SM fits into one, else plain CTA pairs (cluster of 2)
-int launch1(const KernelArgs& a, int dtype, cudaStream_t st) {
+// CTA pairs (cluster of 2, tcgen05 cta_group::2).  The tuning build can also run clusters of two pairs with multicast
+// weight quarters (NF_MLP_CLUSTER=4) and the two-tile kernel of nf_mlp2.cu (NF_MLP_IMPL=2): both measured, neither faster
+// (profiles/r02_notes.md), so the release library carries neither.
+int launch(const KernelArgs& a, int dtype, cudaStream_t st) {
     const bool bf = dtype == NF_DTYPE_BF16;
-    const int c4 = bf ? max_clusters4<true>() : max_clusters4<false>();
     const int pairs_grid = num_sms() & ~1;
 #ifdef NF_TUNING
+    const char* impl = getenv("NF_MLP_IMPL");
+    if (impl && atoi(impl) == 2) return launch2(a, dtype, st);
     const char* e = getenv("NF_MLP_CLUSTER");
-    const bool want4 = e ? atoi(e) == 4 : false;
-#else
-    const bool want4 = false;      // measured: no gain (the bound is per-SM ingest, not L2 reads), and GPCs strand a few SMs
-#endif
-    if (want4 && c4 * 4 * 10 >= pairs_grid * 9) {       // at most 10 % of the SMs left without a cluster
-        const int grid = 4 * (c4 < num_sms() / 4 ? c4 : num_sms() / 4);
-        return bf ? launch_t<true, 4>(a, st, grid) : launch_t<false, 4>(a, st, grid);
+    if (e && atoi(e) == 4) {
+        const int c4 = bf ? max_clusters4<true>() : max_clusters4<false>();
+        if (c4 * 4 * 10 >= pairs_grid * 9) {       // at most 10 % of the SMs left without a cluster
+            const int grid = 4 * (c4 < num_sms() / 4 ? c4 : num_sms() / 4);
+            return bf ? launch_t<true, 4>(a, st, grid) : launch_t<false, 4>(a, st, grid);
+        }
     }
+#endif
     return bf ? launch_t<true, 2>(a, st, pairs_grid) : launch_t<false, 2>(a, st, pairs_grid);
 }
 
@@ -658,8 +663,13 @@ using namespace nf;
 extern "C" size_t nf_render_packed_weights_bytes(void) { return (size_t)mlp::PACKED_BYTES; }
 
 extern "C" int nf_render_pack_weights(const float* const* params, int dtype, void* packed_out, void* stream_) {
+    return nf_render_pack_weights_ex(params, dtype, NF_ENC_ALL, packed_out, stream_);
+}
+
+extern "C" int nf_render_pack_weights_ex(const float* const* params, int dtype, int enc_flags, void* packed_out, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     NF_REQUIRE(params && packed_out, NF_E_INVALID, "nf_render_pack_weights: null argument");
+    NF_REQUIRE(enc_flags >= 0 && enc_flags <= NF_ENC_ALL, NF_E_INVALID, "nf_render_pack_weights: enc_flags %d", enc_flags);
     NF_REQUIRE(dtype == NF_DTYPE_F16 || dtype == NF_DTYPE_BF16, NF_E_UNSUPPORTED, "nf_render_pack_weights: dtype %d", dtype);
     mlp::PackArgs p;
     for (int i = 0; i < 12; ++i) {
@@ -669,9 +679,9 @@ extern "C" int nf_render_pack_weights(const float* const* params, int dtype, voi
     }
     const int total = mlp::N256_STEPS * 512 + mlp::N128_STEPS * 256;
     if (dtype == NF_DTYPE_BF16)
-        mlp::k_pack_weights<true><<<(total + 255) / 256, 256, 0, st>>>(p, (uint8_t*)packed_out);
+        mlp::k_pack_weights<true><<<(total + 255) / 256, 256, 0, st>>>(p, (uint8_t*)packed_out, enc_flags);
     else
-        mlp::k_pack_weights<false><<<(total + 255) / 256, 256, 0, st>>>(p, (uint8_t*)packed_out);
+        mlp::k_pack_weights<false><<<(total + 255) / 256, 256, 0, st>>>(p, (uint8_t*)packed_out, enc_flags);
     NF_LAUNCH_OK();
     return NF_OK;
 }

@@ -38,6 +38,24 @@ __host__ __device__ inline int wu_ksteps(int seg) { return seg == 0 ? 4 : 8; }
 __host__ __device__ inline int layer_pe_steps(int l) { return (l == 0 || l == 4) ? KX_STEPS : (l == 9 ? KD_STEPS : 0); }
 
 
+// Encoding ablations: fixed-layout column k of the xyz-like block (0..207) / dir-like block (0..63) -> column of the
+// network's own (narrower) input, or -1 when the block is disabled or k is padding.  flags = NF_ENC_*.
+__host__ __device__ inline int enc_in_xyz(int flags) { return 63 + ((flags & 1) ? 9 : 0) + ((flags & 2) ? 63 : 0) + ((flags & 4) ? 63 : 0); }
+__host__ __device__ inline int enc_in_dir(int flags) { return 27 + ((flags & 8) ? 27 : 0); }
+__host__ __device__ inline int enc_col_xyz(int k, int flags) {
+    if (k < 63) return k;
+    const int d = (flags & 1) ? 9 : 0, s = (flags & 2) ? 63 : 0;
+    if (k < 72) return (flags & 1) ? 63 + (k - 63) : -1;
+    if (k < 135) return (flags & 2) ? 63 + d + (k - 72) : -1;
+    if (k < 198) return (flags & 4) ? 63 + d + s + (k - 135) : -1;
+    return -1;
+}
+__host__ __device__ inline int enc_col_dir(int k, int flags) {
+    if (k < 27) return k;
+    if (k < 54) return (flags & 8) ? 27 + (k - 27) : -1;
+    return -1;
+}
+
 struct KernelArgs {
     const uint8_t* packed;   // weight slabs + small params
     const float* records;    // (n_rows,16)
@@ -52,10 +70,10 @@ struct KernelArgs {
 };
 
 
-int launch(const KernelArgs& a, int dtype, cudaStream_t st);        // dispatches to launch2 (nf_mlp2.cu) unless a tuning build says otherwise
-int launch1(const KernelArgs& a, int dtype, cudaStream_t st);       // one tile per CTA (nf_mlp.cu)
-int launch2(const KernelArgs& a, int dtype, cudaStream_t st);       // two tiles per CTA sharing the weight stream (nf_mlp2.cu)
-size_t pe_scratch_bytes();                                          // per-device scratch of launch2 (allocated once, kept)
+int launch(const KernelArgs& a, int dtype, cudaStream_t st);        // nf_mlp.cu: CTA pairs, one 128-row tile per CTA
+#ifdef NF_TUNING
+int launch2(const KernelArgs& a, int dtype, cudaStream_t st);       // nf_mlp2.cu (experiment): two tiles per CTA sharing the weight stream
+#endif
 
 }  // namespace mlp
 }  // namespace nf

@@ -22,10 +22,14 @@
 // Roles (14 warps): 0-7 epilogue (two groups of four: group g owns columns [64c + 32g, +32) of every 64-column chunk c;
 // order per layer: (half 0, tile 0) (half 0, tile 1) (half 1, tile 0) (half 1, tile 1)), 8 MMA issuer (rank 0) / weight relay (rank 1),
 // 9 loader, 10-13 encoding producers.
+// Compiled into the TUNING build only (python -m neurofluid_b200.build --tuning; NF_MLP_IMPL=2 selects it): it measures the
+// same as the production kernel today (profiles/r02_mlp_timeline.txt, profiles/r02_notes.md), so the release library does
+// not carry it.
 #include "nf_common.cuh"
 #include "nf_mlp.cuh"
 #include "nf_tc.cuh"
 
+#ifdef NF_TUNING
 namespace nf {
 namespace mlp {
 namespace v2 {
@@ -518,11 +522,10 @@ static int launch_t(const KernelArgs& a, cudaStream_t st) {
 
 }  // namespace v2
 
-size_t pe_scratch_bytes() { return (size_t)num_sms() * v2::PE_CTA_BYTES; }
-
 int launch2(const KernelArgs& a, int dtype, cudaStream_t st) {
     return dtype == NF_DTYPE_BF16 ? v2::launch_t<true>(a, st) : v2::launch_t<false>(a, st);
 }
 
 }  // namespace mlp
 }  // namespace nf
+#endif  // NF_TUNING

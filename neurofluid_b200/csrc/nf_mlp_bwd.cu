@@ -84,7 +84,7 @@ struct PackArgs {
     const float* w[12];
 };
 
-__global__ void k_pack_weights_bwd(PackArgs p, uint8_t* out) {
+__global__ void k_pack_weights_bwd(PackArgs p, uint8_t* out, int enc) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     int base = 0;
     size_t byte0 = 0;
@@ -96,10 +96,11 @@ __global__ void k_pack_weights_bwd(PackArgs p, uint8_t* out) {
             const int u = t - base;
             const int step = u / (2 * rows), kc = (u / rows) % 2, i = u % rows;
             // source column of W_layer for slab row i (-1: padding)
+            const int in_xyz = enc_in_xyz(enc), in_dir = enc_in_dir(enc);      // encoding ablations: narrower inputs (nf_mlp.cuh)
             int col = i, ld = 256;
-            if (layer == 9) { ld = 310; col = i < 256 ? i : (i - 256 < 54 ? 256 + (i - 256) : -1); }
-            else if (layer == 4) { ld = 454; col = i < 256 ? 198 + i : (i - 256 < 198 ? i - 256 : -1); }
-            else if (layer == 0) { ld = 198; col = i < 198 ? i : -1; }
+            if (layer == 9) { ld = 256 + in_dir; col = i < 256 ? i : (enc_col_dir(i - 256, enc) < 0 ? -1 : 256 + enc_col_dir(i - 256, enc)); }
+            else if (layer == 4) { ld = in_xyz + 256; col = i < 256 ? in_xyz + i : enc_col_xyz(i - 256, enc); }
+            else if (layer == 0) { ld = in_xyz; col = enc_col_xyz(i, enc); }
             const float* W = p.w[layer];
             uint32_t pk[4], pl[4];
 #pragma unroll
@@ -707,7 +708,12 @@ extern "C" size_t nf_render_param_count(void) { return (size_t)bwd::param_offset
 extern "C" size_t nf_render_packed_weights_bwd_bytes(void) { return bwd::bwd_pack_bytes(); }
 
 extern "C" int nf_render_pack_weights_bwd(const float* const* params, void* packed_out, void* stream_) {
+    return nf_render_pack_weights_bwd_ex(params, NF_ENC_ALL, packed_out, stream_);
+}
+
+extern "C" int nf_render_pack_weights_bwd_ex(const float* const* params, int enc_flags, void* packed_out, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
+    NF_REQUIRE(enc_flags >= 0 && enc_flags <= NF_ENC_ALL, NF_E_INVALID, "nf_render_pack_weights_bwd: enc_flags %d", enc_flags);
     NF_REQUIRE(params && packed_out, NF_E_INVALID, "nf_render_pack_weights_bwd: null argument");
     bwd::PackArgs p;
     for (int i = 0; i < 12; ++i) {
@@ -720,7 +726,7 @@ extern "C" int nf_render_pack_weights_bwd(const float* const* params, void* pack
         bwd::bwd_gemm(g, ns, rows, l);
         total += ns * 2 * rows;      // one thread per 16-byte row piece; it writes the hi and the lo copy
     }
-    bwd::k_pack_weights_bwd<<<(total + 255) / 256, 256, 0, st>>>(p, (uint8_t*)packed_out);
+    bwd::k_pack_weights_bwd<<<(total + 255) / 256, 256, 0, st>>>(p, (uint8_t*)packed_out, enc_flags);
     NF_LAUNCH_OK();
     return NF_OK;
 }

@@ -49,14 +49,15 @@ def ball_query(queries: torch.Tensor, points: torch.Tensor, K: int, radius: floa
     return d2, idx64, nn
 
 
-def pack_nerf_weights(params, dtype=_lib.NF_DTYPE_F16) -> torch.Tensor:
-    """params: 24 CUDA fp32 tensors (weight, bias) x [xyz_encoding_1..8, final, dir, sigma, rgb]."""
+def pack_nerf_weights(params, dtype=_lib.NF_DTYPE_F16, enc_flags=15) -> torch.Tensor:
+    """params: 24 CUDA fp32 tensors (weight, bias) x [xyz_encoding_1..8, final, dir, sigma, rgb].  enc_flags (NF_ENC_*): which
+    encoding blocks the network was built with (narrower first / skip / dir layers when one is off)."""
     assert len(params) == 24
     ps = [p.detach().to(torch.float32).contiguous() for p in params]
     require_cuda(*ps)
     out = torch.empty(lib().nf_render_packed_weights_bytes(), dtype=torch.uint8, device=ps[0].device)
     arr = (C.c_void_p * 24)(*[p.data_ptr() for p in ps])
-    check(lib().nf_render_pack_weights(arr, int(dtype), ptr(out), stream_ptr()), "nf_render_pack_weights")
+    check(lib().nf_render_pack_weights_ex(arr, int(dtype), int(enc_flags), ptr(out), stream_ptr()), "nf_render_pack_weights")
     out._keepalive = ps
     return out
 

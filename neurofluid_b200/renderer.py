@@ -38,16 +38,21 @@ class RenderNet(nn.Module):
         self.fix_radius = cfg.NN_search.fix_radius
         self.num_neighbor = cfg.NN_search.N_neighbor
         enc = cfg.encoding
-        if not (enc.density and enc.var and enc.smoothed_pos and enc.smoothed_dir and enc.exclude_ray):
-            raise NFError("the sm_100a kernels implement the shipped encoding set (density, var, smoothed_pos, "
-                          "smoothed_dir, exclude_ray all on; configs/end2end.yaml:43-49)")
+        if not enc.exclude_ray:
+            raise NFError("exclude_ray=False (blend of the sample position into the smoothed position, "
+                          "models/renderer.py:100-109) is not implemented; every shipped config sets exclude_ray=True")
+        # encoding ablations (models/renderer.py:152-175): a disabled block narrows the networks' inputs; the kernels still
+        # produce all six encodings and the weight packer leaves the disabled block's columns zero (nf_render_pack_weights_ex)
+        self.enc_flags = (1 if enc.density else 0) | (2 if enc.smoothed_pos else 0) | (4 if enc.var else 0) | \
+            (8 if enc.smoothed_dir else 0)
         if not self.fix_radius:
             raise NFError("fix_radius=False has no live code path in the reference (models/renderer.py:119-121)")
         self.embedding_xyz = Embedding(3, 10)
         self.embedding_dir = Embedding(3, 4)
         self.embedding_density = Embedding(1, 4)
-        in_xyz = 3 * self.embedding_xyz.out_channels + self.embedding_density.out_channels      # 198
-        in_dir = 2 * self.embedding_dir.out_channels                                            # 54
+        in_xyz = self.embedding_xyz.out_channels * (1 + bool(enc.smoothed_pos) + bool(enc.var)) + \
+            (self.embedding_density.out_channels if enc.density else 0)                          # 198 with everything on
+        in_dir = self.embedding_dir.out_channels * (1 + bool(enc.smoothed_dir))                  # 54
         self.nerf_coarse = NeRF(in_channels_xyz=in_xyz, in_channels_dir=in_dir)
         self.nerf_fine = NeRF(in_channels_xyz=in_xyz, in_channels_dir=in_dir)
         self.operand_dtype = {"fp16": _lib.NF_DTYPE_F16, "bf16": _lib.NF_DTYPE_BF16}[operand_dtype]
@@ -74,7 +79,7 @@ class RenderNet(nn.Module):
         key = tuple((p.data_ptr(), p._version) for p in params) + (self.operand_dtype,)
         hit = self._packed.get(name)
         if hit is None or hit[0] != key:
-            self._packed[name] = (key, pack_nerf_weights(params, self.operand_dtype))
+            self._packed[name] = (key, pack_nerf_weights(params, self.operand_dtype, self.enc_flags))
         return self._packed[name][1]
 
     def _sample_tables(self, device, use_disp):
@@ -135,7 +140,7 @@ class RenderNet(nn.Module):
             require_cuda(*ps)
             out = torch.empty(lib().nf_render_packed_weights_bwd_bytes(), dtype=torch.uint8, device=ps[0].device)
             arr = (C.c_void_p * 24)(*[p.data_ptr() for p in ps])
-            check(lib().nf_render_pack_weights_bwd(arr, ptr(out), stream_ptr()), "nf_render_pack_weights_bwd")
+            check(lib().nf_render_pack_weights_bwd_ex(arr, int(self.enc_flags), ptr(out), stream_ptr()), "nf_render_pack_weights_bwd")
             out._keepalive = ps
             self._packed[name + "/bwd"] = (key, out)
         return self._packed[name + "/bwd"][1]
@@ -323,14 +328,47 @@ class _RenderFunction(torch.autograd.Function):
             b.d_particles, b.d_params_coarse, b.d_params_fine = ptr(d_particles), ptr(flats[0]), ptr(flats[1])
             b.workspace, b.workspace_bytes = ptr(bws), bws.numel()
             check(lib().nf_render_backward(C.byref(b), stream_ptr()), "nf_render_backward")
+        # the library's flat layout is the full-width network (198 / 454 / 310 input columns); with encoding ablations the
+        # module's own matrices keep only the enabled blocks' columns
+        full_in = [198, 256, 256, 256, 454, 256, 256, 256, 256, 310, 256, 128]
+        cx = [k for k in range(198) if _enc_col(k, net.enc_flags, False) >= 0]
+        cd = [k for k in range(54) if _enc_col(k, net.enc_flags, True) >= 0]
         pgrads = []
         for flat, name in zip(flats, ("nerf_coarse", "nerf_fine")):
             o = 0
-            for p in getattr(net, name).ordered_params():
-                pgrads.append(flat[o:o + p.numel()].view(p.shape))
-                o += p.numel()
+            params = getattr(net, name).ordered_params()
+            for li in range(12):
+                w, bias = params[2 * li], params[2 * li + 1]
+                gw = flat[o:o + w.shape[0] * full_in[li]].view(w.shape[0], full_in[li])
+                o += gw.numel()
+                if net.enc_flags != 15:
+                    if li == 0:
+                        gw = gw[:, cx]
+                    elif li == 4:
+                        gw = torch.cat([gw[:, cx], gw[:, 198:]], 1)
+                    elif li == 9:
+                        gw = torch.cat([gw[:, :256], gw[:, [256 + k for k in cd]]], 1)
+                pgrads.append(gw.reshape(w.shape))
+                pgrads.append(flat[o:o + bias.numel()].view(bias.shape))
+                o += bias.numel()
         need_in = ctx.needs_input_grad
         return (None, None, d_particles if need_in[2] else None) + tuple(gp if need_in[3 + i] else None for i, gp in enumerate(pgrads))
+
+
+def _enc_col(k, flags, is_dir):
+    """Mirror of enc_col_xyz / enc_col_dir (csrc/nf_mlp.cuh): fixed-layout column -> the network's own input column, or -1."""
+    if is_dir:
+        return k if k < 27 else (27 + (k - 27) if (flags & 8) and k < 54 else -1)
+    d, s_ = (9 if flags & 1 else 0), (63 if flags & 2 else 0)
+    if k < 63:
+        return k
+    if k < 72:
+        return 63 + (k - 63) if flags & 1 else -1
+    if k < 135:
+        return 63 + d + (k - 72) if flags & 2 else -1
+    if k < 198:
+        return 63 + d + s_ + (k - 135) if flags & 4 else -1
+    return -1
 
 
 def _render_with_grad(net, mode, physical_particles, ro, rays, use_disp, perturb, noise_std, white_background):

@@ -36,11 +36,15 @@ def import_reference():
 
 
 def render_case(RenderNet, ray_utils, name, n_lat, H, crop, seed, sigma_boost, use_mask=True, rays_stride=1,
-                center=(0.0, 0.0, 0.0), weight_gain=1.0):
+                center=(0.0, 0.0, 0.0), weight_gain=1.0, enc=None):
     from neurofluid_b200 import scenes
-    cfg = scenes.render_cfg(use_mask=use_mask)
+    enc = enc or {}
+    cfg = scenes.render_cfg(use_mask=use_mask, **enc)
     net = RenderNet(cfg, scenes.NEAR, scenes.FAR)
-    sd = scenes.init_render_state(seed, sigma_boost, weight_gain=weight_gain)
+    e = cfg.encoding
+    in_xyz = 63 * (1 + bool(e.smoothed_pos) + bool(e.var)) + (9 if e.density else 0)
+    in_dir = 27 * (1 + bool(e.smoothed_dir))
+    sd = scenes.init_render_state(seed, sigma_boost, in_xyz=in_xyz, in_dir=in_dir, weight_gain=weight_gain)
     net.load_state_dict(sd, strict=True)
     particles = torch.from_numpy(scenes.lattice_particles(n_lat, seed, center=center))
     # rays through the reference's own get_ray_directions/get_rays
@@ -63,12 +67,13 @@ def render_case(RenderNet, ray_utils, name, n_lat, H, crop, seed, sigma_boost, u
         # evident intent (sigma-only coarse pass) and is checked for self-consistency only.
         try:
             fine = net.fine_rendering(particles, ro, rays, focal, cw)
-        except (UnboundLocalError, ValueError):
+        except (UnboundLocalError, ValueError, TypeError):
             fine = {}
     out = {
         "n_lat": n_lat, "H": H, "crop": crop, "seed": seed, "sigma_boost": sigma_boost, "use_mask": use_mask,
         "rays_stride": rays_stride, "weight_gain": weight_gain, "center": np.asarray(center, np.float32),
         "rays": rays.numpy(),                       # stored so the GPU box needs no reference code
+        "enc": np.asarray([bool(e.density), bool(e.smoothed_pos), bool(e.var), bool(e.smoothed_dir)]),
     }
     for k, v in full.items():
         out[f"forward.{k}"] = v.numpy()
@@ -154,6 +159,10 @@ def main():
     render_case(RenderNet, ray_utils, "cfg0_sub", 18, 400, 64, 3, 5.0, rays_stride=16)
     # He-scaled weights: O(1) activations, sigma of both signs, structured rgb -> stresses MLP numerics
     render_case(RenderNet, ray_utils, "small_he", 9, 400, 16, 4, 1.0, weight_gain=2.45)
+    # encoding ablations (models/renderer.py:152-175): the reference's only published numbers are the "wo-smoothed_dir" run
+    render_case(RenderNet, ray_utils, "small_wo_sdir", 9, 400, 16, 6, 5.0, enc=dict(smoothed_dir=False))
+    render_case(RenderNet, ray_utils, "small_min_enc", 9, 400, 16, 7, 5.0, enc=dict(density=False, var=False, smoothed_pos=False,
+                                                                                       smoothed_dir=False))
     render_jitter_case(RenderNet, ray_utils, "small_jitter", 9, 400, 16, 5, 5.0, perturb=1.0, noise_std=0.5, rays_stride=4)
     transition_case(ParticleNet, "small", 8, 0, 0.1, 3)
     transition_case(ParticleNet, "medium", 14, 1, 0.05, 2)

@@ -8,6 +8,7 @@ from neurofluid_b200 import scenes
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 RENDER_CASES = ["small_boost", "small_default", "small_nomask", "cfg0_sub", "small_he"]
+ABLATION_CASES = ["small_wo_sdir", "small_min_enc"]        # encoding blocks switched off (models/renderer.py:152-175)
 TRANSITION_CASES = ["small", "medium"]
 
 
@@ -18,8 +19,15 @@ def rel_l2(a, b):
 
 def load_render_case(name):
     g = np.load(os.path.join(GOLDEN, f"render_{name}.npz"))
-    cfg = scenes.render_cfg(use_mask=bool(g["use_mask"]))
-    sd = scenes.init_render_state(int(g["seed"]), float(g["sigma_boost"]), weight_gain=float(g["weight_gain"]))
+    enc = {}
+    if "enc" in g.files:
+        enc = dict(zip(("density", "smoothed_pos", "var", "smoothed_dir"), [bool(v) for v in g["enc"]]))
+    cfg = scenes.render_cfg(use_mask=bool(g["use_mask"]), **enc)
+    e = cfg.encoding
+    in_xyz = 63 * (1 + bool(e.smoothed_pos) + bool(e.var)) + (9 if e.density else 0)
+    in_dir = 27 * (1 + bool(e.smoothed_dir))
+    sd = scenes.init_render_state(int(g["seed"]), float(g["sigma_boost"]), in_xyz=in_xyz, in_dir=in_dir,
+                                  weight_gain=float(g["weight_gain"]))
     particles = torch.from_numpy(scenes.lattice_particles(int(g["n_lat"]), int(g["seed"]), center=tuple(g["center"])))
     rays = torch.from_numpy(g["rays"])
     cw = torch.from_numpy(scenes.CAMERA_C2W)

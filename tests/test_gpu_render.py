@@ -13,7 +13,7 @@ import neurofluid_b200 as nb
 from neurofluid_b200 import _lib, ops, scenes
 from oracle import renderer as orender
 from oracle import third_party_ops as tpo
-from helpers import RENDER_CASES, load_render_case, rel_l2
+from helpers import ABLATION_CASES, RENDER_CASES, load_render_case, rel_l2
 
 pytestmark = pytest.mark.gpu
 RGB_TOL = 1e-3      # BASELINE.json north_star: 1e-3 relative L2 on rendered RGB
@@ -94,7 +94,7 @@ def test_fused_encoding_mlp_vs_fp32(dev, gain, n, tol_rgb, tol_sigma):
     assert torch.equal(out_p, out[perm])
 
 
-@pytest.mark.parametrize("name", RENDER_CASES)
+@pytest.mark.parametrize("name", RENDER_CASES + ABLATION_CASES)
 def test_render_forward_matches_reference_golden(dev, name):
     c = load_render_case(name)
     g = c["g"]

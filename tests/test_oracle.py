@@ -9,10 +9,10 @@ from oracle import renderer as orender
 from oracle import third_party_ops as tpo
 from oracle import transition as otrans
 from neurofluid_b200 import scenes
-from helpers import RENDER_CASES, TRANSITION_CASES, load_render_case, load_transition_case, rel_l2
+from helpers import ABLATION_CASES, RENDER_CASES, TRANSITION_CASES, load_render_case, load_transition_case, rel_l2
 
 
-@pytest.mark.parametrize("name", RENDER_CASES)
+@pytest.mark.parametrize("name", RENDER_CASES + ABLATION_CASES)
 def test_render_oracle_matches_reference_golden(name):
     c = load_render_case(name)
     g = c["g"]
