@@ -172,6 +172,10 @@ typedef struct nf_render_args {
     int32_t u_stride;    /* likewise for u_importance (perturb > 0: u ~ U[0,1) per ray and sample) */
     const float* noise0; /* optional (n_rays, n_coarse): added to sigma before the ReLU in the coarse compositing */
     const float* noise1; /* optional (n_rays, n_coarse + n_importance): the same for the fine pass */
+    /* cfg.encoding.exclude_ray == False (models/renderer.py:100-109): smoothed position = x (1 - alpha) + weighted mean * alpha,
+       alpha = 0.9 when same_smooth_factor, else 0.1 for samples with <= 20 neighbours and 0.9 above */
+    int32_t include_ray;        /* 0: exclude_ray=True (every shipped config) */
+    int32_t same_smooth_factor;
 } nf_render_args;
 
 #define NF_RENDER_SAVE_NEIGHBORS 1

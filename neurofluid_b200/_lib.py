@@ -30,6 +30,7 @@ class RenderArgs(C.Structure):
         ("rgb1", _vp), ("depth1", _vp), ("opacity1", _vp), ("num_nn1", _vp), ("mask1", _vp),
         ("workspace", _vp), ("workspace_bytes", _sz), ("stats", _vp), ("flags", _i32),
         ("z_stride", _i32), ("u_stride", _i32), ("noise0", _vp), ("noise1", _vp),
+        ("include_ray", _i32), ("same_smooth_factor", _i32),
     ]
 
 

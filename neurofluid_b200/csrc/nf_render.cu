@@ -45,6 +45,7 @@ struct StageArgs {
     float radius;
     int K;
     int use_mask, white_bg, mode;
+    int include_ray, same_smooth;              // exclude_ray=False: blend the sample position into the smoothed position
     int search_mode;                           // 0 = index-order stream, 1 = sorted-candidate sweep
     float sub_span;                            // sweep: max depth span of one gather
     int sub_look;                              // sweep: ... and max samples ahead it reaches
@@ -556,7 +557,11 @@ __device__ __forceinline__ void ray_query_group(const StageArgs& p, int lane, co
                         for (int k = 0; k < K; ++k) nbr[(size_t)row * K + k] = p.nbr0[(size_t)row0 * K + k];
                 } else {
                     const float den = wsum + 1e-12f;
-                    const float sx = wx / den, sy = wy / den, sz = wz / den;
+                    float sx = wx / den, sy = wy / den, sz = wz / den;
+                    if (p.include_ray) {          // models/renderer.py:100-109
+                        const float al = (p.same_smooth || nvalid > 20) ? 0.9f : 0.1f;
+                        sx = qx * (1.0f - al) + sx * al; sy = qy * (1.0f - al) + sy * al; sz = qz * (1.0f - al) + sz * al;
+                    }
                     const float tx = sx - rox, ty = sy - roy, tz = sz - roz;
                     const float tn = sqrtf(tx * tx + ty * ty + tz * tz);
                     dst[0] = make_float4(qx, qy, qz, wsum);
@@ -1132,6 +1137,7 @@ extern "C" int nf_render_forward(const nf_render_args* a, void* stream_) {
     p.radius = a->radius;
     p.K = a->K;
     p.use_mask = a->use_mask; p.white_bg = a->white_background; p.mode = a->mode;
+    p.include_ray = a->include_ray; p.same_smooth = a->same_smooth_factor;
     {
         // search tuning: compile-time constants.  A build with -DNF_TUNING (tests/gpu_tune.py) reads NF_* environment
         // overrides instead; the release library never looks at the environment.

@@ -139,6 +139,7 @@ struct GeomArgs {
     float radius;
     float ro[3];
     const float* ro_dev;
+    int include_ray, same_smooth;
     float* dparticles;       // (P, 3), accumulated
 };
 
@@ -196,13 +197,17 @@ __global__ void __launch_bounds__(WARPS * 32) k_geom_bwd(const GeomArgs p) {
         const float Nx = warp_sum(w * nx), Ny = warp_sum(w * ny), Nz = warp_sum(w * nz);
         const float den = W + 1e-12f;
         const float sx = Nx / den, sy = Ny / den, sz = Nz / den;
-        const float ux = sx - rox, uy = sy - roy, uz = sz - roz;
+        // exclude_ray=False: the encoded position is x (1 - alpha) + smoothed * alpha -> its gradient reaches the neighbours scaled by alpha
+        const int nv_cnt = __popc(__ballot_sync(NF_FULL, valid && dist2_exact(qx, qy, qz, nx, ny, nz) != 0.f));
+        const float al = p.include_ray ? ((p.same_smooth || nv_cnt > 20) ? 0.9f : 0.1f) : 1.0f;
+        const float bx = qx * (1.0f - al) + sx * al, by = qy * (1.0f - al) + sy * al, bz = qz * (1.0f - al) + sz * al;
+        const float ux = bx - rox, uy = by - roy, uz = bz - roz;
         const float un = sqrtf(ux * ux + uy * uy + uz * uz);
         const float dxs = ux / un, dys = uy / un, dzs = uz / un;
         const float dot = dxs * g_sd[0] + dys * g_sd[1] + dzs * g_sd[2];
         // d smoothed (direct + through the smoothed direction)
-        const float gsx = g_sm[0] + (g_sd[0] - dxs * dot) / un, gsy = g_sm[1] + (g_sd[1] - dys * dot) / un,
-                    gsz = g_sm[2] + (g_sd[2] - dzs * dot) / un;
+        const float gsx = al * (g_sm[0] + (g_sd[0] - dxs * dot) / un), gsy = al * (g_sm[1] + (g_sd[1] - dys * dot) / un),
+                    gsz = al * (g_sm[2] + (g_sd[2] - dzs * dot) / un);
         const float dNx = gsx / den, dNy = gsy / den, dNz = gsz / den;
         const float dW = g_den - (gsx * sx + gsy * sy + gsz * sz) / den;
         float gx = 0.f, gy = 0.f, gz = 0.f;
@@ -334,6 +339,7 @@ extern "C" int nf_render_backward(const nf_render_bwd_args* b, void* stream_) {
         g.nbr = (const int*)(ws + (coarse ? v.nbr0 : v.nbr1));
         g.particles = a->particles; g.n_rows = rows; g.K = a->K; g.radius = a->radius;
         g.ro[0] = a->ro[0]; g.ro[1] = a->ro[1]; g.ro[2] = a->ro[2]; g.ro_dev = a->ro_dev;
+        g.include_ray = a->include_ray; g.same_smooth = a->same_smooth_factor;
         g.dparticles = b->d_particles;
         k_geom_bwd<<<min((rows + WARPS - 1) / WARPS, num_sms() * 8), WARPS * 32, 0, st>>>(g);
         NF_LAUNCH_OK();

@@ -38,9 +38,8 @@ class RenderNet(nn.Module):
         self.fix_radius = cfg.NN_search.fix_radius
         self.num_neighbor = cfg.NN_search.N_neighbor
         enc = cfg.encoding
-        if not enc.exclude_ray:
-            raise NFError("exclude_ray=False (blend of the sample position into the smoothed position, "
-                          "models/renderer.py:100-109) is not implemented; every shipped config sets exclude_ray=True")
+        self.include_ray = not enc.exclude_ray            # models/renderer.py:100-109
+        self.same_smooth_factor = bool(getattr(enc, "same_smooth_factor", False))
         # encoding ablations (models/renderer.py:152-175): a disabled block narrows the networks' inputs; the kernels still
         # produce all six encodings and the weight packer leaves the disabled block's columns zero (nf_render_pack_weights_ex)
         self.enc_flags = (1 if enc.density else 0) | (2 if enc.smoothed_pos else 0) | (4 if enc.var else 0) | \
@@ -243,6 +242,7 @@ class RenderNet(nn.Module):
             if ju is not None:
                 a.u_importance, a.u_stride = off(ju, NI), NI
             a.noise0, a.noise1 = off(jn0, S0), off(jn1, S1)
+            a.include_ray, a.same_smooth_factor = int(self.include_ray), int(self.same_smooth_factor)
             a.radius, a.K, a.search = float(self.raduis), int(self.num_neighbor), self.search
             a.mode, a.use_mask, a.white_background = int(mode), int(bool(self.cfg.use_mask)), int(bool(white_background))
             a.dtype = self.operand_dtype

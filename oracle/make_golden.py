@@ -73,7 +73,7 @@ def render_case(RenderNet, ray_utils, name, n_lat, H, crop, seed, sigma_boost, u
         "n_lat": n_lat, "H": H, "crop": crop, "seed": seed, "sigma_boost": sigma_boost, "use_mask": use_mask,
         "rays_stride": rays_stride, "weight_gain": weight_gain, "center": np.asarray(center, np.float32),
         "rays": rays.numpy(),                       # stored so the GPU box needs no reference code
-        "enc": np.asarray([bool(e.density), bool(e.smoothed_pos), bool(e.var), bool(e.smoothed_dir)]),
+        "enc": np.asarray([bool(e.density), bool(e.smoothed_pos), bool(e.var), bool(e.smoothed_dir), bool(e.exclude_ray)]),
     }
     for k, v in full.items():
         out[f"forward.{k}"] = v.numpy()
@@ -163,6 +163,7 @@ def main():
     render_case(RenderNet, ray_utils, "small_wo_sdir", 9, 400, 16, 6, 5.0, enc=dict(smoothed_dir=False))
     render_case(RenderNet, ray_utils, "small_min_enc", 9, 400, 16, 7, 5.0, enc=dict(density=False, var=False, smoothed_pos=False,
                                                                                        smoothed_dir=False))
+    render_case(RenderNet, ray_utils, "small_incl_ray", 9, 400, 16, 8, 5.0, enc=dict(exclude_ray=False))
     render_jitter_case(RenderNet, ray_utils, "small_jitter", 9, 400, 16, 5, 5.0, perturb=1.0, noise_std=0.5, rays_stride=4)
     transition_case(ParticleNet, "small", 8, 0, 0.1, 3)
     transition_case(ParticleNet, "medium", 14, 1, 0.05, 2)

@@ -88,8 +88,11 @@ def local_geometry_features(d2, nn, xyz, rays, ro, radius, enc, sigma_only=False
     w = torch.clamp(1 - (dist / radius) ** 3, min=0)
     density = w.sum(-1, keepdim=True)
     smoothed = (w.unsqueeze(-1) * nn).sum(-2) / (density + 1e-12)
-    if not enc.exclude_ray:
-        raise NotImplementedError("exclude_ray=False (alpha blend) is not on any shipped config")
+    if not enc.exclude_ray:                             # models/renderer.py:100-109
+        alpha = torch.full((R, S, 1), 0.9)
+        if not getattr(enc, "same_smooth_factor", False):
+            alpha[num_nn.le(20)] = 0.1
+        smoothed = xyz * (1 - alpha) + smoothed * alpha
     sm = smoothed.reshape(-1, 3)
     sdir = sm - ro.view(1, 3)
     sdir = sdir / torch.norm(sdir, dim=-1, keepdim=True)

@@ -8,7 +8,7 @@ from neurofluid_b200 import scenes
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 RENDER_CASES = ["small_boost", "small_default", "small_nomask", "cfg0_sub", "small_he"]
-ABLATION_CASES = ["small_wo_sdir", "small_min_enc"]        # encoding blocks switched off (models/renderer.py:152-175)
+ABLATION_CASES = ["small_wo_sdir", "small_min_enc", "small_incl_ray"]   # encoding switches (models/renderer.py:100-109,152-175)
 TRANSITION_CASES = ["small", "medium"]
 
 
@@ -21,7 +21,7 @@ def load_render_case(name):
     g = np.load(os.path.join(GOLDEN, f"render_{name}.npz"))
     enc = {}
     if "enc" in g.files:
-        enc = dict(zip(("density", "smoothed_pos", "var", "smoothed_dir"), [bool(v) for v in g["enc"]]))
+        enc = dict(zip(("density", "smoothed_pos", "var", "smoothed_dir", "exclude_ray"), [bool(v) for v in g["enc"]]))
     cfg = scenes.render_cfg(use_mask=bool(g["use_mask"]), **enc)
     e = cfg.encoding
     in_xyz = 63 * (1 + bool(e.smoothed_pos) + bool(e.var)) + (9 if e.density else 0)

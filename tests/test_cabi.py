@@ -77,8 +77,7 @@ def test_rendernet_state_dict_layout_and_errors():
     assert torch.equal(net.set_ro(cw), cw[:, 3])
     with pytest.raises(_lib.NFError):                 # CPU tensors never fall back to a CPU path
         net(torch.zeros(10, 3), cw[:, 3], torch.zeros(4, 6), 1.0, cw)
-    with pytest.raises(_lib.NFError):
-        nb.RenderNet(scenes.render_cfg(exclude_ray=False), scenes.NEAR, scenes.FAR)
+    assert nb.RenderNet(scenes.render_cfg(exclude_ray=False), scenes.NEAR, scenes.FAR).include_ray
     # encoding ablations narrow the networks (models/renderer.py:25-42): state-dict shapes follow the reference's
     abl = nb.RenderNet(scenes.render_cfg(var=False, smoothed_dir=False), scenes.NEAR, scenes.FAR)
     assert abl.nerf_fine.xyz_encoding_1[0].weight.shape == (256, 135) and abl.nerf_fine.dir_encoding[0].weight.shape == (128, 283)

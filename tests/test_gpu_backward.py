@@ -94,7 +94,8 @@ def test_mlp_backward_vs_autograd(dev, n, gain, margin):
 
 @pytest.mark.parametrize("name,mode,margin", [("small_boost", "forward", True), ("small_nomask", "forward", True), ("cfg0_sub", "forward", True),
                                               ("small_boost", "coarse", True), ("small_boost", "forward", False), ("cfg0_sub", "forward", False),
-                                              ("small_wo_sdir", "forward", True), ("small_min_enc", "forward", True)])
+                                              ("small_wo_sdir", "forward", True), ("small_min_enc", "forward", True),
+                                              ("small_incl_ray", "forward", True)])
 def test_render_backward_vs_oracle_autograd(dev, name, mode, margin):
     """loss = mse(rgb0) + mse(rgb1) as in trainer/trainer_e2e.py:236-244; gradients w.r.t. every parameter tensor of both
     MLPs and w.r.t. the particle positions, against autograd through the oracle evaluated on the same merged depths."""
