@@ -244,6 +244,79 @@ def bench_end2end(dev, world, rank, timed, transition="replicated"):
             "note": "BASELINE config[3] shape (honeycone stand-in): transition step + device ray generation + render per frame"}
 
 
+def bench_training(dev):
+    """Training steps through the drop-in modules (forward + backward kernels), single GPU:
+    renderer 1024 random rays of config[1]'s scene (trainer/trainer_renderer.py:102-143), transition model one step of
+    config[2]'s scene (trainer/trainer_transmodel.py:179-197), and one end-to-end step (trainer/trainer_e2e.py:189-302:
+    transition step -> render 1024 rays -> loss -> backward into both networks).  Median of 7, CUDA events."""
+    import neurofluid_b200 as nb
+    from neurofluid_b200 import scenes
+
+    def med(fn, n=7):
+        ts = []
+        for _ in range(n + 2):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return float(np.median(ts[2:]))
+
+    out = {}
+    with torch.enable_grad():
+        rays, focal, cw = scenes.camera_rays(H, W)
+        crop = scenes.center_crop_rays(rays, H, W, 200)
+        sel = torch.randperm(crop.shape[0], generator=torch.Generator().manual_seed(0))[:1024]
+        r = crop[sel].contiguous().to(dev)
+        particles = torch.from_numpy(scenes.lattice_particles(N_LATTICE, 0)).to(dev)
+        rn = nb.RenderNet(scenes.render_cfg(), scenes.NEAR, scenes.FAR); rn.load_state_dict(scenes.init_render_state(0, 5.0)); rn = rn.to(dev)
+        target = torch.rand(1024, 3, device=dev)
+        ro = cw[:, 3].to(dev)
+
+        def render_step():
+            o = rn(particles, ro, r, focal, cw)
+            loss = ((o["rgb0"] - target) ** 2).mean() + ((o["rgb1"] - target) ** 2).mean()
+            for p_ in rn.parameters():
+                p_.grad = None
+            loss.backward()
+        ms = med(render_step)
+        rows = rn.last_stats.sum(0).tolist()
+        out["renderer_1024_rays"] = {"ms_per_step": ms, "rays_per_sec": 1024 / (ms * 1e-3), "mlp_rows_coarse": rows[0], "mlp_rows_fine": rows[1]}
+
+        pos, vel, box, box_n, sd = transition_workload()
+        tn = nb.ParticleNet(gravity=(0.0, 0.0, -9.81)); tn.load_state_dict(sd); tn = tn.to(dev)
+        pos_d, vel_d, box_d, boxn_d = pos.to(dev), vel.to(dev), box.to(dev), box_n.to(dev)
+        gt = pos_d + 0.001
+
+        def trans_step():
+            p1, v1, n1 = tn(pos_d, vel_d, box_d, boxn_d)
+            loss = (torch.exp(-n1 / 40.0) * ((p1 - gt) ** 2).sum(-1)).mean()
+            for p_ in tn.parameters():
+                p_.grad = None
+            loss.backward()
+        ms = med(trans_step)
+        out["transition_30k"] = {"ms_per_step": ms, "particle_steps_per_sec": pos.shape[0] / (ms * 1e-3)}
+
+        n = 23
+        half = (n - 1) / 2 * 0.05
+        p12 = torch.from_numpy(scenes.lattice_particles(n, 0, center=(0.0, 0.0, -1 + 0.03 + half))).to(dev)
+        cw2 = cw.clone(); cw2[2, 3] += -1 + 0.03 + half
+        rays2, focal2, _ = scenes.camera_rays(400, 400)
+        from neurofluid_b200 import ops
+        rr = scenes.center_crop_rays(ops.generate_rays(400, 400, focal2, cw2.to(dev)).cpu(), 400, 400, 100)
+        rr = rr[torch.randperm(rr.shape[0], generator=torch.Generator().manual_seed(1))[:1024]].contiguous().to(dev)
+        ro2 = cw2[:, 3].to(dev)
+
+        def e2e_step():
+            pp, vv, _ = tn(p12, torch.zeros_like(p12), box_d, boxn_d)
+            o = rn(pp, ro2, rr, focal2, cw2)
+            loss = ((o["rgb0"] - target) ** 2).mean() + ((o["rgb1"] - target) ** 2).mean() + 0.1 * torch.relu(pp.abs() - 0.95).mean()
+            for p_ in list(rn.parameters()) + list(tn.parameters()):
+                p_.grad = None
+            loss.backward()
+        ms = med(e2e_step)
+        out["end2end_12k_particles_1024_rays"] = {"ms_per_step": ms, "steps_per_sec": 1e3 / ms}
+    return out
+
+
 def bench_config4(dev, world, rank, timed):
     """BASELINE config[4] size: 37^3 = 50,653 particles, 800x800, rays sharded by image row over the ranks."""
     import neurofluid_b200 as nb
@@ -469,6 +542,8 @@ def main():
     line["transition"] = bench_transition(dev, world, rank, args, timed, pk)
     line["end2end"] = bench_end2end(dev, world, rank, timed)
     line["config4"] = bench_config4(dev, world, rank, timed)
+    if world == 1:
+        line["training"] = bench_training(dev)
     if world > 1:
         line["end2end_sharded_transition"] = bench_end2end(dev, world, rank, timed, transition="sharded")
         line["mgpu_parity"] = mgpu_parity(dev, world, rank)
