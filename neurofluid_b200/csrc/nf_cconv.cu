@@ -1307,29 +1307,290 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_cconv_wgrad(const CWgradArg
     if (warp == WORKER_WARPS) tmem_dealloc(tmem_base, 256);
 }
 
-// ---- small layers: filter gradient = sum_i patch_i (64 cells x cin) (x) g_i (cout), accumulated per block in smem
-__global__ void __launch_bounds__(256) k_cconv_small_wgrad(const Pair* __restrict__ pairs, const int* __restrict__ cnt,
-                                                           const void* __restrict__ in_feat, int ld_in, int kind, int cin, int cout,
-                                                           const float* __restrict__ g, int ld_g, int n_out, float* __restrict__ dK) {
-    extern __shared__ __align__(16) float sm[];
-    const int kn = NCELL * cin * cout, pn = NCELL * cin;
-    float* acc = sm;
+// ---- conv3 (64 -> 3) backward.  With g_i = dL/d ans3_i (3 values) and G_j[c] = K_c^T f_j the forward's projection:
+//   dL/dG_j[c] = sum over the pairs (i, j) of w_ijc g_i = sum over j's OWN list of w_jic' g_i with c' = 63 - c
+// (fluid->fluid lists are symmetric and the filter coordinates of (j, i) mirror those of (i, j)), so one pass over the
+// lists fills dG (N, 64 cells, 3) and everything else is dense:  dL/df_j = sum_c K_c dG_j[c],  dL/dK_c = sum_j f_j (x) dG_j[c].
+__global__ void __launch_bounds__(256) k_conv3_bwd_scatter(const Pair* __restrict__ pairs, const int* __restrict__ cnt,
+                                                           const float* __restrict__ g3 /*(N,3)*/, int n,
+                                                           float* __restrict__ dG /*(N,192)*/, const float4* __restrict__ order) {
+    __shared__ float acc[8][C3_G];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    float* patch = sm + kn + wib * pn;
-    for (int k = threadIdx.x; k < kn; k += blockDim.x) acc[k] = 0.f;
-    __syncthreads();
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_out; i += nwarps) {
-        build_patch(pairs + (size_t)i * MAXNBR, cnt[i], in_feat, ld_in, kind, cin, patch, lane);
-        for (int idx = lane; idx < kn; idx += 32) {
-            const float p = patch[idx / cout];
-            if (p != 0.f) atomicAdd(acc + idx, p * __ldg(g + (size_t)i * ld_g + idx % cout));
+    const int pos_j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (pos_j >= n) return;
+    const int j = order ? __float_as_int(__ldg(&order[pos_j].w)) : pos_j;
+    float* a = acc[wib];
+    for (int k = lane; k < C3_G; k += 32) a[k] = 0.f;
+    __syncwarp();
+    const int m = cnt[j];
+    const Pair* pr = pairs + (size_t)j * MAXNBR;
+    for (int t = lane; t < m; t += 32) {
+        const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(pr + t));
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(pr + t) + 1);
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(pr + t) + 2);
+        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const int i = (int)h0.x;
+        const float gx = __ldg(g3 + 3 * i), gy = __ldg(g3 + 3 * i + 1), gz = __ldg(g3 + 3 * i + 2);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const unsigned cell = (NCELL - 1) - (((c < 4 ? h0.y : h0.z) >> (8 * (c & 3))) & 0xffu);
+            atomicAdd(a + cell * 3, w[c] * gx); atomicAdd(a + cell * 3 + 1, w[c] * gy); atomicAdd(a + cell * 3 + 2, w[c] * gz);
         }
-        __syncwarp();
     }
-    __syncthreads();
-    for (int k = threadIdx.x; k < kn; k += blockDim.x)
-        if (acc[k] != 0.f) atomicAdd(dK + k, acc[k]);
+    __syncwarp();
+    for (int k = lane; k < C3_G; k += 32) dG[(size_t)j * C3_G + k] = a[k];
+}
+
+// dense half of the conv3 backward, 16 particles per pass:  g_ans2 = (dG K^T + g3 Wd3) * (ans2 > 0) (fp32 + bf16) and the
+// filter gradient dK3 (64,64,3) accumulated in registers over the block's particles (one atomic per element per block).
+constexpr int C3B_TP = 16;
+constexpr int C3B_SMEM = (C3_G * C3_IN + C3B_TP * C3_G + C3B_TP * C3_IN + C3B_TP * 4 + 3 * C3_IN) * 4;
+__global__ void __launch_bounds__(256) k_conv3_bwd_dense(const float* __restrict__ dG, const void* __restrict__ x2, int xbf16,
+                                                         const float* __restrict__ kern /*(64,64,3)*/,
+                                                         const float* __restrict__ wd3 /*(3,64)*/, const float* __restrict__ g3,
+                                                         const float* __restrict__ ans2, int n, float* __restrict__ g_ans2,
+                                                         __nv_bfloat16* __restrict__ g_ans2_h, float* __restrict__ dK) {
+    extern __shared__ __align__(16) float sm[];
+    float* sK = sm;                                  // [q = cell*3 + o][ch]
+    float* sG = sK + C3_G * C3_IN;                   // [p][q]
+    float* sX = sG + C3B_TP * C3_G;                  // [p][ch]
+    float* sg3 = sX + C3B_TP * C3_IN;                // [p][4]
+    float* sW = sg3 + C3B_TP * 4;                    // [o][ch]
+    for (int k = threadIdx.x; k < NCELL * C3_IN * C3_OUT; k += blockDim.x) {
+        const int o = k % C3_OUT, ch = (k / C3_OUT) % C3_IN, cell = k / (C3_OUT * C3_IN);
+        sK[(cell * C3_OUT + o) * C3_IN + ch] = __ldg(kern + k);
+    }
+    for (int k = threadIdx.x; k < 3 * C3_IN; k += blockDim.x) sW[k] = __ldg(wd3 + k);
+    const int ch = threadIdx.x & 63, grp = threadIdx.x >> 6;       // a warp has one grp: the sG reads below are broadcasts
+    float acc[48];
+#pragma unroll
+    for (int m = 0; m < 48; ++m) acc[m] = 0.f;
+    for (int i0 = blockIdx.x * C3B_TP; i0 < n; i0 += gridDim.x * C3B_TP) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < C3B_TP * C3_G; k += blockDim.x) {
+            const int r = k / C3_G;
+            sG[k] = i0 + r < n ? __ldg(dG + (size_t)i0 * C3_G + k) : 0.f;
+        }
+        for (int k = threadIdx.x; k < C3B_TP * C3_IN; k += blockDim.x) {
+            const int r = k >> 6;
+            float v = 0.f;
+            if (i0 + r < n) {
+                if (xbf16) v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x2)[(size_t)i0 * C3_IN + k]);
+                else v = __half2float(reinterpret_cast<const __half*>(x2)[(size_t)i0 * C3_IN + k]);
+            }
+            sX[k] = v;
+        }
+        if (threadIdx.x < C3B_TP * 4) {
+            const int r = threadIdx.x >> 2, o = threadIdx.x & 3;
+            sg3[threadIdx.x] = (o < 3 && i0 + r < n) ? __ldg(g3 + (size_t)(i0 + r) * 3 + o) : 0.f;
+        }
+        __syncthreads();
+        {   // feature gradient of particles grp*4 .. grp*4+3, channel ch
+            float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+            const float* g0 = sG + (grp * 4) * C3_G;
+#pragma unroll 8
+            for (int q = 0; q < C3_G; ++q) {
+                const float w = sK[q * C3_IN + ch];
+                d0 += w * g0[q]; d1 += w * g0[C3_G + q]; d2 += w * g0[2 * C3_G + q]; d3 += w * g0[3 * C3_G + q];
+            }
+            const float d[4] = {d0, d1, d2, d3};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = grp * 4 + u, i = i0 + r;
+                if (i < n) {
+                    float v = d[u] + sg3[r * 4] * sW[ch] + sg3[r * 4 + 1] * sW[C3_IN + ch] + sg3[r * 4 + 2] * sW[2 * C3_IN + ch];
+                    if (!(__ldg(ans2 + (size_t)i * C3_IN + ch) > 0.f)) v = 0.f;
+                    g_ans2[(size_t)i * C3_IN + ch] = v;
+                    g_ans2_h[(size_t)i * C3_IN + ch] = __float2bfloat16(v);
+                }
+            }
+        }
+        // filter gradient: this thread owns q = grp*48 .. +47 of channel ch
+#pragma unroll 2
+        for (int r = 0; r < C3B_TP; ++r) {
+            const float x = sX[r * C3_IN + ch];
+            const float4* gq = reinterpret_cast<const float4*>(sG + r * C3_G + grp * 48);
+#pragma unroll
+            for (int m = 0; m < 12; ++m) {
+                const float4 gv = gq[m];
+                acc[4 * m] += x * gv.x; acc[4 * m + 1] += x * gv.y; acc[4 * m + 2] += x * gv.z; acc[4 * m + 3] += x * gv.w;
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < 48; ++m) {
+        const int q = grp * 48 + m;
+        if (acc[m] != 0.f) atomicAdd(dK + ((size_t)(q / 3) * C3_IN + ch) * 3 + q % 3, acc[m]);
+    }
+}
+
+// ---- layer 0 backward, filter side: dK0_fluid (64,4,32) = sum_i patch_f(i) (x) g_i[32:64], dK0_obstacle (64,3,32) likewise
+// with g_i[0:32]; the two conv biases, dense0's weight (32,4) and bias ride along.  A warp rebuilds one particle's two
+// patches as k_layer0 does (8 particles per pass), then all 256 threads add the pass into register accumulators.
+struct L0WgradArgs {
+    const Pair* pairs_ff; const int* cnt_ff;
+    const Pair* pairs_fb; const int* cnt_fb;      // NULL without a container
+    const float* vel_new; const float* box_normals;
+    const float* g;                               // (N,96): d ans0 = [obstacle, fluid, dense]
+    int n;
+    float *dKf, *dbf, *dKo, *dbo, *dWd, *dbd;
+    const float4* order;
+};
+__global__ void __launch_bounds__(256) k_layer0_wgrad(const L0WgradArgs a) {
+    __shared__ __align__(16) float sm_patch[8][NCELL * 4 + NCELL * 3];
+    __shared__ float sgr[8][96];
+    __shared__ float sff[8][4];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    float accf[32], acco[24];
+#pragma unroll
+    for (int m = 0; m < 32; ++m) accf[m] = 0.f;
+#pragma unroll
+    for (int m = 0; m < 24; ++m) acco[m] = 0.f;
+    float accb = 0.f, accd = 0.f;
+    for (int p0 = blockIdx.x * 8; p0 < a.n; p0 += gridDim.x * 8) {
+        __syncthreads();
+        const int pos_i = p0 + wib;
+        float* pf = sm_patch[wib];
+        float* po = pf + NCELL * 4;
+        for (int k = lane; k < NCELL * 7; k += 32) pf[k] = 0.f;
+        __syncwarp();
+        if (pos_i < a.n) {
+            const int i = a.order ? __float_as_int(__ldg(&a.order[pos_i].w)) : pos_i;
+            {
+                const int m = a.cnt_ff[i];
+                const Pair* pr = a.pairs_ff + (size_t)i * MAXNBR;
+                for (int t = lane; t < m; t += 32) {
+                    const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(pr + t));
+                    const float4 w0 = __ldg(reinterpret_cast<const float4*>(pr + t) + 1);
+                    const float4 w1 = __ldg(reinterpret_cast<const float4*>(pr + t) + 2);
+                    const int j = (int)h0.x;
+                    const float f[4] = {1.0f, __ldg(a.vel_new + 3 * j), __ldg(a.vel_new + 3 * j + 1), __ldg(a.vel_new + 3 * j + 2)};
+                    const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const unsigned cell = ((c < 4 ? h0.y : h0.z) >> (8 * (c & 3))) & 0xffu;
+#pragma unroll
+                        for (int ch = 0; ch < 4; ++ch) atomicAdd(pf + cell * 4 + ch, w[c] * f[ch]);
+                    }
+                }
+            }
+            if (a.cnt_fb) {
+                const int m = a.cnt_fb[i];
+                const Pair* pr = a.pairs_fb + (size_t)i * MAXNBR;
+                for (int t = lane; t < m; t += 32) {
+                    const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(pr + t));
+                    const float4 w0 = __ldg(reinterpret_cast<const float4*>(pr + t) + 1);
+                    const float4 w1 = __ldg(reinterpret_cast<const float4*>(pr + t) + 2);
+                    const int j = (int)h0.x;
+                    const float f[3] = {__ldg(a.box_normals + 3 * j), __ldg(a.box_normals + 3 * j + 1), __ldg(a.box_normals + 3 * j + 2)};
+                    const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const unsigned cell = ((c < 4 ? h0.y : h0.z) >> (8 * (c & 3))) & 0xffu;
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) atomicAdd(po + cell * 3 + ch, w[c] * f[ch]);
+                    }
+                }
+            }
+            for (int k = lane; k < 96; k += 32) sgr[wib][k] = __ldg(a.g + (size_t)i * 96 + k);
+            if (lane < 4) sff[wib][lane] = lane == 0 ? 1.0f : __ldg(a.vel_new + 3 * i + lane - 1);
+        } else {
+            for (int k = lane; k < 96; k += 32) sgr[wib][k] = 0.f;
+            if (lane < 4) sff[wib][lane] = 0.f;
+        }
+        __syncthreads();
+        // thread (o = lane, grp = wib) owns patch rows grp*32.. of the fluid filter and grp*24.. of the obstacle filter
+#pragma unroll 1
+        for (int r = 0; r < 8; ++r) {
+            const float go = sgr[r][lane], gf = sgr[r][32 + lane];
+            const float4* qf = reinterpret_cast<const float4*>(sm_patch[r] + wib * 32);
+            const float4* qo = reinterpret_cast<const float4*>(sm_patch[r] + NCELL * 4 + wib * 24);
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const float4 v = qf[m];
+                accf[4 * m] += v.x * gf; accf[4 * m + 1] += v.y * gf; accf[4 * m + 2] += v.z * gf; accf[4 * m + 3] += v.w * gf;
+            }
+#pragma unroll
+            for (int m = 0; m < 6; ++m) {
+                const float4 v = qo[m];
+                acco[4 * m] += v.x * go; acco[4 * m + 1] += v.y * go; acco[4 * m + 2] += v.z * go; acco[4 * m + 3] += v.w * go;
+            }
+            if (wib < 3) accb += sgr[r][wib * 32 + lane];                  // bias sums: obstacle, fluid, dense
+            else if (wib < 7) accd += sgr[r][64 + lane] * sff[r][wib - 3];  // dense0 weight column wib - 3
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < 32; ++m)
+        if (accf[m] != 0.f) atomicAdd(a.dKf + (size_t)(wib * 32 + m) * 32 + lane, accf[m]);
+    if (a.cnt_fb) {
+#pragma unroll
+        for (int m = 0; m < 24; ++m)
+            if (acco[m] != 0.f) atomicAdd(a.dKo + (size_t)(wib * 24 + m) * 32 + lane, acco[m]);
+    }
+    if (wib == 0) { if (accb != 0.f) atomicAdd(a.dbo + lane, accb); }
+    else if (wib == 1) { if (accb != 0.f) atomicAdd(a.dbf + lane, accb); }
+    else if (wib == 2) { if (accb != 0.f) atomicAdd(a.dbd + lane, accb); }
+    else if (wib < 7) { if (accd != 0.f) atomicAdd(a.dWd + lane * 4 + (wib - 3), accd); }
+}
+
+// ---- layer 0 backward, feature side (32 -> 4 through the mirrored, transposed fluid filter): the same project + gather
+// split as conv3's forward.  H_i[c][ch] = sum_o K'[c][o][ch] g_i[o];  d ff_j = sum over j's list of w_jic H_i[c].
+constexpr int L0B_IN = 32, L0B_G = NCELL * 4;
+__global__ void __launch_bounds__(L0B_G) k_layer0_bwd_project(const float* __restrict__ g /*(N,96): columns 32..63*/, int n,
+                                                              const float* __restrict__ kt /*(64,32,4)*/, float* __restrict__ H /*(N,256)*/) {
+    __shared__ float sk[L0B_IN * L0B_G];              // [o][cell*4 + ch]
+    __shared__ float4 sx[L0B_IN];
+    for (int k = threadIdx.x; k < L0B_IN * L0B_G; k += blockDim.x) {
+        const int ch = k & 3, o = (k >> 2) % L0B_IN, cell = k / (4 * L0B_IN);
+        sk[o * L0B_G + cell * 4 + ch] = __ldg(kt + k);
+    }
+    const int q = threadIdx.x;
+    for (int i0 = blockIdx.x * 4; i0 < n; i0 += gridDim.x * 4) {
+        __syncthreads();
+        if (threadIdx.x < 4 * L0B_IN) {
+            const int ii = i0 + (threadIdx.x & 3), o = threadIdx.x >> 2;
+            reinterpret_cast<float*>(sx)[threadIdx.x] = ii < n ? __ldg(g + (size_t)ii * 96 + 32 + o) : 0.f;
+        }
+        __syncthreads();
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+        for (int o = 0; o < L0B_IN; ++o) {
+            const float w = sk[o * L0B_G + q];
+            const float4 x = sx[o];
+            a0 += w * x.x; a1 += w * x.y; a2 += w * x.z; a3 += w * x.w;
+        }
+        if (i0 < n) H[(size_t)i0 * L0B_G + q] = a0;
+        if (i0 + 1 < n) H[(size_t)(i0 + 1) * L0B_G + q] = a1;
+        if (i0 + 2 < n) H[(size_t)(i0 + 2) * L0B_G + q] = a2;
+        if (i0 + 3 < n) H[(size_t)(i0 + 3) * L0B_G + q] = a3;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_layer0_bwd_gather(const Pair* __restrict__ pairs, const int* __restrict__ cnt,
+                                                           const float* __restrict__ H, int n, float* __restrict__ out /*(N,4)*/,
+                                                           const float4* __restrict__ order) {
+    const int lane = threadIdx.x & 31;
+    const int pos_j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (pos_j >= n) return;
+    const int j = order ? __float_as_int(__ldg(&order[pos_j].w)) : pos_j;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int m = cnt[j];
+    const Pair* pr = pairs + (size_t)j * MAXNBR;
+    for (int t = lane; t < m; t += 32) {
+        const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(pr + t));
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(pr + t) + 1);
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(pr + t) + 2);
+        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const float4* hi = reinterpret_cast<const float4*>(H + (size_t)h0.x * L0B_G);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const unsigned cell = ((c < 4 ? h0.y : h0.z) >> (8 * (c & 3))) & 0xffu;
+            const float4 v = __ldg(hi + cell);
+            acc.x += w[c] * v.x; acc.y += w[c] * v.y; acc.z += w[c] * v.z; acc.w += w[c] * v.w;
+        }
+    }
+    acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z); acc.w = warp_sum(acc.w);
+    if (lane == 0) *reinterpret_cast<float4*>(out + (size_t)j * 4) = acc;
 }
 
 // dW (cout, cin) += g^T x over all particles; db (cout) += column sums of g (optional, may alias a second target)
@@ -1395,13 +1656,11 @@ __global__ void k_flip_transpose(const float* __restrict__ K, int cin, int cout,
 }
 
 // start of the backward pass: gpt = g_pos_out + g_vel_out / dt;  g_ans3 = gpt / 128;  d_pos = g_pos_out;  d_vel = dt * gpt
-// (+ the feature path, added by k_bwd_tail);  ff = [1, vel_new]
+// (+ the feature path, added by k_bwd_tail)
 __global__ void k_bwd_head(const float* __restrict__ g_pos_out, const float* __restrict__ g_vel_out, const float* __restrict__ vel_new,
-                           int n, float dt, float* __restrict__ g_ans3, float* __restrict__ d_pos, float* __restrict__ d_vel,
-                           float* __restrict__ ff) {
+                           int n, float dt, float* __restrict__ g_ans3, float* __restrict__ d_pos, float* __restrict__ d_vel) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    ff[4 * i] = 1.f;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         const float gp = g_pos_out ? g_pos_out[3 * i + a] : 0.f, gv = g_vel_out ? g_vel_out[3 * i + a] : 0.f;
@@ -1409,20 +1668,7 @@ __global__ void k_bwd_head(const float* __restrict__ g_pos_out, const float* __r
         g_ans3[3 * i + a] = gpt * (1.0f / 128);
         d_pos[3 * i + a] = gp;
         d_vel[3 * i + a] = dt * gpt;
-        ff[4 * i + 1 + a] = vel_new[3 * i + a];
     }
-}
-
-// g_ans2 = (conv3^T(g_ans3) + g_ans3 Wd3) * (ans2 > 0)  -> fp32 + bf16
-__global__ void k_bwd_l3_finish(const float* __restrict__ t2, const float* __restrict__ g_ans3, const float* __restrict__ wd3 /*(3,64)*/,
-                                const float* __restrict__ ans2, int n, float* __restrict__ g_ans2, __nv_bfloat16* __restrict__ g_ans2_h) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n * 64) return;
-    const int i = t >> 6, c = t & 63;
-    float v = t2[t] + g_ans3[3 * i] * wd3[c] + g_ans3[3 * i + 1] * wd3[64 + c] + g_ans3[3 * i + 2] * wd3[128 + c];
-    if (!(ans2[t] > 0.f)) v = 0.f;
-    g_ans2[t] = v;
-    g_ans2_h[t] = __float2bfloat16(v);
 }
 
 // d_vel += conv0_fluid^T(g)[1:4] + (g_ans0[:, 64:96] Wd0)[1:4]     (fluid features are [1, vel_new]; vel_new = vel + g dt)
@@ -1439,7 +1685,7 @@ __global__ void k_bwd_tail(const float* __restrict__ g_ffc /*(N,4)*/, const floa
 }
 
 struct BwdPackLayout {
-    size_t scratch_k, scratch_w, l1, l2, k3t, k0ft, total;
+    size_t scratch_k, scratch_w, l1, l2, k0ft, total;
 };
 inline BwdPackLayout bwd_pack_layout() {
     BwdPackLayout L;
@@ -1449,25 +1695,24 @@ inline BwdPackLayout bwd_pack_layout() {
     L.scratch_w = take((size_t)96 * 64 * 4);
     L.l1 = take(ConvCfg<64, 96>::PACKED_BYTES);
     L.l2 = take(ConvCfg<64, 64>::PACKED_BYTES);
-    L.k3t = take((size_t)NCELL * 3 * 64 * 4);
     L.k0ft = take((size_t)NCELL * 32 * 4 * 4);
     L.total = o;
     return L;
 }
 
 struct BwdWsLayout {
-    size_t g_ans3, t2, g_ans2, g_ans2_h, g_ans1, g_ans1_h, g_ans0, ff, g_ffc, total;
+    size_t g_ans3, h0, g_ans2, g_ans2_h, g_ans1, g_ans1_h, g_ans0, g_ffc, total;
 };
 inline BwdWsLayout bwd_ws_layout(int n) {
     BwdWsLayout L;
     size_t o = 0;
     auto take = [&](size_t b) { size_t r = o; o += align_up(b, 256); return r; };
     const size_t N = (size_t)(n > 0 ? n : 1);
-    L.g_ans3 = take(N * 3 * 4); L.t2 = take(N * 64 * 4);
+    L.g_ans3 = take(N * 3 * 4); L.h0 = take(N * L0B_G * 4);
     L.g_ans2 = take(N * 64 * 4); L.g_ans2_h = take(N * 64 * 2);
     L.g_ans1 = take(N * 64 * 4); L.g_ans1_h = take(N * 64 * 2);
     L.g_ans0 = take(N * 96 * 4);
-    L.ff = take(N * 4 * 4); L.g_ffc = take(N * 4 * 4);
+    L.g_ffc = take(N * 4 * 4);
     L.total = o;
     return L;
 }
@@ -1506,15 +1751,6 @@ static int launch_small(const Pair* pairs, const int* cnt, const void* in_feat, 
     const size_t smem = (size_t)NCELL * cin * cout * 4 + (size_t)8 * NCELL * cin * 4;
     NF_CUDA_OK(cudaFuncSetAttribute(k_cconv_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_cconv_small<<<min((n_out + 7) / 8, 2 * num_sms()), 256, smem, st>>>(pairs, cnt, in_feat, ld_in, kind, cin, cout, kern, nullptr, n_out, out);
-    NF_LAUNCH_OK();
-    return NF_OK;
-}
-
-static int launch_small_wgrad(const Pair* pairs, const int* cnt, const void* in_feat, int ld_in, int kind, int cin, int cout, const float* g,
-                              int ld_g, int n_out, float* dK, cudaStream_t st) {
-    const size_t smem = (size_t)NCELL * cin * cout * 4 + (size_t)8 * NCELL * cin * 4;
-    NF_CUDA_OK(cudaFuncSetAttribute(k_cconv_small_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_cconv_small_wgrad<<<min((n_out + 7) / 8, num_sms()), 256, smem, st>>>(pairs, cnt, in_feat, ld_in, kind, cin, cout, g, ld_g, n_out, dK);
     NF_LAUNCH_OK();
     return NF_OK;
 }
@@ -1714,8 +1950,6 @@ extern "C" int nf_transition_pack_weights_bwd(const float* const* p, void* packe
         k_pack_conv<64, 64, true><<<(tot + 255) / 256, 256, 0, st>>>(sk, nullptr, sw, nullptr, 64, b + L.l2);
         NF_LAUNCH_OK();
     }
-    k_flip_transpose<<<(NCELL * 64 * 3 + 255) / 256, 256, 0, st>>>(p[14], 64, 3, (float*)(b + L.k3t), nullptr, nullptr);
-    NF_LAUNCH_OK();
     k_flip_transpose<<<(NCELL * 4 * 32 + 255) / 256, 256, 0, st>>>(p[0], 4, 32, (float*)(b + L.k0ft), nullptr, nullptr);
     NF_LAUNCH_OK();
     return NF_OK;
@@ -1747,25 +1981,29 @@ extern "C" int nf_transition_backward(const nf_transition_bwd_args* b, void* str
     const float* ans0 = (const float*)(ws + L.ans0); const void* x0 = ws + L.x0;
     const float* ans1 = (const float*)(ws + L.ans1); const void* x1 = ws + L.x1;
     const float* ans2 = (const float*)(ws + L.ans2); const void* x2 = ws + L.x2;
-    float* g_ans3 = (float*)(bw + B.g_ans3); float* t2 = (float*)(bw + B.t2);
+    float* g_ans3 = (float*)(bw + B.g_ans3);
     float* g_ans2 = (float*)(bw + B.g_ans2); __nv_bfloat16* g_ans2_h = (__nv_bfloat16*)(bw + B.g_ans2_h);
     float* g_ans1 = (float*)(bw + B.g_ans1); void* g_ans1_h = bw + B.g_ans1_h;
     float* g_ans0 = (float*)(bw + B.g_ans0);
-    float* ff = (float*)(bw + B.ff); float* g_ffc = (float*)(bw + B.g_ffc);
+    float* g_ffc = (float*)(bw + B.g_ffc);
     const bool xbf = a->dtype == NF_DTYPE_BF16;
     const int xkind = xbf ? 2 : 1;
     const int ntiles = (N + 127) / 128;
     const int nsplit = ntiles < 8 ? ntiles : 8;
     int rc;
 
-    k_bwd_head<<<(N + 255) / 256, 256, 0, st>>>(b->g_pos_out, b->g_vel_out, vel_new, N, a->dt, g_ans3, b->d_pos, b->d_vel, ff);
+    k_bwd_head<<<(N + 255) / 256, 256, 0, st>>>(b->g_pos_out, b->g_vel_out, vel_new, N, a->dt, g_ans3, b->d_pos, b->d_vel);
     NF_LAUNCH_OK();
     // ---- layer 3: ans3 = conv3(x2) + dense3(x2)
-    if ((rc = launch_small_wgrad(pairs_ff, cnt_ff, x2, 64, xkind, 64, 3, g_ans3, 3, N, dP + PO.off[14], st)) != NF_OK) return rc;
-    if ((rc = launch_dense_wgrad(g_ans3, 3, 3, x2, 64, xkind, 64, N, dP + PO.off[16], dP + PO.off[15], dP + PO.off[17], st)) != NF_OK) return rc;
-    if ((rc = launch_small(pairs_ff, cnt_ff, g_ans3, 3, 0, 3, 64, (const float*)(wb + BL.k3t), N, t2, st)) != NF_OK) return rc;
-    k_bwd_l3_finish<<<(N * 64 + 255) / 256, 256, 0, st>>>(t2, g_ans3, (const float*)(w + PL.w_dense3), ans2, N, g_ans2, g_ans2_h);
+    const float4* order = grid_view(ws + L.grid_f, N).sorted;     // the forward's fluid grid is still in its workspace
+    float* dG = (float*)(ws + L.g3);                              // the forward's projection buffer is free again
+    k_conv3_bwd_scatter<<<(N + 7) / 8, 256, 0, st>>>(pairs_ff, cnt_ff, g_ans3, N, dG, order);
     NF_LAUNCH_OK();
+    NF_CUDA_OK(cudaFuncSetAttribute(k_conv3_bwd_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, C3B_SMEM));
+    k_conv3_bwd_dense<<<min((N + C3B_TP - 1) / C3B_TP, num_sms()), 256, C3B_SMEM, st>>>(
+        dG, x2, xbf ? 1 : 0, (const float*)(w + PL.k3), (const float*)(w + PL.w_dense3), g_ans3, ans2, N, g_ans2, g_ans2_h, dP + PO.off[14]);
+    NF_LAUNCH_OK();
+    if ((rc = launch_dense_wgrad(g_ans3, 3, 3, x2, 64, xkind, 64, N, dP + PO.off[16], dP + PO.off[15], dP + PO.off[17], st)) != NF_OK) return rc;
     // ---- layer 2: ans2 = conv2(x1) + dense2(x1) + ans1
     CWgradArgs wg;
     wg.slab_j = (const int*)(ws + L.slab_j); wg.slab_w = (const float4*)(ws + L.slab_w); wg.slab_off = (const unsigned short*)(ws + L.slab_off);
@@ -1775,7 +2013,7 @@ extern "C" int nf_transition_backward(const nf_transition_bwd_args* b, void* str
     if ((rc = launch_dense_wgrad(g_ans2, 64, 64, x1, 64, xkind, 0, N, dP /*unused: cin = 0*/, dP + PO.off[11], dP + PO.off[13], st)) != NF_OK) return rc;
     ConvArgs c;
     c.slab_j = wg.slab_j; c.slab_w = wg.slab_w; c.slab_off = wg.slab_off; c.n = N; c.begin = 0; c.end = N; c.dense = 1; c.relu_out = 0;
-    c.order = grid_view(ws + L.grid_f, N).sorted;     // the forward's fluid grid is still in its workspace
+    c.order = order;
     c.x_in = g_ans2_h; c.w_packed = wb + BL.l2; c.residual = g_ans2; c.ld_res = 64; c.ans = g_ans1; c.x_out = g_ans1_h; c.cout = 64;
     c.mask_src = ans1; c.ld_mask = 64;
     if ((rc = launch_conv<64, 64>(c, NF_DTYPE_BF16, st)) != NF_OK) return rc;
@@ -1787,13 +2025,18 @@ extern "C" int nf_transition_backward(const nf_transition_bwd_args* b, void* str
     c.mask_src = ans0; c.ld_mask = 96;
     if ((rc = launch_conv<64, 96>(c, NF_DTYPE_BF16, st)) != NF_OK) return rc;
     // ---- layer 0: ans0 = [conv0_obstacle(box normals), conv0_fluid([1, vel']), dense0([1, vel'])]
-    if (M > 0)
-        if ((rc = launch_small_wgrad(pairs_fb, cnt_fb, a->box_normals, 3, 0, 3, 32, g_ans0, 96, N, dP + PO.off[2], st)) != NF_OK) return rc;
-    if ((rc = launch_small_wgrad(pairs_ff, cnt_ff, ff, 4, 0, 4, 32, g_ans0 + 32, 96, N, dP + PO.off[0], st)) != NF_OK) return rc;
-    if ((rc = launch_dense_wgrad(g_ans0, 96, 32, ff, 4, 0, 0, N, dP, dP + PO.off[3], nullptr, st)) != NF_OK) return rc;        // db conv0_obstacle
-    if ((rc = launch_dense_wgrad(g_ans0 + 32, 96, 32, ff, 4, 0, 0, N, dP, dP + PO.off[1], nullptr, st)) != NF_OK) return rc;   // db conv0_fluid
-    if ((rc = launch_dense_wgrad(g_ans0 + 64, 96, 32, ff, 4, 0, 4, N, dP + PO.off[4], dP + PO.off[5], nullptr, st)) != NF_OK) return rc;   // dense0
-    if ((rc = launch_small(pairs_ff, cnt_ff, g_ans0 + 32, 96, 0, 32, 4, (const float*)(wb + BL.k0ft), N, g_ffc, st)) != NF_OK) return rc;
+    L0WgradArgs l0;
+    l0.pairs_ff = pairs_ff; l0.cnt_ff = cnt_ff; l0.pairs_fb = M > 0 ? pairs_fb : nullptr; l0.cnt_fb = M > 0 ? cnt_fb : nullptr;
+    l0.vel_new = vel_new; l0.box_normals = a->box_normals; l0.g = g_ans0; l0.n = N; l0.order = order;
+    l0.dKf = dP + PO.off[0]; l0.dbf = dP + PO.off[1]; l0.dKo = dP + PO.off[2]; l0.dbo = dP + PO.off[3];
+    l0.dWd = dP + PO.off[4]; l0.dbd = dP + PO.off[5];
+    k_layer0_wgrad<<<min((N + 7) / 8, 2 * num_sms()), 256, 0, st>>>(l0);
+    NF_LAUNCH_OK();
+    float* h0 = (float*)(bw + B.h0);
+    k_layer0_bwd_project<<<min((N + 3) / 4, 2 * num_sms()), L0B_G, 0, st>>>(g_ans0, N, (const float*)(wb + BL.k0ft), h0);
+    NF_LAUNCH_OK();
+    k_layer0_bwd_gather<<<(N + 7) / 8, 256, 0, st>>>(pairs_ff, cnt_ff, h0, N, g_ffc, order);
+    NF_LAUNCH_OK();
     k_bwd_tail<<<(N + 255) / 256, 256, 0, st>>>(g_ffc, g_ans0, (const float*)(w + PL.w_dense0), N, b->d_vel);
     NF_LAUNCH_OK();
     return NF_OK;

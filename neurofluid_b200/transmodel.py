@@ -228,7 +228,9 @@ class ParticleNet(nn.Module):
         self.num_fluid_neighbors, self.pos_correction = outs[2], outs[3]
         self._keep = (pos, vel, box, box_feats)
         if train:
-            return (outs[0], outs[1], outs[2]), dict(args=a, ws=ws, keep=(pos, vel, box, box_feats, outs, self._packed_weights(),
+            # the outputs themselves stay out of `keep`: they become the autograd node's outputs, and a node that holds
+            # its own outputs is a reference cycle through C++ that frees this step's workspace only at a gc pass
+            return (outs[0], outs[1], outs[2]), dict(args=a, ws=ws, keep=(pos, vel, box, box_feats, self._packed_weights(),
                                                                            self._box_grid(box)), n=pos.shape[0])
         return outs[0], outs[1], outs[2]
 

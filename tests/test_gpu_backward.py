@@ -319,3 +319,33 @@ def test_end2end_train_step_like_trainer_e2e(dev):
     assert abs(float(lc) - float(lr)) < 1e-4 * abs(float(lr))
     for k, p in tn2.named_parameters():
         assert rel_l2(p.grad.cpu(), sdg[k].grad) < 2 * GRAD_TOL, (k, rel_l2(p.grad.cpu(), sdg[k].grad))
+
+
+def test_training_steps_release_their_workspaces(dev):
+    """Every training forward owns a workspace (hundreds of MB at scene size) that must die with its graph, by reference
+    counting: with the garbage collector switched off the allocated memory may not grow from step to step."""
+    import gc
+    sd, pos, vel, box, box_n, rng = _transition_case()
+    tn = nb.ParticleNet(gravity=(0.0, 0.0, -9.81)); tn.load_state_dict(sd); tn = tn.to(dev)
+    rn = nb.RenderNet(scenes.render_cfg(), scenes.NEAR, scenes.FAR); rn.load_state_dict(scenes.init_render_state(0, 5.0)); rn = rn.to(dev)
+    rays, focal, cw = scenes.camera_rays(40, 40)
+    rays = scenes.center_crop_rays(rays, 40, 40, 12).to(dev)
+    args = [t.to(dev) for t in (pos - torch.tensor([0.1, -0.2, -0.7]), vel, box, box_n)]
+    gc.collect()
+    gc.disable()
+    try:
+        seen = []
+        for it in range(6):
+            with torch.enable_grad():
+                pp, vv, _ = tn(*args)
+                r = rn(pp, cw[:, 3].to(dev), rays, focal, cw.to(dev))
+                loss = (r["rgb1"] ** 2).mean() + (r["rgb0"] ** 2).mean() + (vv ** 2).mean()
+                for p in list(tn.parameters()) + list(rn.parameters()):
+                    p.grad = None
+                loss.backward()
+            del pp, vv, r, loss
+            torch.cuda.synchronize()
+            seen.append(torch.cuda.memory_allocated(dev))
+    finally:
+        gc.enable()
+    assert max(seen[3:]) <= max(seen[1:3]), seen      # (caches alternate between two sizes; growth is the failure)
