@@ -102,9 +102,13 @@ NF_API int nf_render_pack_weights_ex(const float* const* params_host, int dtype,
  *           + NeRF.forward (models/nerf.py:83-124)
  * records (n_rows,16) fp32: [x(3), density, smoothed(3), variance(3), ray_dir(3), smoothed_dir(3)]
  * out (n_rows,4) fp32: [r,g,b,sigma]   (sigma_only != 0: [0,0,0,sigma], layers after sigma skipped)
+ * workspace: nf_nerf_mlp_workspace_bytes() of device memory, 256-byte aligned (per-CTA staging of the encoded features
+ *            between the warps that compute them and the bulk copies that feed them to the tensor cores; a constant ~45 MB,
+ *            independent of n_rows; nf_render_forward carves the same region out of its own workspace)
  * ------------------------------------------------------------------------------------------- */
+NF_API size_t nf_nerf_mlp_workspace_bytes(void);
 NF_API int nf_nerf_mlp_forward(const void* packed_weights, int dtype, const float* records, int n_rows, int sigma_only,
-                        float* out, void* stream);
+                        float* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Whole renderer forward over one chunk of rays

@@ -97,7 +97,8 @@ SIGNATURES = {
     "nf_render_packed_weights_bytes": (_sz, []),
     "nf_render_pack_weights": (C.c_int, [C.POINTER(_vp), C.c_int, _vp, _vp]),
     "nf_render_pack_weights_ex": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, _vp, _vp]),
-    "nf_nerf_mlp_forward": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, _vp, _vp]),
+    "nf_nerf_mlp_workspace_bytes": (C.c_size_t, []),
+    "nf_nerf_mlp_forward": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, _vp, _vp, C.c_size_t, _vp]),
     "nf_render_workspace_bytes": (_sz, [C.c_int, C.c_int, C.c_int]),
     "nf_render_workspace_bytes_ex": (_sz, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "nf_render_workspace_view": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(RenderWsView)]),

@@ -1127,6 +1127,7 @@ struct CWgradArgs {
     const void* x_in;      // (N, CIN) layer input, forward operand dtype
     const void* g;         // (N, 64) bf16: gradient w.r.t. the layer's pre-activation
     int n, ntiles, nsplit;
+    const float4* order;   // NULL or the fluid grid's cell-sorted copy (.w = particle index): tiles in cell order
     float* dK;             // (64 cells, CIN, 64) accumulated
     float* dWd;            // (64, CIN) accumulated (nn.Linear layout)
 };
@@ -1180,21 +1181,45 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_cconv_wgrad(const CWgradArg
             }
         }
     } else {
+        // patch slab of filter row s for the tile's 128 particles: the forward kernel's worker loop (k_cconv_tc): NG particles
+        // per warp at a time, GL lanes per particle, CPL channels per lane, EB entries per iteration with the next iteration's
+        // {j, w} already in flight
+        constexpr int GL = (CIN == 64) ? 8 : 16;
+        constexpr int CPL = CIN / GL;
+        constexpr int NG = 32 / GL;
         const int rbase = warp * ROWS_PER_WARP;
-        constexpr bool THIRD = (CIN == 96);
-        const uint32_t* xin32 = reinterpret_cast<const uint32_t*>(a.x_in);
-        const unsigned short* xin16 = reinterpret_cast<const unsigned short*>(a.x_in);
+        const int gq = lane / GL, cl = lane % GL;
+        const uint8_t* xin = reinterpret_cast<const uint8_t*>(a.x_in);
         auto cvt2 = [](uint32_t v, float& lo, float& hi) {
             if (XBF16) { lo = __uint_as_float(v << 16); hi = __uint_as_float(v & 0xffff0000u); }
             else { const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&v)); lo = t.x; hi = t.y; }
         };
-        auto cvt1 = [](unsigned short v) {
-            if (XBF16) return __uint_as_float((uint32_t)v << 16);
-            return __half2float(*reinterpret_cast<const __half*>(&v));
-        };
         auto packb = [](float lo, float hi) -> uint32_t {
             __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
             return *reinterpret_cast<uint32_t*>(&h);
+        };
+        auto load_feat = [&](int j, uint32_t (&f)[CPL / 2]) {
+            const uint8_t* p = xin + (size_t)j * (CIN * 2) + cl * (CPL * 2);
+            if constexpr (CPL == 8) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+                f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < CPL / 2; ++i) f[i] = __ldg(reinterpret_cast<const uint32_t*>(p) + i);
+            }
+        };
+        auto fma_feat = [&](const float4& w, const uint32_t (&f)[CPL / 2], float (&acc)[4][CPL]) {
+#pragma unroll
+            for (int i = 0; i < CPL / 2; ++i) {
+                float f0, f1;
+                cvt2(f[i], f0, f1);
+                acc[0][2 * i] += w.x * f0; acc[1][2 * i] += w.y * f0; acc[2][2 * i] += w.z * f0; acc[3][2 * i] += w.w * f0;
+                acc[0][2 * i + 1] += w.x * f1; acc[1][2 * i + 1] += w.y * f1; acc[2][2 * i + 1] += w.z * f1; acc[3][2 * i + 1] += w.w * f1;
+            }
+        };
+        auto particle_of = [&](int tpos) -> int {      // tile position -> particle (cell order when the forward's grid is passed)
+            if (tpos >= a.n) return -1;
+            return a.order ? __float_as_int(__ldg(&a.order[tpos].w)) : tpos;
         };
         for (int it = 0; it < my_tiles; ++it) {
             const int row0 = (split + it * a.nsplit) * 128;
@@ -1202,75 +1227,75 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_cconv_wgrad(const CWgradArg
             // gradient tile: (row, 8-column group) pieces of 16 bytes, row-major in HBM -> tile image
             for (int p = threadIdx.x; p < 128 * 8; p += WORKER_WARPS * 32) {
                 const int r = p >> 3, q = p & 7;
+                const int row = particle_of(row0 + r);
                 uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                if (row0 + r < a.n) v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(a.g) + (size_t)(row0 + r) * 128 + q * 16);
+                if (row >= 0) v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(a.g) + (size_t)row * 128 + q * 16);
                 *reinterpret_cast<uint4*>(smem + C::SM_G + q * 2048 + r * 16) = v;
             }
 #pragma unroll 1
-            for (int r = 0; r < ROWS_PER_WARP; ++r) {
-                const int rl = rbase + r, row = row0 + rl;
-                float acc[4][3];
+            for (int R = 0; R < ROWS_PER_WARP / NG; ++R) {
+                const int rl = rbase + R * NG + gq;
+                const int row = particle_of(row0 + rl);
+                float acc[4][CPL];
 #pragma unroll
-                for (int x = 0; x < 4; ++x) acc[x][0] = acc[x][1] = acc[x][2] = 0.f;
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int i = 0; i < CPL; ++i) acc[x][i] = 0.f;
                 if (s < 16) {
-                    int beg = 0, end = 0;
-                    if (row < a.n) {
+                    int beg = 0, n = 0;
+                    if (row >= 0) {
                         beg = __ldg(a.slab_off + (size_t)row * SLABOFF + s);
-                        end = __ldg(a.slab_off + (size_t)row * SLABOFF + s + 1);
+                        n = (int)__ldg(a.slab_off + (size_t)row * SLABOFF + s + 1) - beg;
                     }
-#pragma unroll 1
-                    for (int e0 = beg; e0 < end; e0 += 32) {
-                        int ej = 0;
-                        float4 ew = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (e0 + lane < end) {
-                            ej = __ldg(a.slab_j + (size_t)row * SLABCAP + e0 + lane);
-                            ew = __ldg(a.slab_w + (size_t)row * SLABCAP + e0 + lane);
-                        }
-                        const int cnt = min(32, end - e0);
-#pragma unroll 1
-                        for (int u0 = 0; u0 < cnt; u0 += 8) {
-                            uint32_t fp[8];
-                            unsigned short fs[8];
+                    const int nmax = __reduce_max_sync(NF_FULL, n);
+                    const size_t ebase = (size_t)max(row, 0) * SLABCAP + beg;
+                    constexpr int EB = 4;
+                    int jn[EB];
+                    float4 wn[EB];
+                    auto fetch = [&](int e) {
 #pragma unroll
-                            for (int u = 0; u < 8; ++u) {
-                                const int j = __shfl_sync(NF_FULL, ej, (u0 + u) & 31);
-                                fp[u] = __ldg(xin32 + (((size_t)j * CIN) >> 1) + lane);
-                                if (THIRD) fs[u] = __ldg(xin16 + (size_t)j * CIN + 64 + lane);
-                            }
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) {
-                                const int src = (u0 + u) & 31;
-                                const float wx = __shfl_sync(NF_FULL, ew.x, src), wy = __shfl_sync(NF_FULL, ew.y, src);
-                                const float wz = __shfl_sync(NF_FULL, ew.z, src), ww = __shfl_sync(NF_FULL, ew.w, src);
-                                float f0, f1;
-                                cvt2(fp[u], f0, f1);
-                                acc[0][0] += wx * f0; acc[1][0] += wy * f0; acc[2][0] += wz * f0; acc[3][0] += ww * f0;
-                                acc[0][1] += wx * f1; acc[1][1] += wy * f1; acc[2][1] += wz * f1; acc[3][1] += ww * f1;
-                                if (THIRD) {
-                                    const float f2 = cvt1(fs[u]);
-                                    acc[0][2] += wx * f2; acc[1][2] += wy * f2; acc[2][2] += wz * f2; acc[3][2] += ww * f2;
-                                }
-                            }
+                        for (int u = 0; u < EB; ++u) {
+                            jn[u] = 0; wn[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (e + u < n) { jn[u] = __ldg(a.slab_j + ebase + e + u); wn[u] = __ldg(a.slab_w + ebase + e + u); }
                         }
+                    };
+                    fetch(0);
+#pragma unroll 1
+                    for (int e = 0; e < nmax; e += EB) {
+                        int jc[EB];
+                        float4 wc[EB];
+                        uint32_t f[EB][CPL / 2];
+#pragma unroll
+                        for (int u = 0; u < EB; ++u) { jc[u] = jn[u]; wc[u] = wn[u]; }
+#pragma unroll
+                        for (int u = 0; u < EB; ++u) load_feat(jc[u], f[u]);
+                        fetch(e + EB);
+#pragma unroll
+                        for (int u = 0; u < EB; ++u) fma_feat(wc[u], f[u], acc);
                     }
-                } else if (row < a.n) {
-                    cvt2(__ldg(xin32 + (((size_t)row * CIN) >> 1) + lane), acc[0][0], acc[0][1]);
-                    if (THIRD) acc[0][2] = cvt1(__ldg(xin16 + (size_t)row * CIN + 64 + lane));
+                } else if (row >= 0) {
+                    uint32_t f[CPL / 2];
+                    load_feat(row, f);
+#pragma unroll
+                    for (int i = 0; i < CPL / 2; ++i) cvt2(f[i], acc[0][2 * i], acc[0][2 * i + 1]);
                 }
                 const int nx = (s < 16) ? 4 : 1;
 #pragma unroll
                 for (int x = 0; x < 4; ++x) {
                     if (x < nx) {
-                        {
-                            const int k = x * CIN + 2 * lane;
-                            const uint32_t addr = s_a + (uint32_t)(k >> 3) * 2048 + (uint32_t)rl * 16 + (uint32_t)(k & 7) * 2;
-                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(packb(acc[x][0], acc[x][1])) : "memory");
-                        }
-                        if (THIRD) {
-                            const int k = x * CIN + 64 + lane;
-                            const uint32_t addr = s_a + (uint32_t)(k >> 3) * 2048 + (uint32_t)rl * 16 + (uint32_t)(k & 7) * 2;
-                            const uint32_t bits = packb(acc[x][2], 0.f);
-                            asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)(bits & 0xffffu)) : "memory");
+                        const int k = x * CIN + cl * CPL;
+                        if constexpr (CPL == 8) {
+                            const uint32_t addr = s_a + (uint32_t)(k >> 3) * 2048 + (uint32_t)rl * 16;
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(packb(acc[x][0], acc[x][1])),
+                                         "r"(packb(acc[x][2], acc[x][3])), "r"(packb(acc[x][4], acc[x][5])), "r"(packb(acc[x][6], acc[x][7]))
+                                         : "memory");
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < CPL / 2; ++i) {
+                                const int kk = k + 2 * i;
+                                const uint32_t addr = s_a + (uint32_t)(kk >> 3) * 2048 + (uint32_t)rl * 16 + (uint32_t)(kk & 7) * 2;
+                                asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(packb(acc[x][2 * i], acc[x][2 * i + 1])) : "memory");
+                            }
                         }
                     }
                 }
@@ -2007,7 +2032,7 @@ extern "C" int nf_transition_backward(const nf_transition_bwd_args* b, void* str
     // ---- layer 2: ans2 = conv2(x1) + dense2(x1) + ans1
     CWgradArgs wg;
     wg.slab_j = (const int*)(ws + L.slab_j); wg.slab_w = (const float4*)(ws + L.slab_w); wg.slab_off = (const unsigned short*)(ws + L.slab_off);
-    wg.n = N; wg.ntiles = ntiles; wg.nsplit = nsplit;
+    wg.n = N; wg.ntiles = ntiles; wg.nsplit = nsplit; wg.order = order;
     wg.x_in = x1; wg.g = g_ans2_h; wg.dK = dP + PO.off[10]; wg.dWd = dP + PO.off[12];
     if ((rc = launch_wgrad<64>(wg, xbf, st)) != NF_OK) return rc;
     if ((rc = launch_dense_wgrad(g_ans2, 64, 64, x1, 64, xkind, 0, N, dP /*unused: cin = 0*/, dP + PO.off[11], dP + PO.off[13], st)) != NF_OK) return rc;

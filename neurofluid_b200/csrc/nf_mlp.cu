@@ -1,28 +1,15 @@
-// nf_mlp.cu -- persistent fused positional-encoding + NeRF MLP on tcgen05 tensor cores (sm_100a).
+// nf_mlp.cu -- weight packing and the C entry points of the fused positional-encoding + NeRF MLP; the production kernel is
+// k_nerf_mlp2 (nf_mlp2.cu, two tiles per CTA).
 //
 // replaces: Embedding.forward x6 (models/nerf.py:21-38 via models/renderer.py:125-179) and
 //           NeRF.forward (models/nerf.py:83-124; two instances, models/renderer.py:43-44).
 //
-// Work unit: a tile of 128 compact "geometry records" (16 fp32 per evaluated ray sample, written by
-// the ray-stage kernels in nf_render.cu).  One persistent CTA per SM walks tiles; inside a CTA
-//
-//   warps 6-9  (PE producers, thread = row)  record -> sin/cos features (fp32 math, double-angle
-//              recurrences re-anchored at 2^5) -> fp16/bf16 A-operand tiles written straight into
-//              shared memory in the UMMA K-major core-matrix layout.  The 252-wide feature row never
-//              exists in HBM.
-//   warp 5     (weight producer, one lane)   streams the pre-packed weight K-slabs (8 KB each, already
-//              in UMMA layout) from L2 with cp.async.bulk into a 7-stage mbarrier ring.
-//   warp 4     (MMA issuer, one lane)        issues tcgen05.mma M=128,N=256(128),K=16 per slab; the
-//              fp32 accumulator of layer l lives in TMEM columns [256*(l&1), +256): two buffers, so
-//              layer l+1's MMAs run while layer l's accumulator is being drained.
-//   warps 0-3  (epilogue, thread = row)      tcgen05.ld -> +bias -> ReLU -> fp16 -> back into the
-//              shared-memory activation tile (in place), signalling the MMA warp per 64-column chunk so
-//              the next layer starts before the epilogue ends.  sigma (256->1) and rgb (128->3) heads
-//              are register dot products in the epilogues of layers 8 and 10; (r,g,b,sigma) goes out as
-//              one float4 per row.
-//
-// Per row the tensor pipe does 671,744 MAC (665,984 algorithmic + K padding 198->208, 54->64).
-// HBM traffic per row: 64 B record in, 16 B out (+4 B row id); weights (1.34 MB/net) stay in L2.
+// This file also keeps the round-1/2 ONE-tile-per-CTA kernel k_nerf_mlp, compiled into the tuning build only
+// (-DNF_TUNING, NF_MLP_IMPL=1; NF_MLP_CLUSTER=4 adds its 4-CTA weight-multicast flavour): it is the comparison the
+// two-tile kernel is measured against (tests/gpu_mlp_power.py, profiles/r02_notes.md).  Its layout: 14 warps --
+// 0-7 epilogue (two groups of four, pipelined tcgen05.ld one chunk ahead), 8 MMA issuer (rank 0) / weight relay (rank 1),
+// 9 weight loader (4-stage x 16 KB ring of weight units), 10-13 encoding producers writing the A tiles straight into
+// shared memory; accumulators double-buffered in TMEM by layer parity.
 #include <type_traits>
 
 #include <stdlib.h>
@@ -34,6 +21,7 @@
 namespace nf {
 namespace mlp {
 
+#ifdef NF_TUNING
 // Weight ring: one stage holds one weight UNIT (nf_mlp.cuh): up to 8 consecutive K-steps of one N-HALF of a layer
 // (128 of its 256 output features; 64 of 128 for the dir layer), one CTA's 64 (32) rows of it = 16 KB.  The issuer
 // waits once and commits once per unit, and runs each layer as [half 0, K low] [half 1, K low] [half 0, K high]
@@ -482,6 +470,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp(const KernelArgs a)
     if (warp == W_ISSUE) tmem_dealloc<PAIR>(tmem_base, 512);
 }
 
+#endif  // NF_TUNING (one-tile kernel)
+
 // ------------------------------------------------------------------------------------------------
 // weight packer: fp32 nn.Linear tensors -> K-step slabs in UMMA core-matrix order + fp32 small params
 // slab(step)[kc][n][e]  (kc: 8-column chunk 0/1, n: output row, e: 0..7) = W_layer[n][k_src(step,kc,e)]
@@ -584,6 +574,7 @@ __global__ void k_pack_weights(PackArgs p, uint8_t* out, int enc) {
     }
 }
 
+#ifdef NF_TUNING
 template <bool BF16, int CL>
 static int launch_t(const KernelArgs& a, cudaStream_t st, int grid) {
     auto* kern = k_nerf_mlp<BF16, CL>;
@@ -606,7 +597,6 @@ static int launch_t(const KernelArgs& a, cudaStream_t st, int grid) {
     return NF_OK;
 }
 
-#ifdef NF_TUNING
 // How many clusters of four CTAs (one CTA per SM: 227 KB of shared memory each) the device can hold at once: a cluster
 // lives inside one GPC, so GPCs whose SM count is not a multiple of four leave SMs idle.  Queried once per device.
 template <bool BF16>
@@ -632,27 +622,29 @@ static int max_clusters4() {
     }
     return cached[dev] > 0 ? cached[dev] : 0;
 }
-#endif
+#endif  // NF_TUNING
 
-// CTA pairs (cluster of 2, tcgen05 cta_group::2).  The tuning build can also run clusters of two pairs with multicast
-// weight quarters (NF_MLP_CLUSTER=4) and the two-tile kernel of nf_mlp2.cu (NF_MLP_IMPL=2): both measured, neither faster
-// (profiles/r02_notes.md), so the release library carries neither.
+
+// Production: the two-tile kernel (nf_mlp2.cu).  The tuning build can select the one-tile kernel (NF_MLP_IMPL=1), optionally
+// as clusters of two pairs with multicast weight quarters (NF_MLP_CLUSTER=4), for back-to-back comparisons on one box.
 int launch(const KernelArgs& a, int dtype, cudaStream_t st) {
-    const bool bf = dtype == NF_DTYPE_BF16;
-    const int pairs_grid = num_sms() & ~1;
 #ifdef NF_TUNING
     const char* impl = getenv("NF_MLP_IMPL");
-    if (impl && atoi(impl) == 2) return launch2(a, dtype, st);
-    const char* e = getenv("NF_MLP_CLUSTER");
-    if (e && atoi(e) == 4) {
-        const int c4 = bf ? max_clusters4<true>() : max_clusters4<false>();
-        if (c4 * 4 * 10 >= pairs_grid * 9) {       // at most 10 % of the SMs left without a cluster
-            const int grid = 4 * (c4 < num_sms() / 4 ? c4 : num_sms() / 4);
-            return bf ? launch_t<true, 4>(a, st, grid) : launch_t<false, 4>(a, st, grid);
+    if (impl && atoi(impl) == 1) {
+        const bool bf = dtype == NF_DTYPE_BF16;
+        const int pairs_grid = num_sms() & ~1;
+        const char* e = getenv("NF_MLP_CLUSTER");
+        if (e && atoi(e) == 4) {
+            const int c4 = bf ? max_clusters4<true>() : max_clusters4<false>();
+            if (c4 * 4 * 10 >= pairs_grid * 9) {       // at most 10 % of the SMs left without a cluster
+                const int grid = 4 * (c4 < num_sms() / 4 ? c4 : num_sms() / 4);
+                return bf ? launch_t<true, 4>(a, st, grid) : launch_t<false, 4>(a, st, grid);
+            }
         }
+        return bf ? launch_t<true, 2>(a, st, pairs_grid) : launch_t<false, 2>(a, st, pairs_grid);
     }
 #endif
-    return bf ? launch_t<true, 2>(a, st, pairs_grid) : launch_t<false, 2>(a, st, pairs_grid);
+    return launch2(a, dtype, st);
 }
 
 }  // namespace mlp
@@ -693,14 +685,19 @@ static int env_int(const char* name, int dflt) {
 }
 #endif
 
+extern "C" size_t nf_nerf_mlp_workspace_bytes(void) { return mlp::PE_SCRATCH_BYTES; }
+
 extern "C" int nf_nerf_mlp_forward(const void* packed, int dtype, const float* records, int n_rows, int sigma_only,
-                                   float* out, void* stream_) {
+                                   float* out, void* workspace, size_t workspace_bytes, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     NF_REQUIRE(packed && out && n_rows >= 0, NF_E_INVALID, "nf_nerf_mlp_forward: bad arguments");
     NF_REQUIRE(dtype == NF_DTYPE_F16 || dtype == NF_DTYPE_BF16, NF_E_UNSUPPORTED, "nf_nerf_mlp_forward: dtype %d", dtype);
     if (n_rows == 0) return NF_OK;
     NF_REQUIRE(records != nullptr, NF_E_INVALID, "nf_nerf_mlp_forward: null records");
+    NF_REQUIRE(workspace && workspace_bytes >= mlp::PE_SCRATCH_BYTES, NF_E_WORKSPACE, "nf_nerf_mlp_forward: workspace %zu < %zu",
+               workspace_bytes, (size_t)mlp::PE_SCRATCH_BYTES);
     mlp::KernelArgs a;
+    a.pe_scratch = (uint8_t*)workspace;
     a.packed = (const uint8_t*)packed;
     a.records = records;
     a.rowid = nullptr;

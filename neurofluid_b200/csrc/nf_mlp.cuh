@@ -1,4 +1,4 @@
-// nf_mlp.cuh -- launch interface of the fused PE + NeRF MLP kernel (nf_mlp.cu)
+// nf_mlp.cuh -- launch interface, constants and packed-weight layout of the fused PE + NeRF MLP kernels (nf_mlp.cu, nf_mlp2.cu)
 #pragma once
 #include "nf_common.cuh"
 
@@ -56,7 +56,13 @@ __host__ __device__ inline int enc_col_dir(int k, int flags) {
     return -1;
 }
 
+// Encoded-feature scratch of the two-tile kernel (nf_mlp2.cu): per CTA, 2 passes x 2 tiles x (xyz-like 26 + dir-like 8 chunks
+// of 2 KB).  Part of the caller's workspace; sized for the largest grid the kernel launches (one CTA per SM, <= 160).
+constexpr int PE_SCRATCH_CTAS = 160;
+constexpr size_t PE_SCRATCH_BYTES = (size_t)PE_SCRATCH_CTAS * 2 * 2 * (26 + 8) * 2048;
+
 struct KernelArgs {
+    uint8_t* pe_scratch;     // PE_SCRATCH_BYTES of device memory, 16-byte aligned (L2-resident while a launch runs)
     const uint8_t* packed;   // weight slabs + small params
     const float* records;    // (n_rows,16)
     const int* rowid;        // (n_rows) destination index in out4, <0 = skip; NULL = identity
@@ -70,10 +76,8 @@ struct KernelArgs {
 };
 
 
-int launch(const KernelArgs& a, int dtype, cudaStream_t st);        // nf_mlp.cu: CTA pairs, one 128-row tile per CTA
-#ifdef NF_TUNING
-int launch2(const KernelArgs& a, int dtype, cudaStream_t st);       // nf_mlp2.cu (experiment): two tiles per CTA sharing the weight stream
-#endif
+int launch(const KernelArgs& a, int dtype, cudaStream_t st);        // nf_mlp.cu: dispatch (production: launch2)
+int launch2(const KernelArgs& a, int dtype, cudaStream_t st);       // nf_mlp2.cu: CTA pairs, two 128-row tiles per CTA sharing the weight stream
 
 }  // namespace mlp
 }  // namespace nf

@@ -1,35 +1,44 @@
-// nf_mlp2.cu -- the fused positional-encoding + NeRF MLP forward with TWO 128-row tiles per CTA (sm_100a, tcgen05).
+// nf_mlp2.cu -- the fused positional-encoding + NeRF MLP forward (sm_100a, tcgen05): TWO 128-row tiles per CTA.
 //
 // replaces: Embedding.forward x6 (models/nerf.py:21-38 via models/renderer.py:125-179) and NeRF.forward
-//           (models/nerf.py:83-124); same arithmetic, operands and packed weights as k_nerf_mlp (nf_mlp.cu).
+//           (models/nerf.py:83-124; two instances, models/renderer.py:43-44).
 //
-// Why two tiles.  The one-tile kernel's timeline (profiles/r02_mlp_timeline.txt) shows ~3,400-3,800 cycles per layer
-// against 2,048 of MMA: (1) nothing overlaps a layer's accumulator drain + epilogue, because the next layer of the same
-// tile needs its result, and (2) every SM has to take in 64 KB of weights per tile-layer, and bulk copies land at
-// ~23.7 B/clk per SM (2,765 cycles per layer; halving the L2 reads with a 4-CTA multicast changed nothing: the bound is
-// the SM's ingest, not L2).  Here every weight unit that arrives in shared memory is used by BOTH tiles of the CTA (half
-// the ingest per row), and while one tile's accumulator is being drained the tensor pipe works on the other tile.
+// Work unit: a tile of 128 compact "geometry records" (16 fp32 per evaluated ray sample, written by the ray-stage kernels
+// in nf_render.cu).  Persistent CTAs, one per SM, run as CTA PAIRS (cluster of 2, tcgen05 cta_group::2, M = 256); a pair
+// takes 4 tiles per pass: tile T (0, 1) of CTA r = rows of tile 4 * pass + 2 r + T.
 //
-// Per CTA pair (cluster of 2, tcgen05 cta_group::2, M = 256): 4 tiles per pass, tile T of CTA r = rows of tile
-// 4 * pass + 2 r + T.  Shared memory: two in-place activation tiles (2 x 64 KB), a 5-stage x 16 KB ring, small params.
-// The ring carries, in consumption order (nf_mlp.cuh), the weight units AND -- for the layers that read encoded
-// features (0, 4: xyz-like; 9: dir-like) -- "A pieces": 4 K-steps of a tile's encoded features.  The encodings are
-// written by the 4 producer warps to a per-CTA scratch in global memory (L2) one pass ahead, as tile images, so that
-// they occupy no shared memory between the layers that use them.
-// TMEM: accumulators of tile T in columns [256 T, 256 T + 256), single-buffered: the issuer waits for "accumulator
-// half drained" before it overwrites one.
+// Why two tiles per CTA (profiles/r02_mlp_timeline.txt, profiles/r02_notes.md).  A layer needs 2,048 cycles of MMA per
+// tile AND 2,048 cycles to drain its 128 x 256 fp32 accumulator out of TMEM (tcgen05.ld moves 64 B per clock per SM), and
+// the next layer of the same tile needs that drain's result: with one tile per CTA the two never overlap (measured:
+// ~3,750 cycles per layer).  Here the tensor pipe works on one tile while the other tile's accumulator is drained, and
+// every weight unit that lands in shared memory is used by BOTH tiles (half the L2 -> SM weight traffic per row).
+// Measured on the same box, back to back: fine network 37.1 -> 32.0 ms per 800 x 800 image, bit-identical outputs.
 //
-// Roles (14 warps): 0-7 epilogue (two groups of four: group g owns columns [64c + 32g, +32) of every 64-column chunk c;
-// order per layer: (half 0, tile 0) (half 0, tile 1) (half 1, tile 0) (half 1, tile 1)), 8 MMA issuer (rank 0) / weight relay (rank 1),
-// 9 loader, 10-13 encoding producers.
-// Compiled into the TUNING build only (python -m neurofluid_b200.build --tuning; NF_MLP_IMPL=2 selects it): it measures the
-// same as the production kernel today (profiles/r02_mlp_timeline.txt, profiles/r02_notes.md), so the release library does
-// not carry it.
+// Shared memory (222 KB): two in-place activation tiles (2 x 64 KB, UMMA K-major no-swizzle "tile image":
+// byte(row r, column k) = (k / 8) * 2048 + r * 16 + (k % 8) * 2), a 5-stage x 16 KB mbarrier ring, the fp32 biases / heads.
+// The ring carries, in consumption order (nf_mlp.cuh), the weight units AND -- for the layers that read encoded features
+// (0, 4: xyz-like; 9: dir-like) -- "A pieces": 4 K-steps of a tile's encoded features.  The encodings are written by the 4
+// producer warps to a per-CTA scratch in the caller's workspace (KernelArgs::pe_scratch, L2-resident) one pass ahead, as
+// tile images, so that they occupy no shared memory between the layers that use them.  (Writing them straight into ring
+// stages was tried: with 4 of the 5 stages held by one K-block there is no room to produce ahead, 32 -> 54 ms.)
+// TMEM: accumulators of tile T in columns [256 T, 256 T + 256), single-buffered: the issuer waits for "accumulator half
+// drained" before it overwrites one.
+//
+// Roles (14 warps): 0-7 epilogue (two groups of four; group g owns columns [64c + 32g, +32) of every 64-column chunk c;
+// order per layer: (half 0, tile 0) (half 0, tile 1) (half 1, tile 0) (half 1, tile 1); tcgen05.ld -> +bias -> ReLU ->
+// fp16 -> back into the tile's activation image; sigma (256 -> 1) and rgb (128 -> 3) heads are register dot products),
+// 8 MMA issuer (rank 0; converged warp, one elected lane issues; one wait + one commit per weight unit) / weight relay
+// (rank 1), 9 loader (cp.async.bulk), 10-13 encoding producers (record -> sin/cos by double-angle recurrence re-anchored
+// at 2^5, fp32 -> fp16/bf16).
+// A variant that runs tile 1 one weight unit behind tile 0 (so that accumulator halves complete in drain order) measured
+// 41 ms: not kept.  The tuning build (-DNF_TUNING) can still run the one-tile kernel of nf_mlp.cu for comparison.
+//
+// Per row the tensor pipe does 671,744 MAC (665,984 algorithmic + K padding 198->208, 54->64).
+// HBM traffic per row: 64 B record in, 16 B out (+4 B row id); weights (1.34 MB/net) stay in L2.
 #include "nf_common.cuh"
 #include "nf_mlp.cuh"
 #include "nf_tc.cuh"
 
-#ifdef NF_TUNING
 namespace nf {
 namespace mlp {
 namespace v2 {
@@ -66,6 +75,7 @@ constexpr int W_ISSUE = 8, W_LOAD = 9, W_PE = 10;
 constexpr int NUM_THREADS = 14 * 32;
 constexpr int PE_TILE_BYTES = (26 + 8) * 2048;          // xyz-like image (26 chunks) + dir-like image (8 chunks)
 constexpr int PE_CTA_BYTES = 2 /*parity*/ * 2 /*tile*/ * PE_TILE_BYTES;
+static_assert((size_t)PE_SCRATCH_CTAS * PE_CTA_BYTES == PE_SCRATCH_BYTES, "encoding scratch size (nf_mlp.cuh)");
 constexpr int TPP = 4;                                  // tiles per pair per pass
 
 // encoded-feature row -> tile image in GLOBAL memory: byte(row r, column k) = (k / 8) * 2048 + r * 16 + (k % 8) * 2
@@ -125,7 +135,7 @@ __device__ __forceinline__ int stages_per_pass(int nl) {
 }
 
 template <bool BF16>
-__global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp2(const KernelArgs a, uint8_t* __restrict__ pe_scratch) {
+__global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp2(const KernelArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr bool PAIR = true;
     const int warp = uniform((int)(threadIdx.x >> 5)), lane = threadIdx.x & 31;
@@ -143,7 +153,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp2(const KernelArgs a
     float4* part = reinterpret_cast<float4*>(smem + SM_PART);
     auto bar = [&](int i) { return s_bar + 8u * (uint32_t)i; };
     auto bar0 = [&](int i) { return mapa_rank(bar(i), 0); };       // the same barrier in the issuer's CTA (rank 0)
-    uint8_t* my_scratch = pe_scratch + (size_t)blockIdx.x * PE_CTA_BYTES;
+    uint8_t* my_scratch = a.pe_scratch + (size_t)blockIdx.x * PE_CTA_BYTES;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NST; ++i) {
@@ -482,29 +492,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp2(const KernelArgs a
     if (warp == W_ISSUE) tmem_dealloc<PAIR>(tmem_base, 512);
 }
 
-// per-device scratch for the encoded features (one block of PE_CTA_BYTES per CTA of the grid): allocated on first use and
-// kept for the life of the process -- like the kernel image itself, it is part of the library's device state, not per-call
-// memory (40 MB, all of it L2-resident while a launch runs)
-static uint8_t* pe_scratch_for_device() {
-    static uint8_t* cached[64] = {nullptr};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    if (!cached[dev]) {
-        void* p = nullptr;
-        if (cudaMalloc(&p, (size_t)num_sms() * PE_CTA_BYTES) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-        cached[dev] = (uint8_t*)p;
-    }
-    return cached[dev];
-}
-
 template <bool BF16>
 static int launch_t(const KernelArgs& a, cudaStream_t st) {
     auto* kern = k_nerf_mlp2<BF16>;
-    uint8_t* scratch = pe_scratch_for_device();
-    NF_REQUIRE(scratch != nullptr, NF_E_CUDA, "nf_mlp: could not allocate the encoding scratch (%zu bytes)", (size_t)num_sms() * PE_CTA_BYTES);
+    NF_REQUIRE(a.pe_scratch != nullptr, NF_E_WORKSPACE, "nf_mlp: no encoding scratch in the workspace");
     NF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(num_sms() & ~1), 1, 1);
+    cfg.gridDim = dim3((unsigned)min(num_sms() & ~1, PE_SCRATCH_CTAS), 1, 1);
     cfg.blockDim = dim3(NUM_THREADS, 1, 1);
     cfg.dynamicSmemBytes = SM_TOTAL;
     cfg.stream = st;
@@ -515,7 +509,7 @@ static int launch_t(const KernelArgs& a, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    NF_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, a, scratch));
+    NF_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, a));
     count_launch();
     return NF_OK;
 }
@@ -528,4 +522,3 @@ int launch2(const KernelArgs& a, int dtype, cudaStream_t st) {
 
 }  // namespace mlp
 }  // namespace nf
-#endif  // NF_TUNING

@@ -953,7 +953,7 @@ static int env_int(const char* name, int dflt) {
 #endif
 
 struct WsLayout {
-    size_t counters, act0, act1, base0, cnt0, miss, z1, rec0, rowid0, out0, rec1, rowid1, out1, nbr0, nbr1, total;
+    size_t counters, pe_scratch, act0, act1, base0, cnt0, miss, z1, rec0, rowid0, out0, rec1, rowid1, out1, nbr0, nbr1, total;
     int cap0, cap1, ns0, ns1;
 };
 
@@ -975,6 +975,7 @@ static WsLayout ws_layout(int R, int S0, int NI, int K = 0 /* > 0: room for the 
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 256); return r; };
     L.counters = take(64);
+    L.pe_scratch = take(mlp::PE_SCRATCH_BYTES);      // encoded-feature scratch of the MLP kernel (nf_mlp.cuh), shared by both networks
     L.act0 = take(sizeof(unsigned) * (size_t)R * 4);
     L.act1 = take(sizeof(unsigned) * (size_t)R * 8);
     L.base0 = take(sizeof(int) * (size_t)R * 4);
@@ -1199,6 +1200,7 @@ extern "C" int nf_render_forward(const nf_render_args* a, void* stream_) {
     tm.mark();
     // ---- coarse network
     mlp::KernelArgs m;
+    m.pe_scratch = (uint8_t*)(b + L.pe_scratch);
     m.packed = (const uint8_t*)a->weights_coarse;
     m.records = p.rec0; m.rowid = p.rowid0; m.n_rows_dev = p.counters + 0; m.n_rows_host = 0; m.n_rows_cap = L.cap0;
     m.n_layers = (a->mode == NF_RENDER_FINE) ? 8 : 10;

@@ -67,9 +67,22 @@ def nerf_mlp(packed: torch.Tensor, records: torch.Tensor, dtype=_lib.NF_DTYPE_F1
     require_cuda(packed, records)
     rec = records.detach().to(torch.float32).contiguous()
     out = torch.zeros((rec.shape[0], 4), dtype=torch.float32, device=rec.device)
+    ws = _mlp_workspace(rec.device)
     check(lib().nf_nerf_mlp_forward(ptr(packed), int(dtype), ptr(rec), rec.shape[0], int(bool(sigma_only)), ptr(out),
-                                    stream_ptr()), "nf_nerf_mlp_forward")
+                                    ptr(ws), ws.numel(), stream_ptr()), "nf_nerf_mlp_forward")
     return out
+
+
+_MLP_WS = {}
+
+
+def _mlp_workspace(device) -> torch.Tensor:
+    """nf_nerf_mlp_forward's staging workspace (constant size), one per device, reused across calls on the current stream."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    ws = _MLP_WS.get(key)
+    if ws is None:
+        ws = _MLP_WS[key] = torch.empty(lib().nf_nerf_mlp_workspace_bytes(), dtype=torch.uint8, device=device)
+    return ws
 
 
 def pack_nerf_weights_bwd(params) -> torch.Tensor:

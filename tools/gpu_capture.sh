@@ -23,8 +23,9 @@ cap k_cconv k_cconv_tc 2 2 python tests/gpu_profile_trans.py 3           # secon
 cap k_mlp_bwd k_mlp_bwd 2 2 python tests/gpu_profile_bwd.py              # second training step: dgrad, wgrad of the coarse net
 # MLP tile timelines (tuning build: the same kernels + trace hooks)
 export NF_B200_LIB=$PWD/neurofluid_b200/libnf_b200_tune.so
-( echo "== k_nerf_mlp (one tile per CTA, production)"; timeout 120 python tests/gpu_mlp_trace.py;
-  echo "== k_nerf_mlp2 (two tiles per CTA, experiment; NF_MLP_IMPL=2)"; NF_MLP_IMPL=2 timeout 120 python tests/gpu_mlp_trace2.py ) > $out/${tag}_mlp_timeline.txt 2>&1
+( echo "== k_nerf_mlp (one tile per CTA; tuning build only, NF_MLP_IMPL=1)"; NF_MLP_IMPL=1 timeout 120 python tests/gpu_mlp_trace.py;
+  echo "== k_nerf_mlp2 (two tiles per CTA, production)"; timeout 120 python tests/gpu_mlp_trace2.py;
+  echo "== sustained, back to back (clock / power sampled)"; REPS=40 timeout 200 python tests/gpu_mlp_power.py ) > $out/${tag}_mlp_timeline.txt 2>&1
 unset NF_B200_LIB
 # transition phases
 timeout 200 python tests/gpu_trans_phases.py > $out/${tag}_trans_phases.txt 2>&1
