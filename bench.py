@@ -520,7 +520,7 @@ def main():
                 "d2h_bytes_per_step": int(rgb_host.numel() * 4) * world, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches_t.item()),
         "clocks": clocks,
-        "roofline": {"kernel": "k_nerf_mlp (fine network)", "bound": "tensor", "achieved": achieved_tflops,
+        "roofline": {"kernel": "k_nerf_mlp2 (fine network; csrc/nf_mlp2.cu)", "bound": "tensor", "achieved": achieved_tflops,
                      "peak": pk["tensor_burst"], "unit": "TFLOP/s", "frac": achieved_tflops / pk["tensor_burst"],
                      "peak_source": f"{pk['src']} bf16 dense, burst (the kernel runs in ~6 ms bursts at full clock inside the step)",
                      "frac_of_sustained_peak": achieved_tflops / pk["tensor"],

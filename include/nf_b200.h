@@ -10,8 +10,11 @@
  *   - plain C: pointers, sizes, scalars; no torch / C++ types cross the boundary.
  *   - every pointer is a DEVICE pointer into caller-owned memory unless its name ends in _host.
  *   - every call is asynchronous on the CUDA stream passed as `stream` (a cudaStream_t cast to
- *     void*; NULL = legacy default stream).  No call synchronises the device.
- *   - no hidden device allocation: scratch comes from the caller, sized by the *_bytes() queries.
+ *     void*; NULL = legacy default stream).  No call synchronises the device, with two exceptions:
+ *     nf_render_backward waits once for two row counters of its forward (they size the backward's tile
+ *     loops), and nf_comm_init blocks inside ncclCommInitRank.
+ *   - no hidden device allocation: scratch comes from the caller, sized by the *_bytes() queries
+ *     (nf_comm_init creates an NCCL communicator, which allocates its own buffers).
  *   - return value: 0 = ok, < 0 = error (NF_E_*); nf_last_error() returns a thread-local message.
  *   - fp32 everywhere at the boundary; neighbour indices int32; neighbour counts int64 where the
  *     reference returns int64 tensors.

@@ -16,8 +16,9 @@
 //
 // Shared memory (222 KB): two in-place activation tiles (2 x 64 KB, UMMA K-major no-swizzle "tile image":
 // byte(row r, column k) = (k / 8) * 2048 + r * 16 + (k % 8) * 2), a 5-stage x 16 KB mbarrier ring, the fp32 biases / heads.
-// The ring carries, in consumption order (nf_mlp.cuh), the weight units AND -- for the layers that read encoded features
-// (0, 4: xyz-like; 9: dir-like) -- "A pieces": 4 K-steps of a tile's encoded features.  The encodings are written by the 4
+// The ring carries, in consumption order (nf_mlp.cuh), the weight units AND -- for layers 4 (xyz-like skip input) and 9
+// (dir-like) -- "A pieces": 4 K-steps of a tile's encoded features.  Layer 0's encodings are bulk-copied into the tile's own
+// activation buffer (dead between the last layer's MMAs and layer 0's first epilogue) by a second loader lane.  The encodings are written by the 4
 // producer warps to a per-CTA scratch in the caller's workspace (KernelArgs::pe_scratch, L2-resident) one pass ahead, as
 // tile images, so that they occupy no shared memory between the layers that use them.  (Writing them straight into ring
 // stages was tried: with 4 of the 5 stages held by one K-block there is no room to produce ahead, 32 -> 54 ms.)
@@ -25,13 +26,14 @@
 // drained" before it overwrites one.
 //
 // Roles (14 warps): 0-7 epilogue (two groups of four; group g owns columns [64c + 32g, +32) of every 64-column chunk c;
-// order per layer: (half 0, tile 0) (half 0, tile 1) (half 1, tile 0) (half 1, tile 1); tcgen05.ld -> +bias -> ReLU ->
+// drain order per layer: (half 0, tile 0) (half 0, tile 1) (half 1, tile 0) (half 1, tile 1); tcgen05.ld -> +bias -> ReLU ->
 // fp16 -> back into the tile's activation image; sigma (256 -> 1) and rgb (128 -> 3) heads are register dot products),
 // 8 MMA issuer (rank 0; converged warp, one elected lane issues; one wait + one commit per weight unit) / weight relay
 // (rank 1), 9 loader (cp.async.bulk), 10-13 encoding producers (record -> sin/cos by double-angle recurrence re-anchored
 // at 2^5, fp32 -> fp16/bf16).
-// A variant that runs tile 1 one weight unit behind tile 0 (so that accumulator halves complete in drain order) measured
-// 41 ms: not kept.  The tuning build (-DNF_TUNING) can still run the one-tile kernel of nf_mlp.cu for comparison.
+// The issuer takes a hidden layer's eight (weight unit, tile) steps in an order that lets tile 0's high-K units go before
+// tile 1's (K low, half 1): the drain runs gap-free (6.0k -> 5.2k cycles per layer of two tiles, 33.2 -> 31.9 ms).  A variant
+// that runs tile 1 a whole weight unit behind tile 0 everywhere measured 41 ms: not kept.  The tuning build (-DNF_TUNING) can still run the one-tile kernel of nf_mlp.cu for comparison.
 //
 // Per row the tensor pipe does 671,744 MAC (665,984 algorithmic + K padding 198->208, 54->64).
 // HBM traffic per row: 64 B record in, 16 B out (+4 B row id); weights (1.34 MB/net) stay in L2.
@@ -64,7 +66,9 @@ enum Bar {
     B_ACC_FREE = B_ACC_FULL + 4,    // [tile 2][half 2]
     B_PE_READY = B_ACC_FREE + 4,    // [parity 2]
     B_PE_FREE = B_PE_READY + 2,     // [parity 2]
-    NUM_BARS = B_PE_FREE + 2,
+    B_L0_FULL = B_PE_FREE + 2,      // [tile 2]: layer 0's xyz-like encodings have landed in the tile's activation buffer
+    B_HID_FREE = B_L0_FULL + 2,     // [tile 2]: the last layer's MMAs have read the tile's activation buffer
+    NUM_BARS = B_HID_FREE + 2,
 };
 constexpr int SM_TMEM_SLOT = SM_BAR + NUM_BARS * 8;
 constexpr int SM_TOTAL = SM_TMEM_SLOT + 16;
@@ -125,11 +129,11 @@ __device__ __forceinline__ void emit_encoding_g(RowWriterG<BF16>& w, const float
     });
 }
 
-__device__ __forceinline__ int stages_per_pass(int nl) {
+__device__ __forceinline__ int stages_per_pass(int nl, bool l0_hid) {
     int n = 0;
     for (int l = 0; l < nl; ++l) {
         const int npe = layer_pe_steps(l);
-        n += 4 * ((npe + wu_ksteps(0) - 1) / wu_ksteps(0)) + (l > 0 ? 2 * (KH_STEPS / wu_ksteps(1)) : 0);
+        n += ((l == 0 && l0_hid) ? 2 : 4) * ((npe + wu_ksteps(0) - 1) / wu_ksteps(0)) + (l > 0 ? 2 * (KH_STEPS / wu_ksteps(1)) : 0);
     }
     return n;
 }
@@ -146,6 +150,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp2(const KernelArgs a
     const int npass = (ntiles + TPP - 1) / TPP;
     if (unit >= npass) return;          // both CTAs of a pair leave together
     const int nl = a.n_layers;
+    // Layer 0 reads its A operand (the xyz-like encodings, 52 KB per tile) from the tile's own activation buffer, which is dead
+    // between the last layer's MMAs and layer 0's first epilogue: one bulk copy per tile from the encoding scratch, issued as
+    // soon as the buffer is free, i.e. under the last layer's drain, instead of 8 ring stages that compete with layer 0's
+    // weights for the SM's ingest (the ring carries <= 64 KB in flight: ~24 B/clk, and a 4-K-step block wants 48 KB per 1,024).
+#ifdef NF_TUNING
+    const bool l0_hid = (a.desc_swap & 64) == 0;       // NF_MLP_DESC_SWAP=64: layer 0's A pieces through the ring, for comparison
+#else
+    constexpr bool l0_hid = true;
+#endif
 
     const uint32_t s_base = smem_u32(smem);
     const uint32_t s_ring = s_base + SM_RING, s_bar = s_base + SM_BAR;
@@ -168,6 +181,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp2(const KernelArgs a
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar(B_PE_READY + i), 4);                  // the 4 producer warps of this CTA
             mbar_init(bar(B_PE_FREE + i), 1);
+            mbar_init(bar(B_L0_FULL + i), prank == 0 ? 2 : 1);  // own expect_tx arrive (+ the peer's relay)
+            mbar_init(bar(B_HID_FREE + i), 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -191,6 +206,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp2(const KernelArgs a
             uint32_t ws = 0, wph = 0, hidw = 0, lcount = 0;
             int ti = 0;
             auto advance = [&]() { if (++ws == NST) { ws = 0; wph ^= 1; } };
+#ifdef NF_TUNING
+            const bool t0_ahead = (a.desc_swap & 32) == 0;     // NF_MLP_DESC_SWAP=32: the plain lockstep order, for comparison
+#else
+            constexpr bool t0_ahead = true;
+#endif
             for (int pass = unit; pass < npass; pass += nunits, ++ti) {
                 for (int l = 0; l < nl; ++l, ++lcount) {
                     const bool n128 = (l == 9);
@@ -201,61 +221,95 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp2(const KernelArgs a
                     const uint32_t bstep = (2u * rpc * 16u) >> 4;
                     uint32_t accf = 0;                                  // bit (T * 2 + nh): that accumulator half has been started
                     const int npe = layer_pe_steps(l);
-                    for (int seg = 0; seg < 2; ++seg) {
-                        const int nsteps = seg == 0 ? npe : (l > 0 ? KH_STEPS : 0);
-                        const int kb = wu_ksteps(seg);
-                        const bool last_seg = (seg == 1) || (l == 0);
-                        for (int k0 = 0; k0 < nsteps; k0 += kb) {
-                            const int g = min(kb, nsteps - k0);
-                            const bool last_blk = last_seg && (k0 + kb >= nsteps);
-                            uint32_t sa[2] = {0u, 0u};
-                            if (seg == 0) {                             // the two tiles' encoded-feature pieces of this K-block
+                    // ---- encoded-feature segment (layers 0, 4, 9): K-blocks of 4 K-steps, A pieces through the ring
+                    for (int k0 = 0; k0 < npe; k0 += wu_ksteps(0)) {
+                        const int g = min(wu_ksteps(0), npe - k0);
+                        const bool last_blk = (l == 0) && (k0 + wu_ksteps(0) >= npe);
+                        const bool from_hid = l0_hid && l == 0;
+                        uint32_t sa[2] = {0u, 0u};
+                        if (from_hid) {
+                            if (k0 == 0) { mbar_wait(bar(B_L0_FULL), ti & 1); mbar_wait(bar(B_L0_FULL + 1), ti & 1); }
+                        } else {
 #pragma unroll
-                                for (int T = 0; T < 2; ++T) {
-                                    mbar_wait(bar(B_WFULL + ws), wph);
-                                    sa[T] = ws;
-                                    advance();
-                                }
-                            }
-#pragma unroll
-                            for (uint32_t nh = 0; nh < 2; ++nh) {
+                            for (int T = 0; T < 2; ++T) {           // the two tiles' encoded-feature pieces of this K-block
                                 mbar_wait(bar(B_WFULL + ws), wph);
-                                const uint64_t bd = umma_desc(s_ring + ws * STAGE, rpc * 16u, 128u);
-#pragma unroll
-                                for (uint32_t T = 0; T < 2; ++T) {
-                                    if (seg == 1 && nh == 0) {          // this block's K-steps read activation chunks k0/4, k0/4 + 1
-                                        mbar_wait(bar(B_ACT_READY + T * 4 + (k0 >> 2)), hidw & 1);
-                                        mbar_wait(bar(B_ACT_READY + T * 4 + (k0 >> 2) + 1), hidw & 1);
-                                    }
-                                    const uint32_t abit = 1u << (T * 2 + nh);
-                                    if (!(accf & abit)) {      // the previous layer's epilogue has drained what these MMAs overwrite
-                                        mbar_wait(bar(B_ACC_FREE + T * 2 + nh), (lcount & 1) ^ 1);
-                                        // the dir layer's halves are 64 columns wide: both lie inside layer 0's half 0
-                                        if (l == 0 && nh == 0) mbar_wait(bar(B_ACC_FREE + T * 2 + 1), (lcount & 1) ^ 1);
-                                    }
-                                    tc_fence_after();
-                                    if (elect_one()) {
-                                        const uint64_t ad = seg == 0 ? umma_desc(s_ring + sa[T] * STAGE, 2048u, 128u)
-                                                                     : umma_desc(s_base + SM_HID + T * 65536 + (uint32_t)k0 * 4096u, 2048u, 128u);
-                                        uint32_t acc = (accf & abit) ? 1u : 0u;
-#pragma unroll
-                                        for (int j = 0; j < WU_KSTEPS; ++j) {
-                                            if (j < g) {
-                                                umma_f16<PAIR>(tmem_base + T * 256 + nh * nhalf, ad + (uint64_t)(j * (4096 >> 4)), bd + (uint64_t)(j * bstep),
-                                                               idesc, acc);
-                                                acc = 1;
-                                            }
-                                        }
-                                        if (last_blk) umma_commit<PAIR>(bar(B_ACC_FULL + T * 2 + nh));
-                                        if (seg == 0 && nh == 1) umma_commit<PAIR>(bar(B_WEMPTY + sa[T]));
-                                        if (T == 1) umma_commit<PAIR>(bar(B_WEMPTY + ws));
-                                    }
-                                    __syncwarp();
-                                    accf |= abit;
-                                }
-                                if (seg == 1) NF_TRACE2(blockIdx.x == 0 && ti == 2 && lane == 0, tslot++);
+                                sa[T] = ws;
                                 advance();
                             }
+                        }
+#pragma unroll
+                        for (uint32_t nh = 0; nh < 2; ++nh) {
+                            mbar_wait(bar(B_WFULL + ws), wph);
+                            const uint64_t bd = umma_desc(s_ring + ws * STAGE, rpc * 16u, 128u);
+#pragma unroll
+                            for (uint32_t T = 0; T < 2; ++T) {
+                                const uint32_t abit = 1u << (T * 2 + nh);
+                                if (!(accf & abit)) {      // the previous layer's epilogue has drained what these MMAs overwrite
+                                    mbar_wait(bar(B_ACC_FREE + T * 2 + nh), (lcount & 1) ^ 1);
+                                    // the dir layer's halves are 64 columns wide: both lie inside layer 0's half 0
+                                    if (l == 0 && nh == 0) mbar_wait(bar(B_ACC_FREE + T * 2 + 1), (lcount & 1) ^ 1);
+                                }
+                                tc_fence_after();
+                                if (elect_one()) {
+                                    const uint64_t ad = from_hid ? umma_desc(s_base + SM_HID + T * 65536 + (uint32_t)k0 * 4096u, 2048u, 128u)
+                                                                 : umma_desc(s_ring + sa[T] * STAGE, 2048u, 128u);
+                                    uint32_t acc = (accf & abit) ? 1u : 0u;
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        if (j < g) {
+                                            umma_f16<PAIR>(tmem_base + T * 256 + nh * nhalf, ad + (uint64_t)(j * (4096 >> 4)), bd + (uint64_t)(j * bstep), idesc, acc);
+                                            acc = 1;
+                                        }
+                                    }
+                                    if (last_blk) umma_commit<PAIR>(bar(B_ACC_FULL + T * 2 + nh));
+                                    if (nh == 1 && !from_hid) umma_commit<PAIR>(bar(B_WEMPTY + sa[T]));
+                                    if (T == 1) umma_commit<PAIR>(bar(B_WEMPTY + ws));
+                                }
+                                __syncwarp();
+                                accf |= abit;
+                            }
+                            advance();
+                        }
+                    }
+                    // ---- hidden segment (layers 1..9): four weight units u = 2 blk + nh (K-block blk of 8 K-steps, N-half nh), each used
+                    // by both tiles.  Order of the eight (unit, tile) steps: tile 0 takes (blk 1, nh 0) BEFORE tile 1 takes (blk 0, nh 1):
+                    // tile 0's high-K units only need tile 0's own activation chunks (the previous layer's THIRD drain), tile 1's
+                    // (blk 0, nh 1) needs the fourth drain to have started; so tile 0's first accumulator half is complete by the time
+                    // the previous layer's last drain ends and the drain -- the busiest resource -- runs without a gap.
+                    if (l > 0) {
+                        uint32_t us[4], up[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) { us[u] = ws; up[u] = wph; advance(); }
+                        const uint32_t perm = t0_ahead ? 0x76534210u : 0x76543210u;
+#pragma unroll
+                        for (int step = 0; step < 8; ++step) {
+                            const uint32_t code = (perm >> (4 * step)) & 7u;
+                            const uint32_t blk = code >> 2, nh = (code >> 1) & 1u, T = code & 1u, u = code >> 1;
+                            const uint32_t k0 = blk * 8u;
+                            mbar_wait(bar(B_WFULL + us[u]), up[u]);
+                            if (nh == 0) {          // this block's K-steps read activation chunks k0/4, k0/4 + 1
+                                mbar_wait(bar(B_ACT_READY + T * 4 + (k0 >> 2)), hidw & 1);
+                                mbar_wait(bar(B_ACT_READY + T * 4 + (k0 >> 2) + 1), hidw & 1);
+                            }
+                            const uint32_t abit = 1u << (T * 2 + nh);
+                            if (!(accf & abit)) mbar_wait(bar(B_ACC_FREE + T * 2 + nh), (lcount & 1) ^ 1);
+                            tc_fence_after();
+                            if (elect_one()) {
+                                const uint64_t bd = umma_desc(s_ring + us[u] * STAGE, rpc * 16u, 128u);
+                                const uint64_t ad = umma_desc(s_base + SM_HID + T * 65536 + k0 * 4096u, 2048u, 128u);
+                                uint32_t acc = (accf & abit) ? 1u : 0u;
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    umma_f16<PAIR>(tmem_base + T * 256 + nh * nhalf, ad + (uint64_t)(j * (4096 >> 4)), bd + (uint64_t)(j * bstep), idesc, acc);
+                                    acc = 1;
+                                }
+                                if (blk == 1) umma_commit<PAIR>(bar(B_ACC_FULL + T * 2 + nh));
+                                if (T == 1) umma_commit<PAIR>(bar(B_WEMPTY + us[u]));
+                                if (l == nl - 1 && code >= 6u) umma_commit<PAIR>(bar(B_HID_FREE + T));   // (blk 1, nh 1, T): the tile's last step
+                            }
+                            __syncwarp();
+                            accf |= abit;
+                            if (T == 1) NF_TRACE2(blockIdx.x == 0 && ti == 2 && lane == 0, tslot++);
                         }
                     }
                     if (l > 0) ++hidw;
@@ -270,7 +324,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp2(const KernelArgs a
         } else if (lane == 0) {
             // ================================================================ relay (rank 1): "my share of stage s has landed"
             uint32_t ws = 0, wph = 0;
-            const int nstages = stages_per_pass(nl);
+            const int nstages = stages_per_pass(nl, l0_hid);
             const uint32_t remote0 = bar0(B_WFULL);
             for (int pass = unit; pass < npass; pass += nunits) {
                 for (int s = 0; s < nstages; ++s) {
@@ -303,7 +357,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp2(const KernelArgs a
                         const int kb = wu_ksteps(seg);
                         for (int k0 = 0; k0 < nsteps; k0 += kb) {
                             const int g = min(kb, nsteps - k0);
-                            if (seg == 0)
+                            if (seg == 0 && !(l0_hid && l == 0))
                                 for (int T = 0; T < 2; ++T)
                                     fill(pe + (size_t)T * PE_TILE_BYTES + (l == 9 ? 26 * 2048 : 0) + (size_t)k0 * 4096, (uint32_t)g * 4096u);
                             const uint32_t mine = (uint32_t)g * 2u * rpc * 16u;
@@ -319,6 +373,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp2(const KernelArgs a
                 mbar_wait(bar(B_WEMPTY + ws), wph ^ 1);
                 if (++ws == NST) { ws = 0; wph ^= 1; }
             }
+        } else if (lane == 1 && l0_hid) {
+            // second loader lane: layer 0's encodings, one bulk copy per tile, as soon as the tile's activation buffer is free
+            constexpr uint32_t L0_BYTES = KX_STEPS * 4096u;
+            const uint32_t l0_remote = bar0(B_L0_FULL);
+            int ti = 0;
+            for (int pass = unit; pass < npass; pass += nunits, ++ti) {
+                const uint8_t* pe = my_scratch + (size_t)(ti & 1) * 2 * PE_TILE_BYTES;
+                mbar_wait(bar(B_PE_READY + (ti & 1)), (ti >> 1) & 1);
+                for (int T = 0; T < 2; ++T) {
+                    mbar_wait(bar(B_HID_FREE + T), (ti & 1) ^ 1);
+                    mbar_arrive_expect_tx(bar(B_L0_FULL + T), L0_BYTES);
+                    bulk_g2s(s_base + SM_HID + T * 65536, pe + (size_t)T * PE_TILE_BYTES, L0_BYTES, bar(B_L0_FULL + T));
+                }
+                if (prank != 0) {           // tell the issuer (rank 0) that this CTA's tiles have landed too
+                    for (int T = 0; T < 2; ++T) {
+                        mbar_wait(bar(B_L0_FULL + T), ti & 1);
+                        mbar_arrive_cluster(l0_remote + 8u * T);
+                    }
+                }
+            }
+            // the last pass's (multicast) "buffer free" arrives have landed before this CTA may exit
+            for (int T = 0; T < 2; ++T) mbar_wait(bar(B_HID_FREE + T), (ti & 1) ^ 1);
         }
     } else if (warp < W_ISSUE) {
         // ================================================================ epilogue

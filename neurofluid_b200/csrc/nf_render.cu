@@ -1204,7 +1204,11 @@ extern "C" int nf_render_forward(const nf_render_args* a, void* stream_) {
     m.packed = (const uint8_t*)a->weights_coarse;
     m.records = p.rec0; m.rowid = p.rowid0; m.n_rows_dev = p.counters + 0; m.n_rows_host = 0; m.n_rows_cap = L.cap0;
     m.n_layers = (a->mode == NF_RENDER_FINE) ? 8 : 10;
+#ifdef NF_TUNING
+    m.desc_swap = env_int("NF_MLP_DESC_SWAP", 0);
+#else
     m.desc_swap = 0;
+#endif
     m.trace = nullptr;
     m.out4 = p.out0;
     int rc = mlp::launch(m, a->dtype, st);

@@ -29,8 +29,11 @@ export NF_B200_LIB=$PWD/neurofluid_b200/libnf_b200_tune.so
 unset NF_B200_LIB
 # transition phases
 timeout 200 python tests/gpu_trans_phases.py > $out/${tag}_trans_phases.txt 2>&1
-# memcheck over the backward / transition / operator tests (the render suite was checked in round 1; new code lives here)
-timeout 1500 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_backward.py tests/test_gpu_transition.py -q -x \
-    -k "not full_size and not end2end" > $out/${tag}_sanitizer_memcheck.log 2>&1
+# memcheck over the backward / transition / operator tests and the small render cases (every kernel of the library runs)
+timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_backward.py tests/test_gpu_transition.py -q -x \
+    -k "not full_size and not end2end and not release" > $out/${tag}_sanitizer_memcheck.log 2>&1
 tail -5 $out/${tag}_sanitizer_memcheck.log
+timeout 600 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_render.py -q -x \
+    -k "not full_size and not production" > $out/${tag}_sanitizer_memcheck_render.log 2>&1
+tail -5 $out/${tag}_sanitizer_memcheck_render.log
 ls -la $out | tail -30
