@@ -488,11 +488,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp2(const KernelArgs a
                             __syncwarp();
                             if (lane == 0) mbar_arrive_cluster(acc_free0 + 8u * (T * 2 + h));
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                const float f = fmaxf(__uint_as_float(v[i]) + bias[h * 64 + i], 0.f);
-                                rgb[T][0] = fmaf(f, wrgb[h * 64 + i], rgb[T][0]);
-                                rgb[T][1] = fmaf(f, wrgb[128 + h * 64 + i], rgb[T][1]);
-                                rgb[T][2] = fmaf(f, wrgb[256 + h * 64 + i], rgb[T][2]);
+                            for (int i = 0; i < 32; i += 4) {       // 16-byte shared-memory loads (all offsets are multiples of 4 floats)
+                                const float4 b4 = *reinterpret_cast<const float4*>(bias + h * 64 + i);
+                                const float4 wr = *reinterpret_cast<const float4*>(wrgb + h * 64 + i);
+                                const float4 wg = *reinterpret_cast<const float4*>(wrgb + 128 + h * 64 + i);
+                                const float4 wb = *reinterpret_cast<const float4*>(wrgb + 256 + h * 64 + i);
+                                const float f0 = fmaxf(__uint_as_float(v[i]) + b4.x, 0.f), f1 = fmaxf(__uint_as_float(v[i + 1]) + b4.y, 0.f);
+                                const float f2 = fmaxf(__uint_as_float(v[i + 2]) + b4.z, 0.f), f3 = fmaxf(__uint_as_float(v[i + 3]) + b4.w, 0.f);
+                                rgb[T][0] = fmaf(f0, wr.x, rgb[T][0]); rgb[T][1] = fmaf(f0, wg.x, rgb[T][1]); rgb[T][2] = fmaf(f0, wb.x, rgb[T][2]);
+                                rgb[T][0] = fmaf(f1, wr.y, rgb[T][0]); rgb[T][1] = fmaf(f1, wg.y, rgb[T][1]); rgb[T][2] = fmaf(f1, wb.y, rgb[T][2]);
+                                rgb[T][0] = fmaf(f2, wr.z, rgb[T][0]); rgb[T][1] = fmaf(f2, wg.z, rgb[T][1]); rgb[T][2] = fmaf(f2, wb.z, rgb[T][2]);
+                                rgb[T][0] = fmaf(f3, wr.w, rgb[T][0]); rgb[T][1] = fmaf(f3, wg.w, rgb[T][1]); rgb[T][2] = fmaf(f3, wb.w, rgb[T][2]);
                             }
                             if (h == 1) {
                                 if (grp == 1) part[tr] = make_float4(rgb[T][0], rgb[T][1], rgb[T][2], sigma[T]);
