@@ -245,8 +245,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_nerf_mlp2(const KernelArgs a
                             for (uint32_t T = 0; T < 2; ++T) {
                                 const uint32_t abit = 1u << (T * 2 + nh);
                                 if (!(accf & abit)) {      // the previous layer's epilogue has drained what these MMAs overwrite
-                                    mbar_wait(bar(B_ACC_FREE + T * 2 + nh), (lcount & 1) ^ 1);
-                                    // the dir layer's halves are 64 columns wide: both lie inside layer 0's half 0
+                                    // the dir layer's halves are 64 columns wide: both lie inside half 0 of a 256-wide layer, so layer
+                                    // 9 only needs layer 8's half-0 drains (waiting for half 1 held the block's four ring stages ~2k
+                                    // cycles longer), and layer 0 of the next pass needs both of layer 9's
+                                    mbar_wait(bar(B_ACC_FREE + T * 2 + (n128 ? 0u : nh)), (lcount & 1) ^ 1);
                                     if (l == 0 && nh == 0) mbar_wait(bar(B_ACC_FREE + T * 2 + 1), (lcount & 1) ^ 1);
                                 }
                                 tc_fence_after();
