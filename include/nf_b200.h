@@ -307,7 +307,9 @@ NF_API int nf_transition_num_phases(void);
 NF_API int nf_transition_step(const nf_transition_args* args, void* stream);
 /* Location of layer `layer`'s activation matrix (the ReLU'd fp16/bf16 rows the next layer gathers from)
  * inside a transition workspace: *offset_bytes from the workspace base, *row_bytes per particle.
- * layer 0: 96 channels, 1 and 2: 64 channels.  Used by the sharded execution to all-gather rows. */
+ * layer 0: 96 channels, 1 and 2: 64 channels.  Used by the sharded execution to all-gather rows.
+ * layer 3..6: the fp32 pre-activation outputs of the four layers (models/transmodel.py:122-131 `ans_convs`): 96, 64, 64
+ * floats per row and, for the last one, 16 floats per row of which the first 3 are the position correction * 128. */
 NF_API int nf_transition_layer_buffer(int n_fluid, int n_box, int layer, size_t* offset_bytes_host,
                                       size_t* row_bytes_host);
 

@@ -2071,10 +2071,15 @@ extern "C" int nf_transition_backward(const nf_transition_bwd_args* b, void* str
 extern "C" int nf_transition_num_phases(void) { return 5; }
 
 extern "C" int nf_transition_layer_buffer(int n_fluid, int n_box, int layer, size_t* off, size_t* row_bytes) {
-    NF_REQUIRE(off && row_bytes && layer >= 0 && layer <= 2, NF_E_INVALID, "nf_transition_layer_buffer: bad arguments");
+    NF_REQUIRE(off && row_bytes && layer >= 0 && layer <= 6, NF_E_INVALID, "nf_transition_layer_buffer: bad arguments");
     const WsLayout L = ws_layout(n_fluid, n_box);
-    *off = layer == 0 ? L.x0 : (layer == 1 ? L.x1 : L.x2);
-    *row_bytes = (layer == 0 ? 96 : 64) * 2;
+    if (layer <= 2) {
+        *off = layer == 0 ? L.x0 : (layer == 1 ? L.x1 : L.x2);
+        *row_bytes = (layer == 0 ? 96 : 64) * 2;
+    } else {        // fp32 pre-activation outputs (the reference's ans_convs[layer - 3]); the last one is padded to 16 floats per row
+        *off = layer == 3 ? L.ans0 : (layer == 4 ? L.ans1 : (layer == 5 ? L.ans2 : L.ans3));
+        *row_bytes = (layer == 3 ? 96 : (layer == 6 ? 16 : 64)) * 4;
+    }
     return NF_OK;
 }
 

@@ -225,6 +225,7 @@ class ParticleNet(nn.Module):
         a = self._args(pos, vel, box, box_feats, outs, ws, debug=debug)
         check(lib().nf_transition_step(C.byref(a), stream_ptr()), "nf_transition_step")
         self._post_overflow()
+        self._last_ws = (ws, pos.shape[0], box.shape[0])
         self.num_fluid_neighbors, self.pos_correction = outs[2], outs[3]
         self._keep = (pos, vel, box, box_feats)
         if train:
@@ -235,6 +236,23 @@ class ParticleNet(nn.Module):
         return outs[0], outs[1], outs[2]
 
     step = forward      # BASELINE.json's wording: TransModel.step
+
+    @property
+    def ans_convs(self):
+        """models/transmodel.py:122-131: the pre-activation outputs of the four layers of the LAST step, fp32
+        `[(N,96), (N,64), (N,64), (N,3)]` (row i = particle i).  Read-only views into the step's workspace: valid until the
+        next `forward` of this module (a training forward's views stay valid while its graph is alive)."""
+        last = getattr(self, "_last_ws", None)
+        if last is None:
+            raise NFError("ans_convs: no step has run yet")
+        ws, n, m = last
+        out = []
+        for layer, width in ((3, 96), (4, 64), (5, 64), (6, 3)):
+            off, rb = C.c_size_t(), C.c_size_t()
+            check(lib().nf_transition_layer_buffer(n, m, layer, C.byref(off), C.byref(rb)), "nf_transition_layer_buffer")
+            rows = ws[off.value: off.value + n * rb.value].view(torch.float32).view(n, rb.value // 4)
+            out.append(rows[:, :width])
+        return out
 
 
 class _TransitionFunction(torch.autograd.Function):

@@ -61,6 +61,11 @@ def test_teacher_forced_step_vs_oracle_with_moving_particles(dev):
     assert torch.equal(nn.cpu(), rn)
     assert rel_l2(net.pos_correction.cpu(), dbg["feats"][-1] / 128) < CORR_TOL
     assert rel_l2(p.cpu(), rp) < 1e-5 and rel_l2(v.cpu(), rv) < 2e-3
+    # the reference's per-layer pre-activation outputs (models/transmodel.py:122-131 `ans_convs`)
+    convs = net.ans_convs
+    assert [tuple(t.shape) for t in convs] == [(pos.shape[0], 96), (pos.shape[0], 64), (pos.shape[0], 64), (pos.shape[0], 3)]
+    for li, (got, ref) in enumerate(zip(convs, dbg["feats"])):
+        assert rel_l2(got.cpu(), ref) < CORR_TOL, (li, rel_l2(got.cpu(), ref))
     # bf16 operands: same path, looser numerics
     netb = make_net(sd, dev, operand_dtype="bf16")
     pb, vb, nnb = netb(pos.to(dev), vel.to(dev), box.to(dev), box_n.to(dev))
