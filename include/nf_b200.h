@@ -353,6 +353,16 @@ NF_API int nf_comm_unique_id(void* id_out_host);
 NF_API int nf_comm_init(const void* id_host, int rank, int world);
 NF_API int nf_comm_finalize(void);
 NF_API int nf_comm_info(int* rank_host, int* world_host);
+/* Peer-memory exchange.  COLLECTIVE (every rank calls it, each with its own buffer of the same size; synchronises the device):
+ * maps every rank's buffer into every other rank through CUDA IPC.  Afterwards an nf_allgather_rows on a range inside the
+ * registered buffer -- and the four exchanges of the sharded nf_transition_step when its workspace is the registered buffer --
+ * is one kernel that stores this rank's rows into every peer's copy over NVLink and raises an epoch flag there, plus a one-warp
+ * kernel that waits for the peers' flags: no NCCL call on the data path.  The buffer must come from a plain cudaMalloc
+ * allocation (PyTorch's default caching allocator qualifies); NF_E_UNSUPPORTED otherwise -- then every rank stays on NCCL.
+ * Registering again replaces the previous buffer; buf = NULL unregisters.  nf_comm_exchange_timeouts: how many waits gave up
+ * after ~4 s because a peer never arrived (0 in a healthy run; results are undefined otherwise). */
+NF_API int nf_comm_register_buffer(void* buf, size_t bytes);
+NF_API int nf_comm_exchange_timeouts(unsigned int* count_host);
 NF_API int nf_allgather_rows(void* buf, size_t bytes_per_rank, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

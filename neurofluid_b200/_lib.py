@@ -36,6 +36,7 @@ class RenderArgs(C.Structure):
 
 NF_RENDER_SAVE_NEIGHBORS = 1
 NF_PHASE_SHARDED = -2
+NF_E_UNSUPPORTED = -4
 NF_COMM_ID_BYTES = 128
 
 
@@ -126,6 +127,8 @@ SIGNATURES = {
     "nf_comm_init": (C.c_int, [_vp, C.c_int, C.c_int]),
     "nf_comm_finalize": (C.c_int, []),
     "nf_comm_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "nf_comm_register_buffer": (C.c_int, [_vp, C.c_size_t]),
+    "nf_comm_exchange_timeouts": (C.c_int, [C.POINTER(C.c_uint)]),
     "nf_allgather_rows": (C.c_int, [_vp, _sz, _vp]),
     "nf_cconv_packed_weights_bytes": (_sz, [C.c_int, C.c_int]),
     "nf_cconv_pack_weights": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),

@@ -534,6 +534,9 @@ struct ConvArgs {
     const float4* order;                   // NULL, or the fluid grid's cell-sorted copy (.w = particle index): tile row t of the
                                            // launch is particle order[begin + t] -- a tile then holds 128 spatial neighbours whose
                                            // neighbour rows overlap (~300 distinct rows per tile: the gathers hit L1, not L2)
+    int tile_rows;                         // 0 / 128: full tiles.  16..64: a CTA takes only that many rows, spread over all 16 worker
+                                           // warps (row = r * 16 + warp): a rank of the sharded step has ~3,700 rows = 30 full tiles
+                                           // on 148 SMs, and a CTA's time is set by the rows per WARP, not by the CTAs in flight
 };
 
 template <int CIN, int COUT_PAD>
@@ -566,7 +569,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_cconv_tc(const ConvArgs a) 
     using C = ConvCfg<CIN, COUT_PAD>;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row0 = a.begin + blockIdx.x * 128;
+    const int tile_rows = (a.tile_rows > 0 && a.tile_rows < 128) ? a.tile_rows : 128;
+    const bool spread = tile_rows < 128;
+    const int row0 = a.begin + blockIdx.x * tile_rows;
     const uint32_t s_base = smem_u32(smem);
     const uint32_t s_a = s_base + C::SM_A, s_w = s_base + C::SM_W, s_bar = s_base + C::SM_BAR;
     float* sbias = reinterpret_cast<float*>(smem + C::SM_BIAS);
@@ -629,11 +634,14 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_cconv_tc(const ConvArgs a) 
         // row starts of this warp's 8 slab lists: smem [r][32] u16 (17 used)
         unsigned short* offs = reinterpret_cast<unsigned short*>(smem + C::SM_OFFS) + warp * ROWS_PER_WARP * 32;
         int* rowmap = reinterpret_cast<int*>(smem + C::SM_ROWMAP);      // tile row -> particle index (or -1)
+        // tile row of this warp's r-th particle: consecutive rows (full tiles), or rows r * 16 + warp (short tiles)
+        auto tile_row = [&](int r) { return spread ? r * WORKER_WARPS + warp : rbase + r; };
         for (int r = 0; r < ROWS_PER_WARP; ++r) {
-            const int tpos = row0 + rbase + r;
+            const int rl = tile_row(r);
+            const int tpos = row0 + rl;
             int row = -1;
-            if (tpos < a.end) row = a.order ? __float_as_int(__ldg(&a.order[tpos].w)) : tpos;
-            if (lane == 0) rowmap[rbase + r] = row;
+            if (rl < tile_rows && tpos < a.end) row = a.order ? __float_as_int(__ldg(&a.order[tpos].w)) : tpos;
+            if (lane == 0) rowmap[rl] = row;
             offs[r * 32 + lane] = (row >= 0 && lane < 17) ? __ldg(a.slab_off + (size_t)row * SLABOFF + lane) : (unsigned short)0;
         }
         __syncwarp();
@@ -672,7 +680,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) k_cconv_tc(const ConvArgs a) 
 #pragma unroll 1
             for (int R = 0; R < ROWS_PER_WARP / NG; ++R) {
                 const int r = R * NG + gq;
-                const int rl = rbase + r, row = rowmap[rl];
+                const int rl = tile_row(r), row = rowmap[rl];
+                if (spread && R > 0 && !__any_sync(NF_FULL, row >= 0)) continue;     // short tile: nothing in this iteration
                 float acc[4][CPL];
 #pragma unroll
                 for (int x = 0; x < 4; ++x)
@@ -982,7 +991,8 @@ template <int CIN, int COUT_PAD>
 static int launch_conv(const ConvArgs& a, int dtype, cudaStream_t st) {
     using C = ConvCfg<CIN, COUT_PAD>;
     if (a.end <= a.begin) return NF_OK;
-    const int grid = (a.end - a.begin + 127) / 128;
+    const int tr = (a.tile_rows > 0 && a.tile_rows < 128) ? a.tile_rows : 128;
+    const int grid = (a.end - a.begin + tr - 1) / tr;
     // the attribute is per device, not per process: set it on every launch instead of caching a flag
     if (dtype == NF_DTYPE_BF16) {
         NF_CUDA_OK(cudaFuncSetAttribute(k_cconv_tc<CIN, COUT_PAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SM_TOTAL));
@@ -1930,7 +1940,7 @@ extern "C" int nf_cconv_forward(const nf_cconv_args* a, void* stream_) {
         c.slab_off = (const unsigned short*)(b + L.slab_off);
         c.x_in = b + L.x16; c.w_packed = (const uint8_t*)a->weights; c.residual = nullptr; c.ld_res = 0;
         c.ans = a->out; c.x_out = nullptr; c.n = a->n_in; c.begin = 0; c.end = a->n_out; c.cout = 64; c.dense = 0;
-        c.mask_src = nullptr; c.ld_mask = 0; c.relu_out = 1; c.order = nullptr;
+        c.mask_src = nullptr; c.ld_mask = 0; c.relu_out = 1; c.order = nullptr; c.tile_rows = 0;
         return a->cin == 96 ? launch_conv<96, 64>(c, a->dtype, st) : launch_conv<64, 64>(c, a->dtype, st);
     }
     const size_t kb = (size_t)NCELL * a->cin * a->cout * 4;
@@ -2038,7 +2048,7 @@ extern "C" int nf_transition_backward(const nf_transition_bwd_args* b, void* str
     if ((rc = launch_dense_wgrad(g_ans2, 64, 64, x1, 64, xkind, 0, N, dP /*unused: cin = 0*/, dP + PO.off[11], dP + PO.off[13], st)) != NF_OK) return rc;
     ConvArgs c;
     c.slab_j = wg.slab_j; c.slab_w = wg.slab_w; c.slab_off = wg.slab_off; c.n = N; c.begin = 0; c.end = N; c.dense = 1; c.relu_out = 0;
-    c.order = order;
+    c.order = order; c.tile_rows = 0;
     c.x_in = g_ans2_h; c.w_packed = wb + BL.l2; c.residual = g_ans2; c.ld_res = 64; c.ans = g_ans1; c.x_out = g_ans1_h; c.cout = 64;
     c.mask_src = ans1; c.ld_mask = 64;
     if ((rc = launch_conv<64, 64>(c, NF_DTYPE_BF16, st)) != NF_OK) return rc;
@@ -2130,6 +2140,13 @@ extern "C" int nf_transition_step(const nf_transition_args* a, void* stream_) {
     const float4* order = a->phase == -1 ? grid_view(b + L.grid_f, N).sorted : nullptr;
     c.slab_j = slab_j; c.slab_w = slab_w; c.slab_off = slab_off; c.n = N; c.begin = begin; c.end = end; c.dense = 1;
     c.mask_src = nullptr; c.ld_mask = 0; c.relu_out = 1; c.order = order;
+    c.tile_rows = 128;
+    if (a->phase != -1)       // a shard: the smallest tile (>= 16 rows) that still fits one wave of CTAs
+        while (c.tile_rows > 16 && (nshard + c.tile_rows / 2 - 1) / (c.tile_rows / 2) <= num_sms()) c.tile_rows /= 2;
+    if (sharded && world > 1) {      // peers may store into this workspace from here on (peer-memory exchange, nf_comm.cu)
+        const int rc = comm::enter(st);
+        if (rc != NF_OK) return rc;
+    }
     for (int ph = ph_lo; ph <= ph_hi; ++ph) {
     if (ph == 0) {
         NF_CUDA_OK(cudaMemsetAsync(flags, 0, 256, st));

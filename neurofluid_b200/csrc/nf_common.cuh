@@ -52,6 +52,7 @@ namespace comm {
 int world();
 int rank();
 int allgather_inplace(void* buf, size_t bytes_per_rank, cudaStream_t st);
+int enter(cudaStream_t st);      // start of a sequence of exchanges on the registered buffer (peer-memory path; no-op otherwise)
 }
 
 // ------------------------------------------------------------------------------------------------

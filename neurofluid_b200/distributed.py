@@ -111,15 +111,52 @@ def init_comm(group=None) -> None:
     _comm_ready["key"] = key
 
 
-def transition_step_sharded(net, pos, vel, box, box_feats, group=None):
+class _StepGraph:
+    """One captured sharded step: static inputs / outputs, the argument block and the CUDA graph that replays the library call."""
+
+    def __init__(self, key, pos_in, vel_in, outs, keep, graph):
+        self.key, self.pos_in, self.vel_in, self.outs, self.keep, self.graph = key, pos_in, vel_in, outs, keep, graph
+
+
+def _capture_step(net, key, p, v, b, bf, ws):
+    """Capture nf_transition_step(phase = NF_PHASE_SHARDED) into a CUDA graph (the library only launches on the stream it is
+    given: kernels, a memset, and either ncclAllGather or the peer-memory exchange kernels, whose epochs live in device
+    memory -- all of it capturable)."""
+    import ctypes as C
+    from . import _lib
+    dev = p.device
+    pos_in, vel_in = p.clone(), v.clone()
+    n = p.shape[0]
+    outs = (torch.empty((n, 3), device=dev), torch.empty((n, 3), device=dev), torch.empty((n,), device=dev),
+            torch.empty((n, 3), device=dev))
+    a = net._args(pos_in, vel_in, b, bf, outs, ws, phase=_lib.NF_PHASE_SHARDED)
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):           # warm-up outside the capture (lazy initialisation inside CUDA / NCCL)
+        _lib.check(_lib.lib().nf_transition_step(C.byref(a), _lib.stream_ptr()), "nf_transition_step")
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize(dev)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        _lib.check(_lib.lib().nf_transition_step(C.byref(a), _lib.stream_ptr()), "nf_transition_step")
+    return _StepGraph(key, pos_in, vel_in, outs, (a, b, bf, ws, net._packed_weights(), net._box_grid(b)), g)
+
+
+def transition_step_sharded(net, pos, vel, box, box_feats, group=None, graph=False):
     """`ParticleNet.forward` with the particles block-sharded over the ranks of `group`.
 
     Every rank holds the full state (pos, vel) and ends up with the full result.  ONE call into the library
     (nf_transition_step, phase NF_PHASE_SHARDED): each rank computes its own rows of every phase, and the library
     all-gathers, in place on the compute stream and with no host work in between, the fp16 activation rows after layers
     0-2 and the packed (pos, vel, neighbour count, delta) rows at the end -- the "position all-gather per step" of
-    BASELINE.json's north_star.  4 NCCL calls per step; bit-identical to the single-GPU step."""
+    BASELINE.json's north_star.  The step's workspace is registered for the library's peer-memory exchange
+    (nf_comm_register_buffer, once per workspace): each of the four exchanges is then a kernel that stores this rank's rows
+    into every peer's workspace over NVLink plus a flag wait, not an NCCL call (NF_B200_NO_PEER=1, or a buffer CUDA IPC
+    cannot export, keeps ncclAllGather).  With `graph=True` the library call is captured into a CUDA graph once per (scene size,
+    container, weights, workspace) and replayed (measured: no faster -- at 8 GPUs a rank's 0.5 ms step is bound by its own
+    kernels, not by the host or the exchanges -- so it is off by default).  Bit-identical to the single-GPU step either way."""
     import ctypes as C
+    import os
     from . import _lib
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
@@ -127,8 +164,28 @@ def transition_step_sharded(net, pos, vel, box, box_feats, group=None):
     init_comm(group)
     net._poll_overflow()
     p, v, b, bf, outs, ws = net._prepare(pos, vel, box, box_feats, None)
-    a = net._args(p, v, b, bf, outs, ws, phase=_lib.NF_PHASE_SHARDED)
-    _lib.check(_lib.lib().nf_transition_step(C.byref(a), _lib.stream_ptr()), "nf_transition_step")
+    reg = (ws.data_ptr(), ws.numel())
+    if _comm_ready.get("registered") != reg:          # collective: every rank reaches this at the same step
+        peer = os.environ.get("NF_B200_NO_PEER", "0") != "1"
+        rc = _lib.lib().nf_comm_register_buffer(_lib.ptr(ws) if peer else None, ws.numel() if peer else 0)
+        if rc != _lib.NF_E_UNSUPPORTED:
+            _lib.check(rc, "nf_comm_register_buffer")
+        _comm_ready["registered"] = reg
+        _comm_ready["peer_memory"] = peer and rc == 0
+        net._step_graph = None
+    if graph and os.environ.get("NF_B200_NO_GRAPH", "0") != "1":
+        key = (tuple(p.shape), b.data_ptr(), b._version, bf.data_ptr(), bf._version, net._packed_weights().data_ptr(), ws.data_ptr(),
+               net.operand_dtype, float(net.time_step), tuple(net._gravity_host))
+        sg = getattr(net, "_step_graph", None)
+        if sg is None or sg.key != key:
+            sg = net._step_graph = _capture_step(net, key, p, v, b, bf, ws)
+        sg.pos_in.copy_(p)
+        sg.vel_in.copy_(v)
+        sg.graph.replay()
+        outs = tuple(t.clone() for t in sg.outs)       # the static outputs are overwritten by the next replay
+    else:
+        a = net._args(p, v, b, bf, outs, ws, phase=_lib.NF_PHASE_SHARDED)
+        _lib.check(_lib.lib().nf_transition_step(C.byref(a), _lib.stream_ptr()), "nf_transition_step")
     net._post_overflow()
     net.num_fluid_neighbors, net.pos_correction = outs[2], outs[3]
     net._keep = (p, v, b, bf)
