@@ -209,7 +209,7 @@ def bench_transition(dev, world, rank, args, timed, pk):
     flops = 2 * 692544 * val / 1e12                             # 692,544 MAC per particle-step
     return {"metric": "particle_steps_per_sec_rollout_30k", "value": val, "unit": "particle-steps/s", "ms_per_step": ms / steps,
             "steps": steps, "n_particles": n, "n_box": box.shape[0], "scaling": "strong",
-            "parallelism": f"particle blocks over {world} GPU(s), 4 NCCL all-gathers per step" if world > 1 else "single GPU",
+            "parallelism": f"particle blocks over {world} GPU(s), 4 in-place exchanges per step (peer-memory stores over NVLink, or ncclAllGather)" if world > 1 else "single GPU",
             "roofline": {"bound": "tensor", "achieved": flops, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": flops / pk["tensor"],
                          "note": "41 GFLOP per step: launch/latency-bound by construction (SURVEY 8d)"}}
 
