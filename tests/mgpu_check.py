@@ -43,6 +43,15 @@ p1, v1, n1 = tn(pos, vel, box, box_n)
 p1, v1, n1 = p1.clone(), v1.clone(), n1.clone()
 p2, v2, n2 = transition_step_sharded(tn, pos, vel, box, box_n)
 ok_t = torch.equal(p1, p2) and torch.equal(v1, v2) and torch.equal(n1, n2)
+# the same step through the other exchange / launch variants: ncclAllGather instead of the peer-memory exchange, CUDA graph replay
+from neurofluid_b200 import distributed as nbd  # noqa: E402
+for no_peer, graph in (("1", False), ("1", True), ("0", True), ("0", False)):
+    os.environ["NF_B200_NO_PEER"] = no_peer
+    nbd._comm_ready.pop("registered", None)          # re-register (collective: every rank does this here)
+    for _ in range(2):                                # the second call of a graph variant is a pure replay
+        p3, v3, n3 = transition_step_sharded(tn, pos, vel, box, box_n, graph=graph)
+    ok_t = ok_t and torch.equal(p1, p3) and torch.equal(v1, v3) and torch.equal(n1, n3)
+os.environ["NF_B200_NO_PEER"] = "0"
 # eval_e2e-shaped rollout: sharded rays (+ sharded or replicated transition) == one process doing everything
 from neurofluid_b200 import ops, pipeline  # noqa: E402
 cams = [(cw, focal)]

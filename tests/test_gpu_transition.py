@@ -225,3 +225,32 @@ def test_continuous_conv_operator_vs_oracle(dev, cin, cout, case):
     with pytest.raises(_lib.NFError):
         ops.ContinuousConv(kernel_size=[4, 4, 4], interpolation="linear", coordinate_mapping="ball_to_cube_volume_preserving",
                            normalize=False, in_channels=200, filters=200)
+
+
+@pytest.mark.parametrize("n_lat", [8, 17, 24])
+def test_phase_by_phase_step_equals_whole_step(dev, n_lat):
+    """The sharded execution runs nf_transition_step phase by phase on row blocks, in array order and -- for small blocks --
+    with short conv tiles spread over all worker warps (16 / 64 / 128 rows per CTA at these three sizes); the whole-step call
+    walks the particles in cell order with full tiles.  Every particle's sums run in pair-list order either way: the results
+    must agree bit for bit, for one block and for two."""
+    import ctypes as C
+    sd = scenes.init_particle_state(2, last_layer_scale=1.0)
+    net = make_net(sd, dev)
+    rng = np.random.RandomState(n_lat)
+    pos = torch.from_numpy(scenes.lattice_particles(n_lat, 2, jitter=0.01, center=(0.0, 0.0, -0.4))).to(dev)
+    vel = torch.from_numpy(rng.normal(0, 0.3, tuple(pos.shape)).astype(np.float32)).to(dev)
+    bp, bn = scenes.box_points(0.06)
+    box, box_n = torch.from_numpy(bp).to(dev), torch.from_numpy(bn).to(dev)
+    p_ref, v_ref, n_ref = (t.clone() for t in net(pos, vel, box, box_n))
+    d_ref = net.pos_correction.clone()
+    N = pos.shape[0]
+    for blocks in ([(0, N)], [(0, N // 3), (N // 3, N)]):
+        p, v, b, bf, outs, ws = net._prepare(pos, vel, box, box_n, None)
+        for o in outs:
+            o.fill_(float("nan"))
+        for ph in range(_lib.lib().nf_transition_num_phases()):
+            for blk in blocks:      # all blocks of a phase before the next phase: what the ranks of a sharded step do
+                a = net._args(p, v, b, bf, outs, ws, phase=ph, shard=blk)
+                _lib.check(_lib.lib().nf_transition_step(C.byref(a), _lib.stream_ptr()), "nf_transition_step")
+        assert torch.equal(outs[0], p_ref) and torch.equal(outs[1], v_ref) and torch.equal(outs[2], n_ref)
+        assert torch.equal(outs[3], d_ref)
