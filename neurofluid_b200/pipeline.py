@@ -22,9 +22,12 @@ from .distributed import gather_image, shard_rows
 
 # ------------------------------------------------------------------------------------------------ render_image
 def render_image(renderer, particle_pos, N_ray, ro, rays, focal_length, cw, ray_chunk=None, iseval=False):
-    """trainer/basetrainer.py:264-309.  `ray_chunk` defaults to the reference's cfg.ray.ray_chunk; any chunk size
-    gives bit-identical results (rays are independent), so callers may pass the whole image."""
-    chunk = int(ray_chunk or renderer.cfg.ray.ray_chunk)
+    """trainer/basetrainer.py:264-309.  The reference walks the image in cfg.ray.ray_chunk = 1024-ray pieces because its
+    O(rays x particles) `repeat` does not fit otherwise; here any chunk size gives bit-identical results (rays are
+    independent; tests/test_gpu_pipeline.py), so the default is ONE call for the whole image (the renderer cuts it into
+    `max_rays_per_launch` launches itself: 5 launches per 800 x 800 image instead of 625 calls).  Pass `ray_chunk` to get the
+    reference's loop."""
+    chunk = int(ray_chunk) if ray_chunk else max(int(N_ray), 1)
     fine = renderer.cfg.ray.N_importance > 0
     acc = {k: [] for k in ("pred_rgbs_0", "num_nn_0", "mask_0", "pred_rgbs_1", "num_nn_1", "mask_1")}
     for ray_idx in range(0, N_ray, chunk):

@@ -72,13 +72,15 @@ def test_render_image_chunk_loop_is_bitwise_the_forward(dev):
     net = net.to(dev)
     p, ro, rays, cw = c["particles"].to(dev), c["ro"].to(dev), c["rays"].to(dev), c["cw"].to(dev)
     whole = net(p, ro, rays, 1.0, cw)
-    ret = pipeline.render_image(net, p, rays.shape[0], ro, rays, 1.0, cw, iseval=True)      # cfg.ray.ray_chunk = 1024
+    ret = pipeline.render_image(net, p, rays.shape[0], ro, rays, 1.0, cw, ray_chunk=net.cfg.ray.ray_chunk, iseval=True)      # the reference's loop: 1024-ray chunks
     assert set(ret) == {"pred_rgbs_0", "num_nn_0", "mask_0", "pred_rgbs_1", "num_nn_1", "mask_1"}
     assert torch.equal(ret["pred_rgbs_1"], whole["rgb1"]) and torch.equal(ret["pred_rgbs_0"], whole["rgb0"])
     assert torch.equal(ret["num_nn_1"], whole["num_nn_1"].view(-1)) and torch.equal(ret["mask_0"], whole["mask_0"])
     lean = pipeline.render_image(net, p, rays.shape[0], ro, rays, 1.0, cw, ray_chunk=300)
     assert set(lean) == {"pred_rgbs_0", "num_nn_0", "pred_rgbs_1", "num_nn_1"}
     assert torch.equal(lean["pred_rgbs_1"], whole["rgb1"])
+    one = pipeline.render_image(net, p, rays.shape[0], ro, rays, 1.0, cw)        # default: the whole image in one call
+    assert torch.equal(one["pred_rgbs_1"], whole["rgb1"]) and torch.equal(one["num_nn_0"], whole["num_nn_0"].view(-1))
 
 
 def test_rollout_and_render_is_the_eval_loop(dev):
