@@ -365,6 +365,8 @@ def mgpu_parity(dev, world, rank):
     p1, v1, n1 = (t.clone() for t in tn(pos, torch.zeros_like(pos), box, box_n))
     p2, v2, n2 = transition_step_sharded(tn, pos, torch.zeros_like(pos), box, box_n)
     ok = ok and torch.equal(p1, p2) and torch.equal(v1, v2) and torch.equal(n1, n2)
+    from neurofluid_b200.distributed import exchange_timeouts
+    ok = ok and exchange_timeouts() == 0          # no peer-memory wait of this whole bench run gave up
     t = torch.tensor([int(ok)], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     return bool(t.item())

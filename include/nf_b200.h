@@ -360,7 +360,7 @@ NF_API int nf_comm_info(int* rank_host, int* world_host);
  * kernel that waits for the peers' flags: no NCCL call on the data path.  The buffer must come from a plain cudaMalloc
  * allocation (PyTorch's default caching allocator qualifies); NF_E_UNSUPPORTED otherwise -- then every rank stays on NCCL.
  * Registering again replaces the previous buffer; buf = NULL unregisters.  nf_comm_exchange_timeouts: how many waits gave up
- * after ~4 s because a peer never arrived (0 in a healthy run; results are undefined otherwise). */
+ * after ~100 s because a peer never arrived (0 in a healthy run; results are undefined otherwise). */
 NF_API int nf_comm_register_buffer(void* buf, size_t bytes);
 NF_API int nf_comm_exchange_timeouts(unsigned int* count_host);
 NF_API int nf_allgather_rows(void* buf, size_t bytes_per_rank, void* stream);

@@ -144,7 +144,8 @@ __global__ void k_signal_enter(Peers P, int rank, int world, unsigned long long*
     if (p < world && p != rank) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(P.flag[p] + 24 + rank), "l"(epoch) : "memory");
 }
 
-// one lane per peer: wait until its flag in THIS rank's memory has reached the epoch (bounded: a lost peer must not hang the GPU)
+// one lane per peer: wait until its flag in THIS rank's memory has reached the epoch (bounded: a lost peer must not hang the GPU
+// for ever; nf_comm_exchange_timeouts reports a wait that gave up)
 __global__ void k_wait_peers(const unsigned long long* flags, int rank, int world, const unsigned long long* my_epoch, unsigned int* timeouts) {
     const int p = threadIdx.x;
     if (p >= world || p == rank) return;
@@ -153,7 +154,8 @@ __global__ void k_wait_peers(const unsigned long long* flags, int rank, int worl
     unsigned long long v;
     do {
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + p) : "memory");
-        if (v < epoch && clock64() - t0 > 8000000000ll) { atomicAdd(timeouts, 1u); break; }     // ~4 s
+        if (v < epoch && clock64() - t0 > 200000000000ll) { atomicAdd(timeouts, 1u); break; }     // ~100 s: a peer that is busy
+                                                                                                  // elsewhere (host work between steps) is waited for
     } while (v < epoch);
 }
 

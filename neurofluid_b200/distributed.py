@@ -89,6 +89,16 @@ def allgather_rows(buf: torch.Tensor, n: int, group=None) -> None:
 _comm_ready = {}
 
 
+def exchange_timeouts() -> int:
+    """How many peer-memory waits gave up (~100 s) because a peer never raised its flag: 0 in a healthy run; results are
+    undefined otherwise.  Synchronises (one 4-byte copy)."""
+    import ctypes as C
+    from . import _lib
+    cnt = C.c_uint(0)
+    _lib.check(_lib.lib().nf_comm_exchange_timeouts(C.byref(cnt)), "nf_comm_exchange_timeouts")
+    return int(cnt.value)
+
+
 def init_comm(group=None) -> None:
     """Create the library's NCCL communicator for the ranks of `group` (idempotent): rank 0 makes the id
     (nf_comm_unique_id), torch.distributed ships its 128 bytes (plumbing), every rank calls nf_comm_init."""

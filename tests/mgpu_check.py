@@ -52,6 +52,7 @@ for no_peer, graph in (("1", False), ("1", True), ("0", True), ("0", False)):
         p3, v3, n3 = transition_step_sharded(tn, pos, vel, box, box_n, graph=graph)
     ok_t = ok_t and torch.equal(p1, p3) and torch.equal(v1, v3) and torch.equal(n1, n3)
 os.environ["NF_B200_NO_PEER"] = "0"
+ok_t = ok_t and nbd.exchange_timeouts() == 0
 # eval_e2e-shaped rollout: sharded rays (+ sharded or replicated transition) == one process doing everything
 from neurofluid_b200 import ops, pipeline  # noqa: E402
 cams = [(cw, focal)]
