@@ -1,6 +1,6 @@
 """Profiling workload (not a pytest): N forwards of BASELINE config[1] (800x800, 64+128, 19,683 particles) and,
 optionally, a few transition steps; prints per-chunk row counts so an ncu capture of launch i can be matched to
-its rows.   python tests/gpu_profile_render.py [n_forwards] [n_transition_steps]"""
+its rows.   python tests/gpu_profile_render.py [n_forwards] [n_transition_steps]     (NF_PROFILE_LATTICE=37: config[4]'s 50,653 particles)"""
 import json, os, sys, torch
 torch.set_grad_enabled(False)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
@@ -11,7 +11,7 @@ nfwd = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 ntr = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 H = 800
 rays, focal, cw = scenes.camera_rays(H, H)
-particles = torch.from_numpy(scenes.lattice_particles(27, 0))
+particles = torch.from_numpy(scenes.lattice_particles(int(os.environ.get("NF_PROFILE_LATTICE", "27")), 0))
 net = nb.RenderNet(scenes.render_cfg(), scenes.NEAR, scenes.FAR); net.load_state_dict(scenes.init_render_state(0, 5.0)); net = net.to(dev)
 rays_d, p_d, ro = rays.to(dev), particles.to(dev), cw[:, 3].to(dev)
 for it in range(nfwd):
