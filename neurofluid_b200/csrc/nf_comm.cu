@@ -263,45 +263,69 @@ extern "C" int nf_comm_register_buffer(void* buf, size_t bytes) {
     close_buffer_mappings();
     IpcRecord all[MAX_RANKS];
     int rc;
+    // Every step below is collective: a rank that fails locally still takes part in the exchanges (with bytes = 0 in its
+    // record), so that all ranks see the failure and fall back to NCCL together instead of leaving the others inside a collective.
+    auto all_have = [&](unsigned long long want) {
+        for (int p = 0; p < g_world; ++p)
+            if (all[p].bytes != want) return false;
+        return true;
+    };
     if (!g_flags) {      // first registration: the flag blocks
         NF_CUDA_OK(cudaMalloc((void**)&g_flags, FLAG_BYTES));
         NF_CUDA_OK(cudaMemset(g_flags, 0, FLAG_BYTES));
         IpcRecord mine;
-        if ((rc = ipc_record(g_flags, FLAG_BYTES, &mine)) != NF_OK) return rc;
+        if (ipc_record(g_flags, FLAG_BYTES, &mine) != NF_OK) memset(&mine, 0, sizeof(mine));
         if ((rc = exchange_records(&mine, all)) != NF_OK) return rc;
-        for (int p = 0; p < g_world; ++p) {
+        bool ok = all_have(FLAG_BYTES);
+        for (int p = 0; ok && p < g_world; ++p) {
             if (p == g_rank) { g_peers.flag[p] = (unsigned long long*)g_flags; continue; }
             void* base = nullptr;
-            NF_CUDA_OK(cudaIpcOpenMemHandle(&base, all[p].handle, cudaIpcMemLazyEnablePeerAccess));
+            if (cudaIpcOpenMemHandle(&base, all[p].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                set_error("cudaIpcOpenMemHandle (flag block of rank %d): %s", p, cudaGetErrorString(cudaGetLastError()));
+                ok = false;
+                break;
+            }
             g_opened_flags[p] = base;
             g_peers.flag[p] = (unsigned long long*)((char*)base + all[p].offset);
+        }
+        mine.bytes = ok ? FLAG_BYTES : 0;
+        if ((rc = exchange_records(&mine, all)) != NF_OK) return rc;
+        if (!all_have(FLAG_BYTES)) {
+            const bool mine_ok = ok;
+            close_all_mappings();
+            if (mine_ok) set_error("nf_comm_register_buffer: a rank could not export or map the flag blocks (CUDA IPC)");
+            return NF_E_UNSUPPORTED;
         }
     }
     if (buf == nullptr || bytes == 0) return NF_OK;
     IpcRecord mine;
-    rc = ipc_record(buf, bytes, &mine);
-    // a rank that cannot export its buffer still takes part in the exchange (bytes = 0) so that all ranks fall back together
-    if (rc != NF_OK) { memset(&mine, 0, sizeof(mine)); }
-    int rc2;
-    if ((rc2 = exchange_records(&mine, all)) != NF_OK) return rc2;
-    for (int p = 0; p < g_world; ++p)
-        if (all[p].bytes != bytes) {
-            set_error("nf_comm_register_buffer: rank %d registered %llu bytes, this rank %zu (or a rank could not export its buffer)", p,
-                      all[p].bytes, bytes);
-            return NF_E_UNSUPPORTED;
-        }
-    for (int p = 0; p < g_world; ++p) {
+    if (ipc_record(buf, bytes, &mine) != NF_OK) memset(&mine, 0, sizeof(mine));
+    if ((rc = exchange_records(&mine, all)) != NF_OK) return rc;
+    bool ok = all_have(bytes);
+    if (!ok && mine.bytes == bytes)
+        set_error("nf_comm_register_buffer: the ranks registered different sizes, or a rank could not export its buffer (CUDA IPC)");
+    for (int p = 0; ok && p < g_world; ++p) {
         if (p == g_rank) { g_peers.buf[p] = (char*)buf; continue; }
         void* base = nullptr;
-        NF_CUDA_OK(cudaIpcOpenMemHandle(&base, all[p].handle, cudaIpcMemLazyEnablePeerAccess));
+        if (cudaIpcOpenMemHandle(&base, all[p].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            set_error("cudaIpcOpenMemHandle (buffer of rank %d): %s", p, cudaGetErrorString(cudaGetLastError()));
+            ok = false;
+            break;
+        }
         g_opened_buf[p] = base;
         g_peers.buf[p] = (char*)base + all[p].offset;
     }
+    // nobody pushes into a peer before every rank has finished mapping (the flags of the next exchange are the barrier for the
+    // data, this exchange is the one for the mappings -- and tells everybody whether everybody succeeded)
+    mine.bytes = ok ? bytes : 0;
+    if ((rc = exchange_records(&mine, all)) != NF_OK) return rc;
+    if (!all_have(bytes)) {
+        const bool mine_ok = ok;
+        close_buffer_mappings();
+        if (mine_ok) set_error("nf_comm_register_buffer: a rank could not map a peer's buffer (CUDA IPC)");
+        return NF_E_UNSUPPORTED;
+    }
     g_reg_base = (char*)buf; g_reg_bytes = bytes;
-    // nobody pushes into a peer before every rank has finished mapping (the flags of the next exchange are the barrier
-    // for the data, this one is for the mappings)
-    char dummy = 0; (void)dummy;
-    if ((rc2 = exchange_records(&mine, all)) != NF_OK) return rc2;
     return NF_OK;
 }
 
