@@ -257,7 +257,7 @@ class ParticleNet(nn.Module):
 
 class _TransitionFunction(torch.autograd.Function):
     """Autograd node of one ParticleNet step: forward = nf_transition_step on a workspace of its own, backward =
-    nf_transition_backward (csrc/nf_cconv.cu).  Differentiable inputs: pos, vel and the 18 parameter tensors."""
+    nf_transition_backward (csrc/nf_cconv_bwd.cu).  Differentiable inputs: pos, vel and the 18 parameter tensors."""
 
     @staticmethod
     def forward(ctx, net, static, pos, vel, *params):
