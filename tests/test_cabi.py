@@ -96,3 +96,14 @@ def test_particlenet_state_dict_layout():
     assert L.nf_transition_num_phases() == 5
     assert L.nf_transition_workspace_bytes(1000, 500) > 2 * 1000 * 128 * 48
     assert ctypes.sizeof(_lib.TransitionArgs) % 8 == 0
+
+
+def test_comm_entry_points_are_no_ops_for_one_rank():
+    """Without nf_comm_init the library is a world of one: the collective entry points return at once (no CUDA call)."""
+    L = _lib.lib()
+    r, w = ctypes.c_int(-1), ctypes.c_int(-1)
+    assert L.nf_comm_info(ctypes.byref(r), ctypes.byref(w)) == 0 and (r.value, w.value) == (0, 1)
+    assert L.nf_comm_register_buffer(None, 0) == 0
+    assert L.nf_allgather_rows(None, 0, None) == 0
+    n = ctypes.c_uint(7)
+    assert L.nf_comm_exchange_timeouts(ctypes.byref(n)) == 0 and n.value == 0

@@ -67,3 +67,33 @@ def test_render_image_needs_the_device():
     rays, focal, cw = scenes.camera_rays(8, 8)
     with pytest.raises(NFError):          # CPU tensors: no fallback
         pipeline.render_image(r, torch.zeros(10, 3), rays.shape[0], cw[:, 3], rays, focal, cw)
+
+
+def test_render_image_chunk_loop_with_a_stand_in_renderer():
+    """trainer/basetrainer.py:264-309: the chunk loop itself (host logic): one call for the whole image by default, the
+    reference's ray_chunk loop on request, results concatenated in ray order."""
+    from types import SimpleNamespace
+
+    class Fake:
+        cfg = SimpleNamespace(ray=SimpleNamespace(ray_chunk=1024, N_importance=128))
+
+        def __init__(self):
+            self.calls = []
+
+        def __call__(self, particles, ro, rays, focal, cw):
+            self.calls.append(rays.shape[0])
+            idx = rays[:, 0:1]
+            return {"rgb0": idx.repeat(1, 3), "rgb1": 2 * idx.repeat(1, 3), "num_nn_0": idx.long().view(-1, 1, 1),
+                    "num_nn_1": idx.long().view(-1, 1, 1), "mask_0": idx, "mask_1": idx}
+
+    rays = torch.arange(2500, dtype=torch.float32).view(-1, 1).repeat(1, 6)
+    f = Fake()
+    one = pipeline.render_image(f, None, rays.shape[0], None, rays, 1.0, None, iseval=True)
+    assert f.calls == [2500]
+    f = Fake()
+    ref = pipeline.render_image(f, None, rays.shape[0], None, rays, 1.0, None, ray_chunk=f.cfg.ray.ray_chunk, iseval=True)
+    assert f.calls == [1024, 1024, 452]
+    assert set(one) == set(ref) == {"pred_rgbs_0", "num_nn_0", "mask_0", "pred_rgbs_1", "num_nn_1", "mask_1"}
+    for k in one:
+        assert torch.equal(one[k], ref[k]), k
+    assert torch.equal(one["pred_rgbs_1"][:, 0], 2 * torch.arange(2500, dtype=torch.float32))
